@@ -1,0 +1,369 @@
+"""bbm_b200 - thin Python binding of libbbmcu.so (include/bbmcu.h), the B200 CUDA backbone for bbm's
+batched BSDF eval / sample / pdf / reflectance, linearizers and fitting losses.
+
+Everything here forwards to the C ABI; there is no Python or CPU implementation of the path.  If the
+shared library is missing or no CUDA device is usable the calls raise - nothing falls back.
+
+Arrays are struct-of-arrays: directions / spectra have shape (3, n), xi (2, n), float32, C-contiguous.
+They may be numpy arrays (host memory, staged by the library) or torch tensors (CPU or CUDA).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbbmcu.so")
+
+NONE, DIFFUSE, SPECULAR, ALL = 0, 1, 2, 3
+RADIANCE, IMPORTANCE = 0, 1
+ATTR_DIFFUSE_SCALE, ATTR_DIFFUSE_PARAMETER, ATTR_SPECULAR_SCALE, ATTR_SPECULAR_PARAMETER, ATTR_DEPENDENT, ATTR_ALL = 1, 2, 4, 8, 16, 15
+METRICS = ["nganL2", "lowL2", "bieronL2", "lowLog", "bieronLog", "standardLog"]
+PARAM_VALUE, PARAM_DEFAULT, PARAM_LOWER, PARAM_UPPER = 0, 1, 2, 3
+MERL_BINS = 1458000
+
+
+class BbmError(RuntimeError):
+    """std::runtime_error on the reference side (core/error.h:42-46)"""
+
+
+class BbmInvalidArgument(BbmError, ValueError):
+    """std::invalid_argument on the reference side (core/stringconvert.h:68,517,540,565)"""
+
+
+class Attr(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("width", C.c_int), ("rows", C.c_int), ("flag", C.c_int), ("offset", C.c_int)]
+
+
+class SphericalGrid(C.Structure):
+    """spherical_linearizer constructor arguments (linearizer/spherical_linearizer.h:37-44)"""
+    _fields_ = [("samples_in", C.c_uint32 * 2), ("samples_out", C.c_uint32 * 2),
+                ("start_in", C.c_float * 2), ("end_in", C.c_float * 2),
+                ("start_out", C.c_float * 2), ("end_out", C.c_float * 2)]
+
+    def size(self):
+        return self.samples_in[0] * self.samples_in[1] * self.samples_out[0] * self.samples_out[1]
+
+
+_lib = None
+
+
+def lib():
+    """load libbbmcu.so (built in-tree by `python -m bbm_b200.build`); raises if it is missing"""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BbmError(f"{LIB_PATH} not found: build it with `python -m bbm_b200.build` (there is no fallback path)")
+        L = C.CDLL(LIB_PATH)
+        L.bbmcu_last_error.restype = C.c_char_p
+        L.bbmcu_last_error.argtypes = [C.c_void_p]
+        L.bbmcu_model_name.restype = C.c_char_p
+        L.bbmcu_fit_key.restype = C.c_char_p
+        L.bbmcu_fit_key.argtypes = [C.c_void_p, C.c_int]
+        L.bbmcu_stream.restype = C.c_void_p
+        L.bbmcu_stream.argtypes = [C.c_void_p]
+        L.bbmcu_launch_count.restype = C.c_uint64
+        L.bbmcu_launch_count.argtypes = [C.c_void_p]
+        L.bbmcu_loss_samples.restype = C.c_uint64
+        L.bbmcu_loss_samples.argtypes = [C.c_void_p]
+        for name in ("bbmcu_destroy", "bbmcu_bsdf_free", "bbmcu_loss_free", "bbmcu_fit_free"):
+            getattr(L, name).restype = None
+            getattr(L, name).argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, ctx=None):
+    if rc == 0:
+        return
+    msg = lib().bbmcu_last_error(ctx).decode(errors="replace")
+    raise (BbmInvalidArgument if rc == 1 else BbmError)(msg)
+
+
+def _ptr(a):
+    """device or host address of a torch tensor / numpy array"""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise BbmInvalidArgument("tensor must be contiguous")
+        return C.c_void_p(a.data_ptr())
+    a = np.asarray(a)
+    if not a.flags["C_CONTIGUOUS"]:
+        raise BbmInvalidArgument("array must be C-contiguous")
+    return C.c_void_p(a.ctypes.data)
+
+
+def _like(a, shape, dtype=np.float32):
+    """output buffer living where `a` lives"""
+    if hasattr(a, "data_ptr"):
+        import torch
+        td = {np.float32: torch.float32, np.int32: torch.int32, np.uint32: torch.int32}[dtype]
+        return torch.empty(shape, dtype=td, device=a.device)
+    return np.empty(shape, dtype)
+
+
+def _n(a, rows):
+    shape = tuple(a.shape)
+    if len(shape) != 2 or shape[0] != rows:
+        raise BbmInvalidArgument(f"expected a ({rows}, n) struct-of-arrays buffer, got {shape}")
+    if str(a.dtype) not in ("float32", "torch.float32"):
+        raise BbmInvalidArgument(f"expected float32, got {a.dtype}")
+    return shape[1]
+
+
+def model_names():
+    L = lib()
+    return [L.bbmcu_model_name(i).decode() for i in range(L.bbmcu_model_count())]
+
+
+def model_layout(name):
+    """[(attribute name, width, rows, flag, offset)] in reflection order (util/reflection.h:141-148)"""
+    L = lib()
+    mid = C.c_int(0)
+    _check(L.bbmcu_model_lookup(name.encode(), C.byref(mid)))
+    n = C.c_int(0)
+    _check(L.bbmcu_model_layout(mid, None, C.byref(n)))
+    arr = (Attr * n.value)()
+    _check(L.bbmcu_model_layout(mid, arr, C.byref(n)))
+    return [(a.name.decode(), a.width, a.rows, a.flag, a.offset) for a in arr]
+
+
+def spherical_grid(samples_in, samples_out, start_in=None, end_in=None, start_out=None, end_out=None):
+    g = SphericalGrid()
+    lib().bbmcu_spherical_grid_default(C.byref(g), samples_in[0], samples_in[1], samples_out[0], samples_out[1])
+    for name, v in (("start_in", start_in), ("end_in", end_in), ("start_out", start_out), ("end_out", end_out)):
+        if v is not None:
+            getattr(g, name)[:] = [float(np.float32(x)) for x in v]
+    return g
+
+
+class Bsdf:
+    """bbm::bsdf_ptr (include/bbm/bsdf_ptr.h:20-165): import from / export to the BSDF string grammar and
+    the parameter enumeration of include/bbm/bsdf_enumerate.h:102-237 (forward order)."""
+
+    def __init__(self, string, _handle=None):
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            _check(lib().bbmcu_bsdf_from_string(None, string.encode(), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.bbmcu_bsdf_free(self._h)
+            self._h = None
+
+    def to_string(self):
+        buf = C.create_string_buffer(1 << 14)
+        _check(lib().bbmcu_bsdf_to_string(self._h, buf, C.c_size_t(len(buf))))
+        return buf.value.decode()
+
+    __str__ = to_string
+
+    def _vec(self, which, flags):
+        n = C.c_int(0)
+        _check(lib().bbmcu_bsdf_get_params(self._h, which, flags, None, C.byref(n)))
+        v = np.empty(n.value, np.float64)
+        _check(lib().bbmcu_bsdf_get_params(self._h, which, flags, v.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return v
+
+    def parameter_values(self, flags=ATTR_ALL):
+        return self._vec(PARAM_VALUE, flags)
+
+    def parameter_default_values(self, flags=ATTR_ALL):
+        return self._vec(PARAM_DEFAULT, flags)
+
+    def parameter_lower_bound(self, flags=ATTR_ALL):
+        return self._vec(PARAM_LOWER, flags)
+
+    def parameter_upper_bound(self, flags=ATTR_ALL):
+        return self._vec(PARAM_UPPER, flags)
+
+    def set_parameter_values(self, values, flags=ATTR_ALL):
+        v = np.ascontiguousarray(values, np.float64)
+        _check(lib().bbmcu_bsdf_set_params(self._h, flags, v.ctypes.data_as(C.c_void_p), len(v)))
+
+
+class Context:
+    """one CUDA device + stream (bbmcu_ctx)"""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().bbmcu_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.bbmcu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def synchronize(self):
+        _check(lib().bbmcu_synchronize(self._h), self._h)
+
+    @property
+    def stream(self):
+        return lib().bbmcu_stream(self._h)
+
+    @property
+    def launches(self):
+        return int(lib().bbmcu_launch_count(self._h))
+
+    # ---- the BSDF concept, batched (concepts/bsdfmodel.h:32-146) -------------------------------
+    def eval(self, bsdf, in_xyz, out_xyz, component=ALL, unit=RADIANCE, rgb=None):
+        n = _n(in_xyz, 3)
+        if _n(out_xyz, 3) != n:
+            raise BbmInvalidArgument("in/out batch sizes differ")
+        rgb = _like(in_xyz, (3, n)) if rgb is None else rgb
+        _check(lib().bbmcu_eval(self._h, bsdf._h, component, unit, _ptr(in_xyz), _ptr(out_xyz), C.c_size_t(n), _ptr(rgb)), self._h)
+        return rgb
+
+    def pdf(self, bsdf, in_xyz, out_xyz, component=ALL, unit=RADIANCE, pdf=None):
+        n = _n(in_xyz, 3)
+        if _n(out_xyz, 3) != n:
+            raise BbmInvalidArgument("in/out batch sizes differ")
+        pdf = _like(in_xyz, (n,)) if pdf is None else pdf
+        _check(lib().bbmcu_pdf(self._h, bsdf._h, component, unit, _ptr(in_xyz), _ptr(out_xyz), C.c_size_t(n), _ptr(pdf)), self._h)
+        return pdf
+
+    def reflectance(self, bsdf, out_xyz, component=ALL, unit=RADIANCE, rgb=None):
+        n = _n(out_xyz, 3)
+        rgb = _like(out_xyz, (3, n)) if rgb is None else rgb
+        _check(lib().bbmcu_reflectance(self._h, bsdf._h, component, unit, _ptr(out_xyz), C.c_size_t(n), _ptr(rgb)), self._h)
+        return rgb
+
+    def sample(self, bsdf, out_xyz, xi_uv, component=ALL, unit=RADIANCE, outputs=None):
+        n = _n(out_xyz, 3)
+        if _n(xi_uv, 2) != n:
+            raise BbmInvalidArgument("out/xi batch sizes differ")
+        d, p, f = outputs if outputs is not None else (_like(out_xyz, (3, n)), _like(out_xyz, (n,)), _like(out_xyz, (n,), np.int32))
+        _check(lib().bbmcu_sample(self._h, bsdf._h, component, unit, _ptr(out_xyz), _ptr(xi_uv), C.c_size_t(n), _ptr(d), _ptr(p), _ptr(f)), self._h)
+        return d, p, f
+
+    def sample_eval_pdf(self, bsdf, out_xyz, xi_uv, component=ALL, unit=RADIANCE, outputs=None):
+        """s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)"""
+        n = _n(out_xyz, 3)
+        if _n(xi_uv, 2) != n:
+            raise BbmInvalidArgument("out/xi batch sizes differ")
+        if outputs is None:
+            outputs = (_like(out_xyz, (3, n)), _like(out_xyz, (n,)), _like(out_xyz, (n,), np.int32), _like(out_xyz, (3, n)), _like(out_xyz, (n,)))
+        d, sp, f, rgb, p = outputs
+        _check(lib().bbmcu_sample_eval_pdf(self._h, bsdf._h, component, unit, _ptr(out_xyz), _ptr(xi_uv), C.c_size_t(n),
+                                           _ptr(d), _ptr(sp), _ptr(f), _ptr(rgb), _ptr(p)), self._h)
+        return outputs
+
+    # ---- linearizers ---------------------------------------------------------------------------
+    def merl_index(self, in_xyz, out_xyz, index=None):
+        n = _n(in_xyz, 3)
+        index = _like(in_xyz, (n,), np.uint32) if index is None else index
+        _check(lib().bbmcu_merl_index(self._h, _ptr(in_xyz), _ptr(out_xyz), C.c_size_t(n), _ptr(index)), self._h)
+        return index
+
+    def merl_dirs(self, first, n, like=None, outputs=None):
+        proto = like if like is not None else np.empty(0, np.float32)
+        i, o = outputs if outputs is not None else (_like(proto, (3, n)), _like(proto, (3, n)))
+        _check(lib().bbmcu_merl_dirs(self._h, C.c_uint32(first), C.c_size_t(n), _ptr(i), _ptr(o)), self._h)
+        return i, o
+
+    def spherical_dirs(self, grid, first, n, like=None):
+        proto = like if like is not None else np.empty(0, np.float32)
+        i, o = _like(proto, (3, n)), _like(proto, (3, n))
+        _check(lib().bbmcu_spherical_dirs(self._h, C.byref(grid), C.c_uint64(first), C.c_size_t(n), _ptr(i), _ptr(o)), self._h)
+        return i, o
+
+    # ---- measured data ---------------------------------------------------------------------------
+    def merl_read(self, filename):
+        rgb = np.empty((3, MERL_BINS), np.float32)
+        _check(lib().bbmcu_merl_read(self._h, filename.encode(), _ptr(rgb)), self._h)
+        return rgb
+
+    def merl_write(self, filename, rgb):
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        if rgb.shape != (3, MERL_BINS):
+            raise BbmInvalidArgument("expected a (3, 1458000) table")
+        _check(lib().bbmcu_merl_write(self._h, filename.encode(), _ptr(rgb)), self._h)
+
+    # ---- losses ------------------------------------------------------------------------------------
+    def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0):
+        return Loss(self, metric, reference, grid, component, unit, first, count)
+
+
+class Loss:
+    """a bbm::sampledlossfunction (include/bbm/sampledlossfunction.h:26-95) with one of the six error
+    functors of include/loss/*.h.  `reference` is a Bsdf or a (3, 1458000) measured MERL table."""
+
+    def __init__(self, ctx, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        m = METRICS.index(metric) if isinstance(metric, str) else int(metric)
+        ref_b = reference._h if isinstance(reference, Bsdf) else None
+        ref_t = None if isinstance(reference, Bsdf) else _ptr(reference)
+        self._keep = reference
+        _check(lib().bbmcu_loss_create(ctx._h, m, C.byref(grid) if grid is not None else None, component, unit, ref_b, ref_t,
+                                       C.c_uint64(first), C.c_uint64(count), C.byref(self._h)), ctx._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.bbmcu_loss_free(self._h)
+            self._h = None
+
+    def samples(self):
+        return int(lib().bbmcu_loss_samples(self._h))
+
+    def __call__(self, bsdf, params=None, grad=False):
+        """loss (K,) and, if grad, gradient (K, P) at K parameter vectors (None: the bsdf's current ones)"""
+        P = len(bsdf.parameter_values())
+        if params is None:
+            K, pp = 1, None
+        else:
+            params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+            K, pp = params.shape[0], params.ctypes.data_as(C.c_void_p)
+            if params.shape[1] != P:
+                raise BbmInvalidArgument(f"expected {P} parameters per row, got {params.shape[1]}")
+        loss = np.empty(K, np.float64)
+        g = np.empty((K, P), np.float64) if grad else None
+        _check(lib().bbmcu_loss_eval(self._h, bsdf._h, pp, C.c_size_t(K), loss.ctypes.data_as(C.c_void_p),
+                                     g.ctypes.data_as(C.c_void_p) if grad else None, None), self.ctx._h)
+        return (loss, g) if grad else loss
+
+    def eval_device(self, bsdf, params, device_out):
+        """same, results left in a CUDA buffer of K*(1+P) doubles on the context's stream (for NCCL)"""
+        params = np.ascontiguousarray(np.atleast_2d(params), np.float64)
+        _check(lib().bbmcu_loss_eval(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(params.shape[0]), None, None,
+                                     _ptr(device_out)), self.ctx._h)
+
+    def terms(self, bsdf, count):
+        t = np.empty(count, np.float32)
+        _check(lib().bbmcu_loss_terms(self._h, bsdf._h, _ptr(t)), self.ctx._h)
+        return t
+
+
+def import_fit(filename):
+    """io::importFIT (include/io/fit.h:34-52): {key: Bsdf}, keys sorted like the reference's std::map"""
+    L = lib()
+    h = C.c_void_p()
+    _check(L.bbmcu_fit_import(None, filename.encode(), C.byref(h)))
+    try:
+        out = {}
+        for i in range(L.bbmcu_fit_count(h)):
+            b = C.c_void_p()
+            _check(L.bbmcu_fit_bsdf(h, i, C.byref(b)))
+            out[L.bbmcu_fit_key(h, i).decode()] = Bsdf(None, _handle=b)
+        return out
+    finally:
+        L.bbmcu_fit_free(h)
+
+
+def export_fit(filename, data, comment=""):
+    """io::exportFIT (include/io/fit.h:62-77)"""
+    L = lib()
+    h = C.c_void_p()
+    _check(L.bbmcu_fit_create(C.byref(h)))
+    try:
+        for k, b in data.items():
+            _check(L.bbmcu_fit_add(h, k.encode(), b._h))
+        _check(L.bbmcu_fit_export(None, h, filename.encode(), comment.encode()))
+    finally:
+        L.bbmcu_fit_free(h)

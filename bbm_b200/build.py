@@ -1,0 +1,70 @@
+"""Build libbbmcu.so (sm_100a) in-tree with nvcc.  `python -m bbm_b200.build [--force] [-v]`.
+
+Each .cu / .cpp under csrc/ is one object; objects are compiled in parallel and rebuilt only when a
+source or header is newer.  Flags: -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false
+(-fmad=false: the reference runs on x86-64 without FMA contraction; parity of sharp lobes and of the
+MERL bin index depends on the float operation sequence)."""
+import concurrent.futures as cf
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "_obj")
+LIB = os.path.join(HERE, "libbbmcu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+DEFINES = []  # ["-DBBMCU_WITH_EPD", "-DBBMCU_WITH_HE"] once those families land
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
+              "-diag-suppress", "20012,20011,20014,177,550"] + DEFINES
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-ffp-contract=off"]
+
+
+def _newest_header():
+    hs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.hpp")) + glob.glob(os.path.join(HERE, "..", "include", "*.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+    if src.endswith(".cu"):
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    else:
+        cmd = ["g++"] + CXX_FLAGS + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, obj, r.returncode, r.stdout + r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
+    hdr = _newest_header()
+    todo, objs = [], []
+    for s in srcs:
+        o = os.path.join(OBJ, os.path.basename(s) + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
+            todo.append(s)
+    log = []
+    if todo:
+        with cf.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            for src, obj, rc, out in ex.map(lambda s: _compile(s, verbose), todo):
+                log.append((src, out))
+                if rc != 0:
+                    raise RuntimeError(f"compiling {src} failed:\n{out}")
+    if todo or not os.path.exists(LIB) or force:
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lineinfo"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("linking libbbmcu.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        for src, out in log:
+            print("==", src)
+            print(out)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

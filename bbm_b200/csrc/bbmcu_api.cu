@@ -1,0 +1,405 @@
+// libbbmcu.so C ABI (include/bbmcu.h): context, model registry, BSDF objects, batched
+// eval / sample / pdf / reflectance, linearizers, MERL binaries and .fit files.
+// Loss entry points live in bbmcu_loss.cu.
+#include <cstring>
+#include <fstream>
+#include <memory>
+
+#include "bbmcu_launch.cuh"
+
+using namespace bbmcu;
+
+namespace bbmcu {
+
+static thread_local std::string g_thread_error;
+void set_thread_error(const std::string& msg) { g_thread_error = msg; }
+const char* thread_error() { return g_thread_error.c_str(); }
+
+bool is_device_pointer(const void* p)
+{
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if(e != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+
+struct ArrayArg { const void* ptr; int planes; bool input; };    // 4-byte elements, SoA planes of n
+
+// classify the buffers of one call: all device (true) or all host (false); mixing is an error
+bool all_device(const std::vector<ArrayArg>& args)
+{
+  int dev = 0, host = 0;
+  for(auto& a : args) { if(!a.ptr) throw std::invalid_argument("BBM: null data pointer"); (is_device_pointer(a.ptr) ? dev : host)++; }
+  if(dev && host) throw std::invalid_argument("BBM: data pointers of one call must be all host or all device memory");
+  return dev > 0;
+}
+
+constexpr size_t kChunk = size_t(1) << 21;       // elements per host-pointer chunk
+
+// Host-pointer path: chunks of the batch flow through kSlots device staging buffers, each chunk's
+// H2D copies, kernel and D2H copies on its own stream so copies of one chunk overlap the kernel
+// and copies of its neighbours.  `launch(stream, device_pointers, chunk_n)` issues the kernel.
+template<class Launch>
+void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, Launch&& launch)
+{
+  if(n == 0) return;
+  const size_t cap = std::min(n, kChunk);
+  size_t need = 0;
+  std::vector<size_t> off(args.size());
+  for(size_t a=0; a < args.size(); ++a) { off[a] = need; need += ((size_t)args[a].planes * cap * 4 + 255) & ~size_t(255); }
+  if(need > ctx->slot_bytes)
+  {
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) BBMCU_CUDA(cudaFree(ctx->slot_buf[s])); ctx->slot_buf[s] = nullptr; }
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaMalloc(&ctx->slot_buf[s], need));
+    ctx->slot_bytes = need;
+  }
+  BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));          // order after earlier device-pointer work
+  size_t chunk_id = 0;
+  for(size_t c0 = 0; c0 < n; c0 += cap, ++chunk_id)
+  {
+    const size_t cn = std::min(cap, n - c0);
+    const int s = (int)(chunk_id % bbmcu_ctx::kSlots);
+    cudaStream_t st = ctx->slot_stream[s];                  // in-order reuse of the slot buffer
+    std::vector<void*> dptr(args.size());
+    for(size_t a=0; a < args.size(); ++a)
+    {
+      dptr[a] = (char*)ctx->slot_buf[s] + off[a];
+      if(args[a].input)
+        BBMCU_CUDA(cudaMemcpy2DAsync(dptr[a], cn*4, (const char*)args[a].ptr + c0*4, n*4, cn*4, args[a].planes, cudaMemcpyHostToDevice, st));
+    }
+    launch(st, dptr, cn);
+    for(size_t a=0; a < args.size(); ++a)
+      if(!args[a].input)
+        BBMCU_CUDA(cudaMemcpy2DAsync((char*)args[a].ptr + c0*4, n*4, dptr[a], cn*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
+  }
+  for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaStreamSynchronize(ctx->slot_stream[s]));
+}
+
+template<class Launch>
+void run_any(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, Launch&& launch)
+{
+  if(!ctx) throw std::invalid_argument("BBM: null context");
+  BBMCU_CUDA(cudaSetDevice(ctx->device));
+  if(all_device(args))
+  {
+    std::vector<void*> p(args.size());
+    for(size_t a=0; a < args.size(); ++a) p[a] = const_cast<void*>(args[a].ptr);
+    launch(ctx->stream, p, n);
+  }
+  else run_hosted(ctx, n, args, launch);
+}
+
+void check_flags(int component, int unit)
+{
+  if(component < 0 || component > 3) throw std::invalid_argument("BBM: invalid bsdf_flag " + std::to_string(component));
+  if(unit != BBMCU_RADIANCE && unit != BBMCU_IMPORTANCE) throw std::invalid_argument("BBM: invalid unit " + std::to_string(unit));
+}
+
+} // anonymous namespace
+} // namespace bbmcu
+
+extern "C" {
+
+// ---- context ------------------------------------------------------------------------------------------
+int bbmcu_init(int device, bbmcu_ctx** out)
+{
+  return guarded(nullptr, [&] {
+    if(!out) throw std::invalid_argument("BBM: null output pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0) throw CudaError(std::string("BBM: no usable CUDA device (") + cudaGetErrorString(e) + "); the CUDA backbone has no CPU fallback");
+    if(device < 0 || device >= count) throw std::invalid_argument("BBM: device " + std::to_string(device) + " out of range (" + std::to_string(count) + " devices)");
+    BBMCU_CUDA(cudaSetDevice(device));
+    std::unique_ptr<bbmcu_ctx> ctx(new bbmcu_ctx);
+    ctx->device = device;
+    cudaDeviceProp prop;
+    BBMCU_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    BBMCU_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+    *out = ctx.release();
+  });
+}
+
+void bbmcu_destroy(bbmcu_ctx* ctx)
+{
+  if(!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]); if(ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]); }
+  if(ctx->epd_g1) cudaFree(ctx->epd_g1);
+  if(ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* bbmcu_last_error(bbmcu_ctx* ctx) { return ctx ? ctx->error.c_str() : thread_error(); }
+int bbmcu_synchronize(bbmcu_ctx* ctx) { return guarded(ctx, [&] { if(!ctx) throw std::invalid_argument("BBM: null context"); BBMCU_CUDA(cudaStreamSynchronize(ctx->stream)); }); }
+void* bbmcu_stream(bbmcu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t bbmcu_launch_count(bbmcu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- registry -----------------------------------------------------------------------------------------
+int bbmcu_model_count(void) { return (int)bbmcu_host::model_table().size(); }
+const char* bbmcu_model_name(int id)
+{
+  auto& t = bbmcu_host::model_table();
+  return (id >= 0 && id < (int)t.size()) ? t[id].name.c_str() : nullptr;
+}
+int bbmcu_model_lookup(const char* name, int* id)
+{
+  return guarded(nullptr, [&] {
+    auto* m = name ? bbmcu_host::find_model(name) : nullptr;
+    if(!m) throw std::invalid_argument(std::string("BBM: unrecognized BSDF model: ") + (name ? name : "(null)"));
+    if(id) *id = m->id;
+  });
+}
+int bbmcu_model_layout(int id, bbmcu_attr* attrs, int* n_attrs)
+{
+  return guarded(nullptr, [&] {
+    auto& t = bbmcu_host::model_table();
+    if(id < 0 || id >= (int)t.size()) throw std::invalid_argument("BBM: invalid model id");
+    int off = 0, k = 0;
+    for(auto& a : t[id].attrs)
+    {
+      if(attrs) { attrs[k].name = a.name.c_str(); attrs[k].width = a.width; attrs[k].rows = a.rows; attrs[k].flag = a.flag; attrs[k].offset = off; }
+      off += a.width; ++k;
+    }
+    if(n_attrs) *n_attrs = k;
+  });
+}
+
+// ---- BSDF objects -------------------------------------------------------------------------------------
+int bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out)
+{
+  return guarded(ctx, [&] {
+    if(!str || !out) throw std::invalid_argument("BBM: null argument");
+    std::unique_ptr<bbmcu_bsdf> b(new bbmcu_bsdf);
+    b->b = bbmcu_host::parse_bsdf(str);
+    make_desc(b->b);                                    // validates lobe/attribute limits early
+    *out = b.release();
+  });
+}
+void bbmcu_bsdf_free(bbmcu_bsdf* b) { delete b; }
+int bbmcu_bsdf_to_string(const bbmcu_bsdf* b, char* buf, size_t cap)
+{
+  return guarded(nullptr, [&] {
+    if(!b || !buf || !cap) throw std::invalid_argument("BBM: null argument");
+    std::string s = b->b.to_string();
+    if(s.size() + 1 > cap) throw std::out_of_range("BBM: buffer too small for BSDF string (" + std::to_string(s.size() + 1) + " bytes needed)");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+int bbmcu_bsdf_param_count(const bbmcu_bsdf* b, int flags) { return b ? b->b.param_count(flags) : -1; }
+int bbmcu_bsdf_get_params(const bbmcu_bsdf* b, int which, int flags, double* values, int* count)
+{
+  return guarded(nullptr, [&] {
+    if(!b) throw std::invalid_argument("BBM: null bsdf");
+    if(which < 0 || which > 3) throw std::invalid_argument("BBM: invalid parameter vector selector");
+    auto v = b->b.params(which, flags);
+    if(values) std::copy(v.begin(), v.end(), values);
+    if(count) *count = (int)v.size();
+  });
+}
+int bbmcu_bsdf_set_params(bbmcu_bsdf* b, int flags, const double* values, int count)
+{
+  return guarded(nullptr, [&] {
+    if(!b || !values) throw std::invalid_argument("BBM: null argument");
+    b->b.set_params(flags, values, count);
+  });
+}
+
+// ---- batched BSDF concept -----------------------------------------------------------------------------
+int bbmcu_eval(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, const float* in, const float* out, size_t n, float* rgb)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    BsdfDesc d = make_desc(bsdf->b);
+    run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {rgb, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_eval(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], cn); });
+  });
+}
+
+int bbmcu_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, const float* in, const float* out, size_t n, float* pdf)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    BsdfDesc d = make_desc(bsdf->b);
+    run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {pdf, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], cn); });
+  });
+}
+
+int bbmcu_reflectance(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, const float* out, size_t n, float* rgb)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    BsdfDesc d = make_desc(bsdf->b);
+    run_any(ctx, n, {{out, 3, true}, {rgb, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_reflectance(ctx, s, d, component, (const float*)p[0], (float*)p[1], cn); });
+  });
+}
+
+int bbmcu_sample(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, const float* out, const float* xi, size_t n, float* dir, float* pdf, int32_t* flag)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    BsdfDesc d = make_desc(bsdf->b);
+    run_any(ctx, n, {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {pdf, 1, false}, {flag, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_sample(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], cn); });
+  });
+}
+
+int bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, const float* out, const float* xi, size_t n,
+                          float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    BsdfDesc d = make_desc(bsdf->b);
+    run_any(ctx, n, {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}},
+            [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_sample_eval_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn); });
+  });
+}
+
+// ---- linearizers ----------------------------------------------------------------------------------------
+int bbmcu_merl_index(bbmcu_ctx* ctx, const float* in, const float* out, size_t n, uint32_t* index)
+{
+  return guarded(ctx, [&] {
+    if(n == 0) return;
+    run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {index, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      MerlIndexOp op; op.in = (const float*)p[0]; op.out = (const float*)p[1]; op.index = (uint32_t*)p[2]; op.n = cn;
+      op.aligned = aligned16(p[0]) && aligned16(p[1]) && aligned16(p[2]) && (cn % 4 == 0);
+      launch_foreach4(ctx, s, op, cn); });
+  });
+}
+
+int bbmcu_merl_dirs(bbmcu_ctx* ctx, uint32_t first, size_t n, float* in, float* out)
+{
+  return guarded(ctx, [&] {
+    if(n == 0) return;
+    size_t done = 0;     // run_any hands out consecutive chunks; track the running first index
+    run_any(ctx, n, {{in, 3, false}, {out, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      MerlDirsOp op; op.first = first + (uint32_t)done; op.in = (float*)p[0]; op.out = (float*)p[1]; op.n = cn;
+      op.aligned = aligned16(p[0]) && aligned16(p[1]) && (cn % 4 == 0);
+      launch_foreach4(ctx, s, op, cn); done += cn; });
+  });
+}
+
+void bbmcu_spherical_grid_default(bbmcu_spherical_grid* g, uint32_t in_phi, uint32_t in_theta, uint32_t out_phi, uint32_t out_theta)
+{
+  if(!g) return;
+  g->samples_in[0] = in_phi; g->samples_in[1] = in_theta; g->samples_out[0] = out_phi; g->samples_out[1] = out_theta;
+  g->start_in[0] = g->start_in[1] = g->start_out[0] = g->start_out[1] = 0.0f;
+  g->end_in[0] = g->end_out[0] = kTwoPi; g->end_in[1] = g->end_out[1] = kHalfPi;    // Constants::Hemisphere()
+}
+
+} // extern "C"
+
+namespace bbmcu {
+SphericalGrid to_device_grid(const bbmcu_spherical_grid& g)
+{
+  if(!g.samples_in[0] || !g.samples_in[1] || !g.samples_out[0] || !g.samples_out[1]) throw std::invalid_argument("BBM: spherical grid with zero samples");
+  SphericalGrid d;
+  d.n_in_phi = g.samples_in[0]; d.n_in_theta = g.samples_in[1]; d.n_out_phi = g.samples_out[0]; d.n_out_theta = g.samples_out[1];
+  d.start_in_phi = g.start_in[0]; d.start_in_theta = g.start_in[1]; d.start_out_phi = g.start_out[0]; d.start_out_theta = g.start_out[1];
+  d.size_in_phi = g.end_in[0] - g.start_in[0]; d.size_in_theta = g.end_in[1] - g.start_in[1];
+  d.size_out_phi = g.end_out[0] - g.start_out[0]; d.size_out_theta = g.end_out[1] - g.start_out[1];
+  return d;
+}
+}
+
+extern "C" {
+
+int bbmcu_spherical_dirs(bbmcu_ctx* ctx, const bbmcu_spherical_grid* grid, uint64_t first, size_t n, float* in, float* out)
+{
+  return guarded(ctx, [&] {
+    if(!grid) throw std::invalid_argument("BBM: null grid");
+    if(n == 0) return;
+    SphericalGrid g = to_device_grid(*grid);
+    size_t done = 0;
+    run_any(ctx, n, {{in, 3, false}, {out, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      SphericalDirsOp op; op.grid = g; op.first = first + done; op.in = (float*)p[0]; op.out = (float*)p[1]; op.n = cn;
+      op.aligned = aligned16(p[0]) && aligned16(p[1]) && (cn % 4 == 0);
+      launch_foreach4(ctx, s, op, cn); done += cn; });
+  });
+}
+
+// ---- MERL binaries (staticmodel/merl.h:173-206) ------------------------------------------------------------
+int bbmcu_merl_read(bbmcu_ctx* ctx, const char* filename, float* rgb)
+{
+  return guarded(ctx, [&] {
+    if(!filename || !rgb) throw std::invalid_argument("BBM: null argument");
+    std::ifstream ifs(filename, std::ios_base::binary);
+    if(!ifs) throw std::runtime_error(std::string("BBM: unable to open MERL BRDF: ") + filename);
+    uint32_t dims[3] = {0, 0, 0};
+    ifs.read(reinterpret_cast<char*>(dims), sizeof(dims));
+    if(!ifs || dims[0] != 90 || dims[1] != 90 || dims[2] != 180) throw std::runtime_error(std::string("BBM: not a recognized MERL BRDF: ") + filename);
+    const size_t N = BBMCU_MERL_BINS;
+    std::vector<double> buf(3*N);
+    ifs.read(reinterpret_cast<char*>(buf.data()), 3*N*sizeof(double));
+    if(!ifs) throw std::runtime_error(std::string("BBM: truncated MERL BRDF: ") + filename);
+    const double scale[3] = {1.0, 1.15, 1.66};
+    for(int c=0; c < 3; ++c)
+      for(size_t i=0; i < N; ++i)
+        rgb[c*N + i] = (float)std::fmax(0.0, buf[c*N + i] * scale[c] / 1500.0);     // stored as double, read back as float
+  });
+}
+
+int bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb)
+{
+  return guarded(ctx, [&] {
+    if(!filename || !rgb) throw std::invalid_argument("BBM: null argument");
+    std::ofstream ofs(filename, std::ios_base::binary);
+    if(!ofs) throw std::runtime_error(std::string("BBM: unable to write MERL BRDF: ") + filename);
+    uint32_t dims[3] = {90, 90, 180};
+    ofs.write(reinterpret_cast<const char*>(dims), sizeof(dims));
+    const size_t N = BBMCU_MERL_BINS;
+    std::vector<double> buf(3*N);
+    const double scale[3] = {1.0, 1.15, 1.66};
+    for(int c=0; c < 3; ++c) for(size_t i=0; i < N; ++i) buf[c*N + i] = (double)rgb[c*N + i] * 1500.0 / scale[c];
+    ofs.write(reinterpret_cast<const char*>(buf.data()), 3*N*sizeof(double));
+  });
+}
+
+// ---- .fit files ------------------------------------------------------------------------------------------------
+int bbmcu_fit_import(bbmcu_ctx* ctx, const char* filename, bbmcu_fit** out)
+{
+  return guarded(ctx, [&] {
+    if(!filename || !out) throw std::invalid_argument("BBM: null argument");
+    std::unique_ptr<bbmcu_fit> f(new bbmcu_fit);
+    f->entries = bbmcu_host::import_fit(filename);
+    *out = f.release();
+  });
+}
+int bbmcu_fit_count(const bbmcu_fit* f) { return f ? (int)f->entries.size() : -1; }
+const char* bbmcu_fit_key(const bbmcu_fit* f, int i) { return (f && i >= 0 && i < (int)f->entries.size()) ? f->entries[i].first.c_str() : nullptr; }
+int bbmcu_fit_bsdf(const bbmcu_fit* f, int i, bbmcu_bsdf** out)
+{
+  return guarded(nullptr, [&] {
+    if(!f || !out || i < 0 || i >= (int)f->entries.size()) throw std::invalid_argument("BBM: invalid fit entry");
+    *out = new bbmcu_bsdf{f->entries[i].second};
+  });
+}
+int bbmcu_fit_create(bbmcu_fit** out) { return guarded(nullptr, [&] { if(!out) throw std::invalid_argument("BBM: null argument"); *out = new bbmcu_fit; }); }
+int bbmcu_fit_add(bbmcu_fit* f, const char* key, const bbmcu_bsdf* b)
+{
+  return guarded(nullptr, [&] { if(!f || !key || !b) throw std::invalid_argument("BBM: null argument"); f->entries.emplace_back(key, b->b); });
+}
+int bbmcu_fit_export(bbmcu_ctx* ctx, const bbmcu_fit* f, const char* filename, const char* comment)
+{
+  return guarded(ctx, [&] { if(!f || !filename) throw std::invalid_argument("BBM: null argument"); bbmcu_host::export_fit(filename, f->entries, comment ? comment : ""); });
+}
+void bbmcu_fit_free(bbmcu_fit* f) { delete f; }
+
+} // extern "C"

@@ -1,0 +1,70 @@
+// Host side of the CUDA backbone: the model/attribute table (the reference's compile-time
+// reflection flattened into data), the BSDF string grammar, parameter enumeration and .fit I/O.
+//
+// Contract restated from the reference:
+//   attribute order   include/util/reflection.h:141-148 (own attributes first, then bases)
+//   enumeration       include/bbm/bsdf_enumerate.h:39-47,102-237, include/core/enumerate.h:28-42
+//   defaults/bounds   include/bbm/bsdf_attribute.h:57-94 and each model header
+//   string grammar    include/core/stringconvert.h:61-75,333-360,512-576, include/util/string_util.h
+//   .fit              include/io/fit.h:34-77
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace bbmcu_host {
+
+// bsdf_attr flags (include/bbm/bsdf_attr_flag.h:17-31)
+enum : int { ATTR_NONE = 0, ATTR_DIFFUSE_SCALE = 1, ATTR_DIFFUSE_PARAM = 2, ATTR_SPECULAR_SCALE = 4, ATTR_SPECULAR_PARAM = 8,
+             ATTR_DEPENDENT = 16, ATTR_ALL = 15 };
+
+struct AttrInfo
+{
+  std::string name;
+  int width;                 // number of scalars
+  int rows;                  // 1, or 2 for [[..],[..]] attributes (complex RGB ior, Bagher F0/F1)
+  int flag;                  // bsdf_attr bit
+  std::vector<double> def, lo, hi;   // per scalar (double so that doubleRGB round trips survive)
+};
+
+struct ModelInfo
+{
+  int id;
+  std::string name;
+  std::vector<AttrInfo> attrs;
+  int n_floats() const { int n = 0; for(auto& a : attrs) n += a.width; return n; }
+};
+
+const std::vector<ModelInfo>& model_table();
+const ModelInfo* find_model(const std::string& name);
+
+struct Lobe
+{
+  const ModelInfo* model;
+  std::vector<double> values;        // full attribute block (all attributes incl. Dependent), reflection order
+};
+
+// bsdf_ptr equivalent: one model, or Aggregate(...) of several
+struct Bsdf
+{
+  bool aggregate = false;
+  std::vector<Lobe> lobes;
+
+  std::string to_string() const;
+  // forward-order enumeration (the reference's run-time aggregate reverses each
+  // lobe; we keep the documented forward order everywhere)
+  int param_count(int flags) const;
+  std::vector<double> params(int which, int flags) const;     // which: 0 value 1 default 2 lower 3 upper
+  void set_params(int flags, const double* v, int n);
+  int attr_floats() const { int n = 0; for(auto& l : lobes) n += (int)l.values.size(); return n; }
+};
+
+// throws std::invalid_argument / std::runtime_error with the reference's wording where it has one
+Bsdf parse_bsdf(const std::string& str);
+std::string format_float(double v);                            // default ostream << float (6 significant digits)
+
+std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename);   // file order preserved
+void export_fit(const std::string& filename, const std::vector<std::pair<std::string, Bsdf>>& data, const std::string& comment);
+
+} // namespace bbmcu_host

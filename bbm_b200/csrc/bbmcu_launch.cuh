@@ -1,0 +1,45 @@
+// Host-side launch helper: pick the compile-time single-model kernel when the BSDF is one model,
+// the run-time lobe-list kernel otherwise.
+#pragma once
+#include "bbmcu_ctx.hpp"
+#include "bbmcu_kernels.cuh"
+
+namespace bbmcu {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template<class Op> void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, const Op& op, size_t n)
+{
+  if(n == 0) return;
+  size_t groups = (n + kVec - 1) / kVec;
+  k_foreach4<Op><<<grid_for(ctx, groups), 256, 0, stream>>>(op, groups);
+  BBMCU_CUDA(cudaGetLastError());
+  ++ctx->launches;
+}
+
+// OpT<B> is one of the BSDF operators of bbmcu_kernels.cuh; fill(op) sets everything but op.bsdf
+template<template<class> class OpT, class Fill>
+void launch_bsdf_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& d, size_t n, Fill&& fill)
+{
+  auto go = [&](auto* tag) {
+    using B = typename std::remove_pointer<decltype(tag)>::type;
+    OpT<B> op; op.bsdf = d; fill(op);
+    launch_foreach4(ctx, stream, op, n);
+  };
+  if(!d.aggregate && d.n_lobes == 1)
+  {
+    bool ok = dispatch_model_host(d.model[0], [&](auto* m) { using M = typename std::remove_pointer<decltype(m)>::type; go((BsdfSingle<M>*)nullptr); });
+    if(!ok) throw std::invalid_argument("BBM: model id " + std::to_string(d.model[0]) + " has no CUDA kernel in this build");
+  }
+  else go((BsdfGeneric*)nullptr);
+}
+
+// entry points implemented one per translation unit so the model instantiations compile in parallel
+void launch_eval(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* rgb, size_t n);
+void launch_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* pdf, size_t n);
+void launch_reflectance(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, float* rgb, size_t n);
+void launch_sample(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi, float* dir, float* pdf, int32_t* flag, size_t n);
+void launch_sample_eval_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
+                            float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n);
+
+} // namespace bbmcu

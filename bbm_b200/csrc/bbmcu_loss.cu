@@ -1,0 +1,291 @@
+// Loss objects of the C ABI (include/bbmcu.h): the six metrics over the MERL or spherical linearizer,
+// batched over K parameter sets, with the analytic parameter gradient.
+// Mirrors include/bbm/sampledlossfunction.h:26-95 and the thin metric classes of include/loss/*.h.
+#include <memory>
+
+#include "bbmcu_launch.cuh"
+#include "bbmcu_losskernel.cuh"
+
+using namespace bbmcu;
+
+namespace bbmcu { SphericalGrid to_device_grid(const bbmcu_spherical_grid& g); }
+
+struct bbmcu_loss
+{
+  bbmcu_ctx* ctx = nullptr;
+  int metric = 0, component = BBMCU_ALL, unit = 0;
+  bool merl_grid = true;
+  SphericalGrid grid{};
+  uint64_t N = 0;            // samples of the whole linearizer
+  uint64_t first = 0;        // this shard
+  size_t count = 0;
+  float* d_in = nullptr;     // 3 planes of count
+  float* d_out = nullptr;
+  float* d_ref = nullptr;
+  // scratch, grown on demand
+  float* d_attrs = nullptr;   size_t attrs_cap = 0;
+  float* h_attrs = nullptr;   size_t h_attrs_cap = 0;   // pinned
+  double* d_partial = nullptr; size_t partial_cap = 0;
+  double* d_result = nullptr;  size_t result_cap = 0;
+  double* h_result = nullptr;  size_t h_result_cap = 0;  // pinned
+  uint32_t* d_bad = nullptr;
+  ~bbmcu_loss()
+  {
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
+    if(h_attrs) cudaFreeHost(h_attrs);
+    if(h_result) cudaFreeHost(h_result);
+  }
+};
+
+namespace {
+
+// run-time lobe list (any aggregate): value pass + per-lobe jacobian pass, gradient through local memory
+__global__ void __launch_bounds__(kLossThreads) k_loss_generic(const LossArgs a, const BsdfDesc shape)
+{
+  extern __shared__ double s_red[];                 // [warps][1 + P]
+  __shared__ BsdfDesc b;
+  const int k = blockIdx.y, P = a.P;
+  if(threadIdx.x == 0) { b = shape; }
+  __syncthreads();
+  for(int i = threadIdx.x; i < a.n_attrs; i += blockDim.x) b.attrs[i] = a.attrs[(size_t)k*a.attr_stride + i];
+  __syncthreads();
+  double acc[1 + kMaxParams];
+  for(int j=0; j <= P; ++j) acc[j] = 0.0;
+  for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x*blockDim.x)
+  {
+    f3 in = make_f3(__ldg(a.in + i), __ldg(a.in + a.n + i), __ldg(a.in + 2*a.n + i));
+    f3 out = make_f3(__ldg(a.out + i), __ldg(a.out + a.n + i), __ldg(a.out + 2*a.n + i));
+    Spec<float> ref(__ldg(a.ref + i), __ldg(a.ref + a.n + i), __ldg(a.ref + 2*a.n + i));
+    float g[kMaxParams];
+    float e = loss_sample_generic(b, a.metric, a.component, in, out, ref, a.want_grad ? g : nullptr);
+    acc[0] += (double)e;
+    if(a.want_grad) for(int j=0; j < P; ++j) acc[1 + j] += (double)g[j];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for(int j=0; j <= P; ++j)
+  {
+    double v = acc[j];
+    for(int o=16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if(lane == 0) s_red[warp*(1 + P) + j] = v;
+  }
+  __syncthreads();
+  if((int)threadIdx.x <= P)
+  {
+    double v = 0.0;
+    for(int w=0; w < kLossThreads/32; ++w) v += s_red[w*(1 + P) + threadIdx.x];
+    a.partial[((size_t)k*gridDim.x + blockIdx.x)*(1 + P) + threadIdx.x] = v;
+  }
+}
+
+// second pass: fixed-order sum of the per-block partial rows, times 1/N
+__global__ void k_loss_finish(const double* partial, int blocks_x, int cols, double inv_n, double* result)
+{
+  const int k = blockIdx.x, j = threadIdx.x;
+  if(j >= cols) return;
+  double v = 0.0;
+  for(int b=0; b < blocks_x; ++b) v += partial[((size_t)k*blocks_x + b)*cols + j];
+  result[(size_t)k*cols + j] = v * inv_n;
+}
+
+// per-sample terms l(idx) (sampledlossfunction::operator()(idx))
+__global__ void __launch_bounds__(256) k_loss_terms(const LossArgs a, const BsdfDesc b, float* terms)
+{
+  for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x*blockDim.x)
+  {
+    f3 in = make_f3(a.in[i], a.in[a.n + i], a.in[2*a.n + i]);
+    f3 out = make_f3(a.out[i], a.out[a.n + i], a.out[2*a.n + i]);
+    Spec<float> ref(a.ref[i], a.ref[a.n + i], a.ref[2*a.n + i]);
+    terms[i] = loss_sample_generic(b, a.metric, a.component, in, out, ref, nullptr);
+  }
+}
+
+template<class T> void grow(T*& p, size_t& cap, size_t need)
+{
+  if(need <= cap) return;
+  if(p) BBMCU_CUDA(cudaFree(p));
+  p = nullptr; cap = 0;
+  BBMCU_CUDA(cudaMalloc(&p, need*sizeof(T)));
+  cap = need;
+}
+
+void check_metric(int metric) { if(metric < 0 || metric > 5) throw std::invalid_argument("BBM: unknown loss metric " + std::to_string(metric)); }
+
+} // anonymous namespace
+
+extern "C" {
+
+int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
+                      const bbmcu_bsdf* reference_bsdf, const float* reference_merl_rgb,
+                      uint64_t first, uint64_t count, bbmcu_loss** out)
+{
+  return guarded(ctx, [&] {
+    if(!ctx || !out) throw std::invalid_argument("BBM: null argument");
+    check_metric(metric);
+    if((reference_bsdf != nullptr) == (reference_merl_rgb != nullptr)) throw std::invalid_argument("BBM: exactly one of reference_bsdf / reference_merl_rgb must be given");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<bbmcu_loss> L(new bbmcu_loss);
+    L->ctx = ctx; L->metric = metric; L->component = component; L->unit = unit;
+    L->merl_grid = (grid == nullptr);
+    if(grid) { L->grid = to_device_grid(*grid); L->N = L->grid.size(); } else L->N = kMerlBins;
+    if(first > L->N) throw std::out_of_range("BBM: loss shard starts beyond the linearizer size");
+    if(count == 0) count = L->N - first;
+    if(first + count > L->N) throw std::out_of_range("BBM: loss shard exceeds the linearizer size");
+    L->first = first; L->count = (size_t)count;
+    const size_t n = L->count;
+    if(n == 0) { *out = L.release(); return; }
+    BBMCU_CUDA(cudaMalloc(&L->d_in, 3*n*sizeof(float)));
+    BBMCU_CUDA(cudaMalloc(&L->d_out, 3*n*sizeof(float)));
+    BBMCU_CUDA(cudaMalloc(&L->d_ref, 3*n*sizeof(float)));
+    BBMCU_CUDA(cudaMalloc(&L->d_bad, sizeof(uint32_t)));
+    BBMCU_CUDA(cudaMemsetAsync(L->d_bad, 0, sizeof(uint32_t), ctx->stream));
+    // 1. the linearizer's directions for this shard (materialised once; both sides of every parity test
+    //    and every pass read these same float triples)
+    const bool al = (n % 4 == 0);
+    if(L->merl_grid) { MerlDirsOp op; op.first = (uint32_t)first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
+    else { SphericalDirsOp op; op.grid = L->grid; op.first = first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
+    // 2. the reference operand tabulated at those directions (it never changes during a fit)
+    if(reference_bsdf)
+    {
+      BsdfDesc d = make_desc(reference_bsdf->b);
+      launch_eval(ctx, ctx->stream, d, component, L->d_in, L->d_out, L->d_ref, n);
+    }
+    else
+    {
+      // merl_data::eval: component must be exactly All (staticmodel/merl.h:83), nearest-bin lookup
+      float* d_table = nullptr;
+      const float* table = reference_merl_rgb;
+      if(!is_device_pointer(reference_merl_rgb))
+      {
+        BBMCU_CUDA(cudaMalloc(&d_table, 3*(size_t)kMerlBins*sizeof(float)));
+        BBMCU_CUDA(cudaMemcpyAsync(d_table, reference_merl_rgb, 3*(size_t)kMerlBins*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        table = d_table;
+      }
+      if(component == BBMCU_ALL)
+      {
+        MerlLookupOp op; op.table = table; op.in = L->d_in; op.out = L->d_out; op.rgb = L->d_ref; op.bad = L->d_bad; op.n = n; op.aligned = al;
+        launch_foreach4(ctx, ctx->stream, op, n);
+      }
+      else BBMCU_CUDA(cudaMemsetAsync(L->d_ref, 0, 3*n*sizeof(float), ctx->stream));
+      uint32_t bad = 0;
+      BBMCU_CUDA(cudaMemcpyAsync(&bad, L->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+      if(d_table) BBMCU_CUDA(cudaFree(d_table));
+      // the reference throws from lookup() on such samples
+      if(bad) throw std::out_of_range("BBM: " + std::to_string(bad) + " samples of the linearizer map outside the MERL table (NaN direction pairs); the reference throws 'lookup out of range' here");
+    }
+    BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = L.release();
+  });
+}
+
+void bbmcu_loss_free(bbmcu_loss* L) { if(L) { cudaSetDevice(L->ctx->device); cudaStreamSynchronize(L->ctx->stream); delete L; } }
+uint64_t bbmcu_loss_samples(const bbmcu_loss* L) { return L ? L->N : 0; }
+
+int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params, size_t K, double* loss_out, double* grad_out, double* device_out)
+{
+  bbmcu_ctx* ctx = L ? L->ctx : nullptr;
+  return guarded(ctx, [&] {
+    if(!L || !bsdf) throw std::invalid_argument("BBM: null argument");
+    if(K == 0) return;
+    if(!params && K != 1) throw std::invalid_argument("BBM: params == NULL requires K == 1");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    const int P = bsdf->b.param_count(BBMCU_ATTR_ALL);
+    if(P > kMaxParams) throw std::invalid_argument("BBM: more than " + std::to_string(kMaxParams) + " fit parameters");
+    BsdfDesc shape = make_desc(bsdf->b);
+    const int A = bsdf->b.attr_floats();
+    const bool want_grad = (grad_out != nullptr) || (device_out != nullptr);
+    const int cols = 1 + P;
+    // attribute blocks for the K parameter sets
+    grow(L->d_attrs, L->attrs_cap, K*(size_t)A);
+    if(K*(size_t)A > L->h_attrs_cap)
+    {
+      if(L->h_attrs) { BBMCU_CUDA(cudaFreeHost(L->h_attrs)); L->h_attrs = nullptr; L->h_attrs_cap = 0; }
+      BBMCU_CUDA(cudaMallocHost(&L->h_attrs, K*(size_t)A*sizeof(float)));
+      L->h_attrs_cap = K*(size_t)A;
+    }
+    BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));      // the previous upload from this pinned buffer has been consumed
+    {
+      bbmcu_host::Bsdf tmp = bsdf->b;
+      for(size_t k=0; k < K; ++k)
+      {
+        if(params) tmp.set_params(BBMCU_ATTR_ALL, params + k*P, P);
+        size_t off = 0;
+        for(auto& l : tmp.lobes) for(double v : l.values) L->h_attrs[k*A + off++] = (float)v;
+      }
+    }
+    BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, L->h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    // launch shape: about 8 resident blocks per SM over all K
+    const size_t n = L->count;
+    unsigned max_bx = (unsigned)std::max<size_t>(1, (n + kLossThreads - 1) / kLossThreads);
+    unsigned bx = (unsigned)std::max<size_t>(1, ((size_t)ctx->sm_count*8 + K - 1) / K);
+    if(bx > max_bx) bx = max_bx;
+    grow(L->d_partial, L->partial_cap, K*(size_t)bx*cols);
+    grow(L->d_result, L->result_cap, K*(size_t)cols);
+    LossArgs a;
+    a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = n; a.attrs = L->d_attrs; a.attr_stride = A; a.n_attrs = A;
+    a.metric = L->metric; a.component = L->component; a.want_grad = want_grad ? 1 : 0; a.partial = L->d_partial; a.P = P;
+    bool done = false;
+    if(n > 0)
+    {
+      const int m0 = shape.model[0];
+      if(shape.n_lobes == 1 && !shape.aggregate)
+        done = launch_loss_single_g0(m0, ctx->stream, a, bx, (unsigned)K) || launch_loss_single_g1(m0, ctx->stream, a, bx, (unsigned)K) ||
+               launch_loss_single_g2(m0, ctx->stream, a, bx, (unsigned)K) || launch_loss_single_g3(m0, ctx->stream, a, bx, (unsigned)K);
+      else if(shape.n_lobes == 2 && shape.aggregate && m0 == M_Lambertian)
+      {
+        const int m1 = shape.model[1];
+        done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)K) ||
+               launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)K);
+      }
+      if(!done) k_loss_generic<<<dim3(bx, (unsigned)K), kLossThreads, (kLossThreads/32)*cols*sizeof(double), ctx->stream>>>(a, shape);
+      BBMCU_CUDA(cudaGetLastError());
+      ++ctx->launches;
+    }
+    else BBMCU_CUDA(cudaMemsetAsync(L->d_partial, 0, K*(size_t)bx*cols*sizeof(double), ctx->stream));
+    double* result = device_out ? device_out : L->d_result;
+    k_loss_finish<<<(unsigned)K, 64, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
+    BBMCU_CUDA(cudaGetLastError());
+    ++ctx->launches;
+    if(device_out) return;                       // caller all-reduces / reads it on the stream
+    if(K*(size_t)cols > L->h_result_cap)
+    {
+      if(L->h_result) { BBMCU_CUDA(cudaFreeHost(L->h_result)); L->h_result = nullptr; L->h_result_cap = 0; }
+      BBMCU_CUDA(cudaMallocHost(&L->h_result, K*(size_t)cols*sizeof(double)));
+      L->h_result_cap = K*(size_t)cols;
+    }
+    BBMCU_CUDA(cudaMemcpyAsync(L->h_result, L->d_result, K*(size_t)cols*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    for(size_t k=0; k < K; ++k)
+    {
+      if(loss_out) loss_out[k] = L->h_result[k*cols];
+      if(grad_out) for(int j=0; j < P; ++j) grad_out[k*P + j] = L->h_result[k*cols + 1 + j];
+    }
+  });
+}
+
+int bbmcu_loss_terms(bbmcu_loss* L, const bbmcu_bsdf* bsdf, float* terms)
+{
+  bbmcu_ctx* ctx = L ? L->ctx : nullptr;
+  return guarded(ctx, [&] {
+    if(!L || !bsdf || !terms) throw std::invalid_argument("BBM: null argument");
+    if(L->count == 0) return;
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc shape = make_desc(bsdf->b);
+    LossArgs a{};
+    a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = L->count; a.metric = L->metric; a.component = L->component;
+    const bool dev = is_device_pointer(terms);
+    float* d_terms = terms;
+    if(!dev) BBMCU_CUDA(cudaMalloc(&d_terms, L->count*sizeof(float)));
+    k_loss_terms<<<grid_for(ctx, L->count), 256, 0, ctx->stream>>>(a, shape, d_terms);
+    BBMCU_CUDA(cudaGetLastError());
+    ++ctx->launches;
+    if(!dev)
+    {
+      BBMCU_CUDA(cudaMemcpyAsync(terms, d_terms, L->count*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+      BBMCU_CUDA(cudaFree(d_terms));
+    }
+  });
+}
+
+} // extern "C"

@@ -1,0 +1,21 @@
+// loss(+gradient) kernel instantiations, pair lobe after a Lambertian lobe, model group 0
+#include "bbmcu_losskernel.cuh"
+namespace bbmcu {
+bool launch_loss_pair_g0(int model, cudaStream_t s, const LossArgs& a, unsigned bx, unsigned K)
+{
+  switch(model) {
+    BBMCU_LOSS_CASE_PAIR(M_Lambertian)
+    BBMCU_LOSS_CASE_PAIR(M_OrenNayar)
+    BBMCU_LOSS_CASE_PAIR(M_Phong)
+    BBMCU_LOSS_CASE_PAIR(M_NganBlinnPhong)
+    BBMCU_LOSS_CASE_PAIR(M_Lafortune)
+    BBMCU_LOSS_CASE_PAIR(M_NganLafortune)
+    BBMCU_LOSS_CASE_PAIR(M_Ward)
+    BBMCU_LOSS_CASE_PAIR(M_WardDuer)
+    BBMCU_LOSS_CASE_PAIR(M_WardDuerGeislerMoroder)
+    BBMCU_LOSS_CASE_PAIR(M_NganWard)
+    BBMCU_LOSS_CASE_PAIR(M_NganWardDuer)
+    default: return false;
+  }
+}
+}

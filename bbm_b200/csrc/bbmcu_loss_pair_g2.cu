@@ -1,0 +1,18 @@
+// loss(+gradient) kernel instantiations, pair lobe after a Lambertian lobe, model group 2
+#include "bbmcu_losskernel.cuh"
+namespace bbmcu {
+bool launch_loss_pair_g2(int model, cudaStream_t s, const LossArgs& a, unsigned bx, unsigned K)
+{
+  switch(model) {
+    BBMCU_LOSS_CASE_PAIR(M_GGX)
+    BBMCU_LOSS_CASE_PAIR(M_GGXHeitz)
+    BBMCU_LOSS_CASE_PAIR(M_PhongWalter)
+    BBMCU_LOSS_CASE_PAIR(M_LowMicrofacet)
+    BBMCU_LOSS_CASE_PAIR(M_LowMicrofacetFit)
+    BBMCU_LOSS_CASE_PAIR(M_LowSmooth)
+    BBMCU_LOSS_CASE_PAIR(M_Ribardiere)
+    BBMCU_LOSS_CASE_PAIR(M_RibardiereAnisotropic)
+    default: return false;
+  }
+}
+}

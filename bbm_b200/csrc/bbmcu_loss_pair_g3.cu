@@ -1,0 +1,17 @@
+// loss(+gradient) kernel instantiations, pair lobe after a Lambertian lobe, model group 3
+#include "bbmcu_losskernel.cuh"
+namespace bbmcu {
+bool launch_loss_pair_g3(int model, cudaStream_t s, const LossArgs& a, unsigned bx, unsigned K)
+{
+  switch(model) {
+    BBMCU_LOSS_CASE_PAIR(M_Bagher)
+#ifdef BBMCU_WITH_EPD
+    BBMCU_LOSS_CASE_PAIR(M_EPD)
+#endif
+#ifdef BBMCU_WITH_HE
+    BBMCU_LOSS_CASE_PAIR(M_He) BBMCU_LOSS_CASE_PAIR(M_HeWestin) BBMCU_LOSS_CASE_PAIR(M_HeHolzschuch) BBMCU_LOSS_CASE_PAIR(M_NganHe)
+#endif
+    default: return false;
+  }
+}
+}

@@ -1,0 +1,17 @@
+// loss(+gradient) kernel instantiations, single lobe, model group 3
+#include "bbmcu_losskernel.cuh"
+namespace bbmcu {
+bool launch_loss_single_g3(int model, cudaStream_t s, const LossArgs& a, unsigned bx, unsigned K)
+{
+  switch(model) {
+    BBMCU_LOSS_CASE_SINGLE(M_Bagher)
+#ifdef BBMCU_WITH_EPD
+    BBMCU_LOSS_CASE_SINGLE(M_EPD)
+#endif
+#ifdef BBMCU_WITH_HE
+    BBMCU_LOSS_CASE_SINGLE(M_He) BBMCU_LOSS_CASE_SINGLE(M_HeWestin) BBMCU_LOSS_CASE_SINGLE(M_HeHolzschuch) BBMCU_LOSS_CASE_SINGLE(M_NganHe)
+#endif
+    default: return false;
+  }
+}
+}

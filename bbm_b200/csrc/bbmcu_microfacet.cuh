@@ -1,0 +1,531 @@
+// Microfacet building blocks: Fresnel terms, normal distributions (D, G1, sample, pdf),
+// joint masking-shadowing terms and the microfacet combinator.
+//
+// Behaviour follows (restated, not copied):
+//   include/bbm/fresnel_cook.h:41-56, fresnel_schlick.h:42-52, fresnel_complex.h:29-51,
+//   include/core/ior.h:58-72, include/bsdfmodel/bagher.h:38-51
+//   include/ndf/beckmann.h:49-201, ggx.h:50-189, phong.h:40-131, low.h:44-132,
+//   include/ndf/studentt.h:41-197, sgd.h:48-193
+//   include/maskingshadowing/vgroove.h:30-47, uncorrelated.h:30-42, heightcorrelated.h:30-54,
+//   include/maskingshadowing/vanginneken.h:37-74
+//   include/bsdfmodel/microfacet.h:74-199, scaledmodel.h:50-67
+//
+// Every eval-side function is a template over the scalar type T (float, or Dual<N> for the
+// analytic parameter gradient); directions are always plain float.  sample / pdf are float only.
+#pragma once
+#include "bbmcu_math.cuh"
+
+namespace bbmcu {
+
+// =============================================================================================
+// Fresnel
+// =============================================================================================
+// ior::convert(ior <- reflectance): (1 + sqrt(r)) / (1 - sqrt(r))      (core/ior.h:66-72)
+template<class T> BBMCU_D T ior_from_reflectance(const T& r) { T t = m_safe_sqrt(r); return (1.0f + t) / (1.0f - t); }
+// ior::convert(reflectance <- ior): ((n-1)/(n+1))^2                      (core/ior.h:58-64)
+template<class T> BBMCU_D T reflectance_from_ior(const T& n) { T t = (n - 1.0f) / (n + 1.0f); return t*t; }
+
+// Cook-Torrance Fresnel of an index of refraction (fresnel_cook.h:47-55)
+template<class T> BBMCU_D T fresnel_cook(const T& eta, float c)
+{
+  T g = m_safe_sqrt(eta*eta + c*c - 1.0f);
+  T a = (g - c) / (g + c);
+  T b = (c*(g + c) - 1.0f) / (c*(g - c) + 1.0f);
+  return m_max(0.5f * (a*a) * (1.0f + b*b), 0.0f);
+}
+// Schlick of a reflectance at normal incidence: R0 + (1-R0) * pow(1-c, 5.0)  (fresnel_schlick.h:48-51).
+// The reference's pow(float, 5.0) runs in double and is rounded once.
+BBMCU_D float schlick_w(float c) { double w = 1.0 - (double)c; double w2 = w*w; return (float)(w2*w2*w); }
+template<class T> BBMCU_D T fresnel_schlick(const T& R0, float c) { return R0 + (1.0f - R0) * schlick_w(c); }
+
+// Conductor Fresnel, Shirley 1985 in real arithmetic (fresnel_complex.h:31-50)
+template<class T> BBMCU_D T fresnel_complex(const T& n, const T& k, float c)
+{
+  float c2 = c*c, s2 = 1.0f - c2;
+  T n2 = n*n, k2 = k*k;
+  T temp = n2 - k2 - s2;
+  T a2b2 = m_safe_sqrt(temp*temp + 4.0f*n2*k2);
+  T a = m_safe_sqrt(0.5f * (a2b2 + temp));
+  T a2c = 2.0f*a*c;
+  T Rs = (a2b2 - a2c + c2) / (a2b2 + a2c + c2);
+  T Rp = Rs * (c2*a2b2 - (a2c - s2)*s2) / (c2*a2b2 + (a2c + s2)*s2);
+  return 0.5f*(Rs + Rp);
+}
+
+// Fresnel policies: NA attribute floats; eval returns T (scalar) or Spec<T> (spectral).
+struct FresnelCookIor      { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_cook(a[0], c); } };
+struct FresnelSchlickR0    { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_schlick(a[0], c); } };
+struct FresnelComplexScalar{ static constexpr int NA = 2; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_complex(a[0], a[1], c); } };
+struct FresnelComplexRGB   { static constexpr int NA = 6; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
+    return Spec<T>(fresnel_complex(a[0], a[3], c), fresnel_complex(a[1], a[4], c), fresnel_complex(a[2], a[5], c)); } };
+struct FresnelSchlickRGB   { static constexpr int NA = 3; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
+    return Spec<T>(fresnel_schlick(a[0], c), fresnel_schlick(a[1], c), fresnel_schlick(a[2], c)); } };
+// fresnel::bagher: schlick(F0) - F1*cos   (bagher.h:47-50); attribute = [F0 rgb, F1 rgb]
+struct FresnelBagher       { static constexpr int NA = 6; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
+    return Spec<T>(fresnel_schlick(a[0], c) - a[3]*c, fresnel_schlick(a[1], c) - a[4]*c, fresnel_schlick(a[2], c) - a[5]*c); } };
+
+// scalar-or-spectrum helpers
+template<class T> BBMCU_D Spec<T> to_spec(const T& a) { return Spec<T>(a); }
+template<class T> BBMCU_D Spec<T> to_spec(const Spec<T>& a) { return a; }
+
+// the rational fit shared by the Beckmann and Phong G1 (beckmann.h:196, phong.h:127), evaluated in
+// double by the reference (double literals) and rounded to float.
+BBMCU_D float smith_rational(float a)
+{
+  if(!(a < 1.6f)) return 1.0f;
+  double x = a;
+  return (float)((3.535*x + 2.181*x*x) / (1.0 + 2.276*x + 2.577*x*x));
+}
+template<int N> BBMCU_D Dual<N> smith_rational(const Dual<N>& a)
+{
+  if(!(a.v < 1.6f)) return Dual<N>(1.0f);
+  float x = a.v;
+  float num = 3.535f*x + 2.181f*x*x, den = 1.0f + 2.276f*x + 2.577f*x*x;
+  float dnum = 3.535f + 2.0f*2.181f*x, dden = 2.276f + 2.0f*2.577f*x;
+  return chain(a, smith_rational(x), (dnum*den - num*dden)/(den*den));
+}
+
+// =============================================================================================
+// Normal distributions.  Interface:
+//   NA                      attribute floats
+//   D<T>(h, a)              eval (h.z > 0 checked here)           -> T or Spec<T>
+//   G1<T>(v, m, a)          monodirectional shadowing               -> T or Spec<T>
+//   sample(view, xi, a)     microfacet normal (xi range already checked by the caller too)
+//   pdf(view, m, a)
+// =============================================================================================
+template<bool ANISO> struct Alpha2 { template<class T> BBMCU_D static void get(const T* a, T& ax, T& ay) { ax = a[0]; ay = ANISO ? a[1] : a[0]; } };
+
+BBMCU_D bool xi_valid(f2 xi) { return (xi.x >= 0.0f) && (xi.y >= 0.0f) && (xi.x <= 1.0f) && (xi.y <= 1.0f); }
+
+// ---- Beckmann (beckmann.h) -------------------------------------------------------------------
+template<bool ANISO, bool NORMALIZE, bool SAMPLE_VISIBLE = true>
+struct NdfBeckmann
+{
+  static constexpr int NA = ANISO ? 2 : 1;
+  template<class T> BBMCU_D static T D(f3 h, const T* a)
+  {
+    if(!(h.z > 0.0f)) return T(0.0f);
+    T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    float c2 = h.z*h.z;
+    T sx = h.x/ax, sy = h.y/ay;
+    T d = m_exp(-(sx*sx + sy*sy) / c2) / (ax*ay*c2*c2);
+    if(NORMALIZE) d = d * kInvPi;
+    return d;
+  }
+  template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
+    T aa;
+    if(ANISO) { T sx = v.x*a[0], sy = v.y*a[1]; aa = m_rsqrt((sx*sx + sy*sy) / (v.z*v.z)); }
+    else aa = m_rcp(a[0] * tanTheta(v));
+    return smith_rational(aa);
+  }
+  BBMCU_D static float pdf(f3 view, f3 m, const float* a)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    float p = D<float>(m, a);
+    if(SAMPLE_VISIBLE) p *= G1<float>(view, m, a) * fabsf(dot(view, m)) / view.z;
+    else p *= m.z;
+    return (p > 0.0f) ? p : 0.0f;
+  }
+  BBMCU_D static f3 sample(f3 view, f2 xi, const float* a)
+  {
+    if(!xi_valid(xi)) return make_f3(0, 0, 0);
+    float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    if(SAMPLE_VISIBLE)
+    {
+      // Jakob 2014 (beckmann.h:87-115); the double/float mix follows the reference's promotions.
+      f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
+      float tanT = tanTheta(vs);
+      float maxval = erff(1.0f / tanT);
+      float x0 = fminf(fmaxf(xi.x, 1e-5f), (float)(1.0 - 10e-6));
+      float x1 = fminf(fmaxf(xi.y, 1e-5f), (float)(1.0 - 10e-6));
+      float x = maxval - (maxval + 1.0f) * erff(sqrtf(-logf(x0)));
+      float gauss = kInvSqrtPi * tanT * expf(-(vs.z*vs.z));
+      x0 = (float)((double)x0 * (1.0 + (double)maxval + (double)gauss));
+#pragma unroll
+      for(int i=0; i < 3; ++i)
+      {
+        float slope = (float)erfinv_ref(x);
+        float g = kInvSqrtPi * tanT * expf(-slope*slope);
+        float value = (float)(1.0 + (double)x + (double)g - (double)x0);
+        float deriv = (float)(1.0 - (double)(slope*tanT));
+        x -= value / deriv;
+      }
+      float s0 = 0.0f, s1 = 0.0f;
+      if(x > -1.0f && x < 1.0f) { s0 = (float)erfinv_ref(x); s1 = (float)erfinv_ref((float)(2.0*(double)x1 - 1.0)); }
+      f2 cs = cossinPhi(vs);
+      float ux = (cs.x*s0 + (-cs.y)*s1) * ax;      // rotation2d(cos,sin) * slope, then unstretch
+      float uy = (cs.y*s0 + cs.x*s1) * ay;
+      return normalize(make_f3(-ux, -uy, 1.0f));
+    }
+    else
+    {
+      // Walter 2007 with anisotropic extension (beckmann.h:117-135)
+      float cp = cosf(kTwoPi * xi.x), sp = sinf(kTwoPi * xi.x);
+      float nrm;
+      if(ANISO) { cp *= ax; sp *= ay; nrm = cp*cp + sp*sp; float r = 1.0f/sqrtf(nrm); cp *= r; sp *= r; }
+      else nrm = ax*ax;
+      float cosT = (float)(1.0 / sqrt(1.0 - (double)(nrm*logf(xi.y))));
+      float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+      return make_f3(cp*sinT, sp*sinT, cosT);
+    }
+  }
+};
+
+// ---- GGX (ggx.h) -----------------------------------------------------------------------------
+template<bool ANISO>
+struct NdfGGX
+{
+  static constexpr int NA = ANISO ? 2 : 1;
+  template<class T> BBMCU_D static T D(f3 h, const T* a)
+  {
+    if(!(h.z > 0.0f)) return T(0.0f);
+    T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    T sx = h.x/ax, sy = h.y/ay;
+    T t = (sx*sx + sy*sy) + h.z*h.z;
+    return m_rcp(kPi * (ax*ay) * (t*t));
+  }
+  template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
+    T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    T r2 = ax*ay;
+    return g1_tail(r2 * tanTheta2(v));
+  }
+  // 2.0 / (1.0 + sqrt(1.0 + x)) evaluated in double by the reference (ggx.h:184-187)
+  BBMCU_D static float g1_tail(float x) { return (float)(2.0 / (double)(float)(1.0 + sqrt(1.0 + (double)x))); }
+  template<int N> BBMCU_D static Dual<N> g1_tail(const Dual<N>& x) { float s = sqrtf(1.0f + x.v); float den = 1.0f + s; return chain(x, 2.0f/den, -1.0f/(den*den*s)); }
+
+  BBMCU_D static float pdf(f3 view, f3 m, const float* a)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    float p = D<float>(m, a);
+    p *= G1<float>(view, m, a) * fabsf(dot(view, m)) / view.z;
+    return (p > 0.0f) ? p : 0.0f;
+  }
+  // Heitz 2017 visible-normal sampling (ggx.h:86-107)
+  BBMCU_D static f3 sample(f3 view, f2 xi, const float* a)
+  {
+    if(!xi_valid(xi)) return make_f3(0, 0, 0);
+    float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
+    f3 T1 = (vs.z < 0.99999988079071044921875f) ? normalize(cross(vs, make_f3(0, 0, 1))) : make_f3(1, 0, 0);
+    f3 T2 = cross(T1, vs);
+    float aa = (float)(1.0 / (1.0 + (double)vs.z));
+    float r = sqrtf(xi.x);
+    bool lower = xi.y < aa;
+    float phi = (float)((lower ? (double)(xi.y/aa) : 1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
+    float cp = cosf(phi), sp = sinf(phi);
+    float P1 = r*cp;
+    float P2 = (float)((lower ? 1.0 : (double)vs.z) * (double)r * (double)sp);
+    // safe_sqrt(1.0 - P1*P1 - P2*P2) is a double, but double * float-array converts the scalar to float first
+    float w = (float)sqrt(fmax(1.0 - (double)(P1*P1) - (double)(P2*P2), 0.0));
+    f3 n = (T1*P1 + T2*P2) + vs*w;
+    return normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
+  }
+};
+
+// ---- Phong NDF (ndf/phong.h) -----------------------------------------------------------------
+struct NdfPhong
+{
+  static constexpr int NA = 1;
+  template<class T> BBMCU_D static T D(f3 h, const T* a)
+  {
+    if(!(h.z > 0.0f)) return T(0.0f);
+    T nrm = (a[0] + 2.0f) / kTwoPi;
+    return m_pow(h.z, a[0]) * nrm;
+  }
+  template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
+    T aa = m_sqrt(0.5f*a[0] + 1.0f) / tanTheta(v);
+    return smith_rational(aa);
+  }
+  BBMCU_D static float pdf(f3, f3 m, const float* a)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    return D<float>(m, a) * fabsf(m.z);
+  }
+  BBMCU_D static f3 sample(f3, f2 xi, const float* a)
+  {
+    if(!xi_valid(xi)) return make_f3(0, 0, 0);
+    float cosT = (float)pow((double)xi.x, 1.0 / (double)(a[0] + 2.0f));
+    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float ph = xi.y * kTwoPi;
+    return make_f3(cosf(ph)*sinT, sinf(ph)*sinT, cosT);
+  }
+};
+
+// ---- Low NDF (ndf/low.h): (1 + B (1 - h.z))^-C, unnormalised; G1 = 1 ---------------------------
+struct NdfLow
+{
+  static constexpr int NA = 2;
+  // the reference evaluates the base in double (1.0 literals) and calls the double pow
+  BBMCU_D static float D_(f3 h, float B, float C) { return (float)pow(1.0 + (double)B*(1.0 - (double)h.z), -(double)C); }
+  template<class T> BBMCU_D static T D(f3 h, const T* a);
+  template<class T> BBMCU_D static T G1(f3, f3, const T*) { return T(1.0f); }
+  BBMCU_D static float pdf(f3, f3 m, const float* a)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    float B = a[0], C = a[1];
+    float nrm = (fabsf(C - 1.0f) < kEps) ? (float)(1.0f / log(1.0 + (double)B))
+                                         : (float)(((double)C - 1.0) / (1.0 - pow(1.0 + (double)B, 1.0 - (double)C)));
+    float p = D_(m, B, C) * B * ((0.5f*kInvPi) * nrm);
+    return (p > 0.0f) ? p : 0.0f;
+  }
+  BBMCU_D static f3 sample(f3, f2 xi, const float* a)
+  {
+    if(!xi_valid(xi)) return make_f3(0, 0, 0);
+    float B = a[0], C = a[1];
+    float term = (fabsf(C - 1.0f) < kEps)
+               ? (float)exp((double)xi.x * log(1.0 + (double)B))
+               : (float)pow(1.0 + (double)xi.x * (pow(1.0 + (double)B, 1.0 - (double)C) - 1.0), -1.0 / ((double)C - 1.0));
+    float cosT = (float)((1.0 + (double)B - (double)term) / (double)B);
+    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float ph = xi.y * kTwoPi;
+    return make_f3(cosf(ph)*sinT, sinf(ph)*sinT, cosT);
+  }
+};
+template<> BBMCU_D float NdfLow::D<float>(f3 h, const float* a) { return (h.z > 0.0f) ? D_(h, a[0], a[1]) : 0.0f; }
+template<class T> BBMCU_D T NdfLow::D(f3 h, const T* a)
+{
+  if(!(h.z > 0.0f)) return T(0.0f);
+  T base = 1.0f + a[0]*(1.0f - h.z);
+  T r = m_pow(base, -a[1]);
+  r.v = D_(h, a[0].v, a[1].v);
+  return r;
+}
+
+// ---- Student-t NDF (ndf/studentt.h) -----------------------------------------------------------
+template<bool ANISO>
+struct NdfStudentT
+{
+  static constexpr int NA = ANISO ? 3 : 2;     // roughness[1|2], gamma
+  template<class T> BBMCU_D static T D(f3 h, const T* a)
+  {
+    if(!(h.z > 0.0f)) return T(0.0f);
+    T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    const T& gamma = a[NA-1];
+    float c2 = h.z*h.z;
+    T nrm = kPi * (ax*ay) * (c2*c2);
+    T sx = h.x/ax, sy = h.y/ay;
+    T den = m_pow(1.0f + (sx*sx + sy*sy) / ((gamma - 1.0f)*c2), gamma);
+    return m_rcp(nrm * den);
+  }
+  BBMCU_D static float ratfit(float x, float n0, float n1, float n2, float n3, float d0, float d1, float d2, float d3)
+  {
+    // the reference evaluates these rational fits with double literals and rounds num/den to float
+    double x1 = x, x2 = (double)(x*x), x3 = (double)((x*x)*x);
+    float num = (float)(n0 + n1*x1 + n2*x2 + n3*x3), den = (float)(d0 + d1*x1 + d2*x2 + d3*x3);
+    return num / den;
+  }
+  template<int N> BBMCU_D static Dual<N> ratfit(const Dual<N>& x, float n0, float n1, float n2, float n3, float d0, float d1, float d2, float d3)
+  {
+    float v = x.v, num = n0 + v*(n1 + v*(n2 + v*n3)), den = d0 + v*(d1 + v*(d2 + v*d3));
+    float dn = n1 + v*(2.0f*n2 + v*3.0f*n3), dd = d1 + v*(2.0f*d2 + v*3.0f*d3);
+    return chain(x, ratfit(v, n0, n1, n2, n3, d0, d1, d2, d3), (dn*den - num*dd)/(den*den));
+  }
+  template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
+    if(!(v.z < 0.99999988079071044921875f)) return T(1.0f);
+    T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    const T& gamma = a[NA-1];
+    T sx = v.x*ax, sy = v.y*ay;
+    T z = v.z * m_rsqrt(sx*sx + sy*sy);
+    T S1 = m_pow((gamma - 1.0f) + z*z, 1.5f - gamma) / z;
+    T F21 = ratfit(z, 0.0f, 1.066f, 2.655f, 4.892f, 1.038f, 2.969f, 4.305f, 4.418f);
+    T F22 = ratfit(gamma, 14.402f, -27.145f, 20.574f, -2.745f, -30.612f, 86.567f, -84.341f, 29.938f);
+    T F23 = ratfit(gamma, -129.404f, 324.987f, -299.305f, 93.268f, -92.609f, 256.006f, -245.663f, 86.064f);
+    T F24 = ratfit(z, 6.537f, 6.074f, -0.623f, 5.223f, 6.538f, 6.103f, -3.218f, 6.347f);
+    T S2 = F21 * (F22 + F23*F24);
+    T S1s = m_pow(gamma - 1.0f, gamma) / (2.0f*gamma - 3.0f);
+    T lambda = m_tgamma(gamma - 0.5f) / m_tgamma(gamma) * kInvSqrtPi * (S1s*S1 + m_sqrt(gamma - 1.0f)*S2) - 0.5f;
+    return 1.0f / (1.0f + lambda);
+  }
+  BBMCU_D static float pdf(f3, f3 m, const float* a)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    float p = D<float>(m, a) * m.z;
+    return (p > 0.0f) ? p : 0.0f;
+  }
+  BBMCU_D static f3 sample(f3, f2 xi, const float* a)
+  {
+    if(!xi_valid(xi)) return make_f3(0, 0, 0);
+    float gamma = a[NA-1];
+    float cp = cosf(kTwoPi * xi.x), sp = sinf(kTwoPi * xi.x);
+    float nrm;
+    if(ANISO) {
+      float qx = cp/a[0], qy = sp/a[1];
+      nrm = 1.0f / (qx*qx + qy*qy);
+      cp *= a[0]; sp *= a[1];
+      float r = 1.0f/sqrtf(cp*cp + sp*sp); cp *= r; sp *= r;
+    }
+    else nrm = a[0]*a[0];
+    float tan2 = (float)((pow((double)xi.y, 1.0 / (1.0 - (double)gamma)) - 1.0) * (double)(gamma - 1.0f) * (double)nrm);
+    float cosT = (float)(1.0 / sqrt(1.0 + (double)tan2));
+    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    return make_f3(cp*sinT, sp*sinT, cosT);
+  }
+};
+
+// ---- Shifted Gamma Distribution (ndf/sgd.h), spectral.  Attribute block in reflection order:
+//      K[3] Lambda[3] c[3] theta0[3] k[3] (Dependent) then alpha[3] p[3] ----------------------------
+struct NdfSGD
+{
+  static constexpr int NA = 21;
+  template<class T> BBMCU_D static T D1(float tan2, float c4pi, const T& alpha, const T& p, const T& K)
+  {
+    T temp = alpha + tan2/alpha;
+    T den = m_pow(temp, p);
+    T P22 = (den > kEps) ? m_exp(-temp)/den : T(0.0f);
+    return P22 / c4pi * K;
+  }
+  template<class T> BBMCU_D static Spec<T> D(f3 h, const T* a)
+  {
+    if(!(h.z > 0.0f)) return Spec<T>(T(0.0f));
+    float tan2 = tanTheta2(h);
+    float c2 = h.z*h.z;
+    float c4pi = kPi * (float)((double)c2*(double)c2);   // Pi * pow(cos, 4.0)
+    return Spec<T>(D1(tan2, c4pi, a[15], a[18], a[0]), D1(tan2, c4pi, a[16], a[19], a[1]), D1(tan2, c4pi, a[17], a[20], a[2]));
+  }
+  template<class T> BBMCU_D static T G11(float theta, const T& Lambda, const T& c, const T& theta0, const T& k)
+  {
+    if(!(theta > val(theta0))) return T(1.0f);
+    return 1.0f + Lambda*(1.0f - m_exp(c*m_pow(theta - theta0, k)));
+  }
+  template<class T> BBMCU_D static Spec<T> G1(f3 v, f3 m, const T* a)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return Spec<T>(T(0.0f));
+    float theta = sph_theta(v);
+    return Spec<T>(G11(theta, a[3], a[6], a[9], a[12]), G11(theta, a[4], a[7], a[10], a[13]), G11(theta, a[5], a[8], a[11], a[14]));
+  }
+  BBMCU_D static float avg_alpha(const float* a) { return ((a[15] + a[16]) + a[17]) / 3.0f; }
+  BBMCU_D static float pdf(f3 view, f3 m, const float* a) { float al = avg_alpha(a); return NdfGGX<false>::pdf(view, m, &al); }
+  BBMCU_D static f3 sample(f3 view, f2 xi, const float* a) { float al = avg_alpha(a); return NdfGGX<false>::sample(view, xi, &al); }
+};
+
+// =============================================================================================
+// Joint masking-shadowing
+// =============================================================================================
+BBMCU_D bool g_mask(f3 in, f3 out, f3 m) { return (dot(in, m) > 0.0f) && (dot(out, m) > 0.0f); }
+
+struct GVGroove {
+  template<class NDF, class T> BBMCU_D static auto eval(f3 in, f3 out, f3 m, const T* a) -> decltype(NDF::template G1<T>(in, m, a))
+  {
+    using R = decltype(NDF::template G1<T>(in, m, a));
+    if(!g_mask(in, out, m)) return R(T(0.0f));
+    // min(1.0, min(2.0*m.z*in.z/(in.m), 2.0*m.z*out.z/(out.m))) in double, rounded (vgroove.h:41-46)
+    double gi = 2.0*(double)m.z*(double)in.z/(double)dot(in, m);
+    double go = 2.0*(double)m.z*(double)out.z/(double)dot(out, m);
+    return R(T((float)fmin(1.0, fmin(gi, go))));
+  }
+};
+struct GUncorrelated {
+  template<class NDF, class T> BBMCU_D static auto eval(f3 in, f3 out, f3 m, const T* a) -> decltype(NDF::template G1<T>(in, m, a))
+  {
+    using R = decltype(NDF::template G1<T>(in, m, a));
+    if(!g_mask(in, out, m)) return R(T(0.0f));
+    return NDF::template G1<T>(in, m, a) * NDF::template G1<T>(out, m, a);
+  }
+};
+struct GHeightCorrelated {
+  template<class NDF, class T> BBMCU_D static T eval(f3 in, f3 out, f3 m, const T* a)
+  {
+    if(!g_mask(in, out, m)) return T(0.0f);
+    T gi = NDF::template G1<T>(in, m, a), go = NDF::template G1<T>(out, m, a);
+    T gio = gi*go;
+    T den = gi + go - gio;
+    return (den > kEps) ? gio/den : T(0.0f);
+  }
+};
+struct GVanGinneken {
+  template<class NDF, class T> BBMCU_D static T eval(f3 in, f3 out, f3 m, const T* a)
+  {
+    if(!g_mask(in, out, m)) return T(0.0f);
+    float phi = fabsf(sph_phi(in) - sph_phi(out));                 // un-wrapped, as the reference (vanginneken.h:50)
+    float lambda = (float)(4.41*(double)phi / (4.41*(double)phi + 1.0));
+    T gi = NDF::template G1<T>(in, m, a), go = NDF::template G1<T>(out, m, a);
+    T gio = gi*go;
+    T den = m_max(gi, go) + lambda*(m_min(gi, go) - gio);
+    return (den > kEps) ? gio/den : T(0.0f);
+  }
+};
+
+// =============================================================================================
+// microfacet<NDF, G, F, NormalizationFactor>, optionally scaled by a leading RGB attribute.
+// Attribute block: [scale rgb (if SCALED)] [NDF attributes] [Fresnel attributes]
+// NORM: 0 Unnormalized (1.0), 1 Walter (4.0), 2 Cook (pi as double)   (microfacet.h:31-36)
+// =============================================================================================
+template<class NDF, class G, class F, int NORM, bool SCALED>
+struct Microfacet
+{
+  static constexpr int SCALE = SCALED ? 0 : -1;
+  static constexpr int OFF_NDF = SCALED ? 3 : 0;
+  static constexpr int OFF_F = OFF_NDF + NDF::NA;
+  static constexpr int NA = OFF_F + F::NA;
+  BBMCU_HD static constexpr double norm() { return NORM == 0 ? 1.0 : (NORM == 1 ? 4.0 : kPiD); }
+
+  // eval without the leading scale (microfacet.h:74-102)
+  template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<T>(T(0.0f));
+    f3 h = halfway(in, out);
+    float inh = dot(in, h), outh = dot(out, h);
+    auto D = NDF::template D<T>(h, a + OFF_NDF);
+    auto Gv = G::template eval<NDF, T>(in, out, h, a + OFF_NDF);
+    auto Fv = F::template eval<T>(a + OFF_F, 0.5f*(inh + outh));
+    // D*G*F / NormalizationFactor / (z_in z_out): the division chain runs in double in the reference
+    Spec<T> dgf = to_spec(D) * to_spec(Gv) * to_spec(Fv);
+    return divide_out(dgf, in.z*out.z);
+  }
+  BBMCU_D static Spec<float> divide_out(const Spec<float>& s, float zz)
+  {
+    double n = norm(), z = zz;
+    return Spec<float>((float)((double)s.r / n / z), (float)((double)s.g / n / z), (float)((double)s.b / n / z));
+  }
+  template<int N> BBMCU_D static Spec<Dual<N>> divide_out(const Spec<Dual<N>>& s, float zz)
+  {
+    Spec<float> v = divide_out(Spec<float>(s.r.v, s.g.v, s.b.v), zz);
+    float k = 1.0f / ((float)norm() * zz);
+    Spec<Dual<N>> r = s * k;
+    r.r.v = v.r; r.g.v = v.g; r.b.v = v.b;
+    return r;
+  }
+  template<class T> BBMCU_D static Spec<T> eval(f3 in, f3 out, const T* a, int component)
+  {
+    Spec<T> r = eval_unscaled<T>(in, out, a, component);
+    if(SCALED) r = r * load_spec(a);
+    return r;
+  }
+  // pdf(h) / (4 |out.h|)  (microfacet.h:154-174)
+  BBMCU_D static float pdf(f3 in, f3 out, const float* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !((out.z > 0.0f) && (in.z > 0.0f))) return 0.0f;
+    f3 h = halfway(in, out);
+    if(h.z < 0.0f) h = -h;
+    return (float)((double)NDF::pdf(out, h, a + OFF_NDF) / (4.0 * (double)fabsf(dot(out, h))));
+  }
+  BBMCU_D static void sample(f3 out, f2 xi, const float* a, int component, f3& dir, float& pdfv, int& flag)
+  {
+    dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
+    if(!(component & FLAG_SPECULAR) || !xi_valid(xi) || !(out.z > 0.0f)) return;
+    f3 m = NDF::sample(out, xi, a + OFF_NDF);
+    dir = reflect(out, m);
+    pdfv = pdf(dir, out, a, component);
+    flag = FLAG_SPECULAR;
+  }
+  // perfect-mirror approximation F(eta, out.z) / N * 4.0 (microfacet.h:186-199), times scale
+  BBMCU_D static Spec<float> reflectance(f3 out, const float* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !(out.z > 0.0f)) return Spec<float>(0.0f);
+    Spec<float> f = to_spec(F::template eval<float>(a + OFF_F, out.z));
+    double n = norm();
+    Spec<float> r((float)((double)f.r / n * 4.0), (float)((double)f.g / n * 4.0), (float)((double)f.b / n * 4.0));
+    if(SCALED) r = r * load_spec(a);
+    return r;
+  }
+};
+
+} // namespace bbmcu

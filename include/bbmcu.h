@@ -1,0 +1,162 @@
+/* bbmcu.h - C ABI of libbbmcu.so, the B200 (sm_100a) CUDA backbone for bbm's data-parallel hot path:
+ * batched BSDF eval / sample / pdf / reflectance for the 34 analytic models, the MERL and spherical
+ * linearizers, the six fitting metrics (loss + analytic parameter gradient) and .fit / BSDF-string I/O.
+ *
+ * The reference (bsdfbenchmark/bbm 0.5.1) has no C ABI on this path: its boundary is a set of C++20
+ * concepts.  Each entry point below names the reference interface it stands in for; INTEGRATION.md
+ * shows the C++ adapter a bbm maintainer would add on top (backbone/cuda).
+ *
+ * Conventions
+ *  - every function returns 0 on success; on failure a non-zero bbmcu_status and a message readable
+ *    through bbmcu_last_error(ctx) (the reference throws std::invalid_argument from its parsers,
+ *    core/stringconvert.h:68,517,540,565, and std::runtime_error elsewhere, core/error.h:42-46).
+ *  - direction / spectrum buffers are struct-of-arrays: an `xyz` (or `rgb`) pointer addresses three
+ *    consecutive planes of n floats (x[n], y[n], z[n]); `uv` two planes.  The reference is
+ *    array-of-structs (std::array<float,3>, backbone/native/include/backbone/array.h:27); adapters
+ *    transpose at the host boundary only.
+ *  - data pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).  Device
+ *    pointers run in place on the context's stream; host pointers are staged through pinned memory
+ *    in chunks, copies overlapped with the kernels.  The caller owns every buffer.
+ *  - there is no CPU fallback: without a usable CUDA device bbmcu_init fails.
+ *  - one context per host thread per device; calls on one context are serialised on its stream.
+ */
+#ifndef BBMCU_H_
+#define BBMCU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define BBMCU_API __attribute__((visibility("default")))
+#else
+#define BBMCU_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bbmcu_ctx bbmcu_ctx;      /* device, stream, staging buffers, precomputed tables           */
+typedef struct bbmcu_bsdf bbmcu_bsdf;    /* = bbm::bsdf_ptr<floatRGB>  (include/bbm/bsdf_ptr.h:20-165)     */
+typedef struct bbmcu_loss bbmcu_loss;    /* = a bbm::sampledlossfunction (include/bbm/sampledlossfunction.h:26-95) */
+
+typedef enum { BBMCU_OK = 0, BBMCU_INVALID_ARGUMENT = 1, BBMCU_RUNTIME_ERROR = 2, BBMCU_CUDA_ERROR = 3, BBMCU_OUT_OF_RANGE = 4 } bbmcu_status;
+
+/* bbm::bsdf_flag (include/bbm/bsdf_flag.h:21-27) and bbm::unit_t (include/bbm/unit.h:20-24) */
+enum { BBMCU_NONE = 0, BBMCU_DIFFUSE = 1, BBMCU_SPECULAR = 2, BBMCU_ALL = 3 };
+enum { BBMCU_RADIANCE = 0, BBMCU_IMPORTANCE = 1 };
+/* bbm::bsdf_attr (include/bbm/bsdf_attr_flag.h:17-31) */
+enum { BBMCU_ATTR_DIFFUSE_SCALE = 1, BBMCU_ATTR_DIFFUSE_PARAMETER = 2, BBMCU_ATTR_SPECULAR_SCALE = 4,
+       BBMCU_ATTR_SPECULAR_PARAMETER = 8, BBMCU_ATTR_DEPENDENT = 16, BBMCU_ATTR_ALL = 15 };
+/* the six metrics of include/loss/cosine_weighted_l2.h and cosine_weighted_log.h */
+enum { BBMCU_NGAN_L2 = 0, BBMCU_LOW_L2 = 1, BBMCU_BIERON_L2 = 2, BBMCU_LOW_LOG = 3, BBMCU_BIERON_LOG = 4, BBMCU_STANDARD_LOG = 5 };
+/* which vector bbmcu_bsdf_get_params returns: parameter_values / _default_values / _lower_bound / _upper_bound
+ * (include/bbm/bsdf_enumerate.h:102-237) */
+enum { BBMCU_PARAM_VALUE = 0, BBMCU_PARAM_DEFAULT = 1, BBMCU_PARAM_LOWER = 2, BBMCU_PARAM_UPPER = 3 };
+
+/* ---- context -------------------------------------------------------------------------------------- */
+BBMCU_API int  bbmcu_init(int device, bbmcu_ctx** out);
+BBMCU_API void bbmcu_destroy(bbmcu_ctx* ctx);
+BBMCU_API const char* bbmcu_last_error(bbmcu_ctx* ctx);          /* ctx may be NULL: error of the last failed call on this thread */
+BBMCU_API int  bbmcu_synchronize(bbmcu_ctx* ctx);
+BBMCU_API void* bbmcu_stream(bbmcu_ctx* ctx);                    /* the cudaStream_t all work of this context is issued on */
+BBMCU_API uint64_t bbmcu_launch_count(bbmcu_ctx* ctx);           /* kernels launched by this context so far */
+
+/* ---- model registry (replaces the BBM_EXPORT_BSDFMODEL tables, include/export/bbm_fromstring.h:48-49) -- */
+typedef struct {
+  const char* name;      /* attribute name as printed by toString                                    */
+  int width;             /* scalars in this attribute                                                  */
+  int rows;              /* 1, or 2 for [[..],[..]] attributes (complex RGB ior, Bagher F0/F1)        */
+  int flag;              /* one BBMCU_ATTR_* bit                                                       */
+  int offset;            /* first float of the attribute in the model's attribute block               */
+} bbmcu_attr;
+BBMCU_API int  bbmcu_model_count(void);                          /* 34 */
+BBMCU_API const char* bbmcu_model_name(int model_id);
+BBMCU_API int  bbmcu_model_lookup(const char* name, int* model_id);
+BBMCU_API int  bbmcu_model_layout(int model_id, bbmcu_attr* attrs, int* n_attrs);   /* reflection order (util/reflection.h:141-148) */
+
+/* ---- BSDF objects: bsdf_import / toString / parameter enumeration ------------------------------------ */
+/* bbm::bsdf_import<floatRGB>(str) (include/bbm/bsdf_import.h:22-26): "Model(args)" or "Aggregate(m1, m2, ...)" */
+BBMCU_API int  bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out);
+BBMCU_API void bbmcu_bsdf_free(bbmcu_bsdf* bsdf);
+BBMCU_API int  bbmcu_bsdf_to_string(const bbmcu_bsdf* bsdf, char* buf, size_t cap);           /* bsdf_ptr::toString */
+BBMCU_API int  bbmcu_bsdf_param_count(const bbmcu_bsdf* bsdf, int attr_flags);
+BBMCU_API int  bbmcu_bsdf_get_params(const bbmcu_bsdf* bsdf, int which, int attr_flags, double* values, int* count);
+BBMCU_API int  bbmcu_bsdf_set_params(bbmcu_bsdf* bsdf, int attr_flags, const double* values, int count);
+
+/* ---- batched BSDF concept (include/concepts/bsdfmodel.h:32-146; include/bbm/bsdf_base.h:76-129) --------- */
+BBMCU_API int  bbmcu_eval(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                const float* in_xyz, const float* out_xyz, size_t n, float* rgb);
+BBMCU_API int  bbmcu_sample(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                  const float* out_xyz, const float* xi_uv, size_t n, float* dir_xyz, float* pdf, int32_t* flag);
+BBMCU_API int  bbmcu_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+               const float* in_xyz, const float* out_xyz, size_t n, float* pdf);
+BBMCU_API int  bbmcu_reflectance(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                       const float* out_xyz, size_t n, float* rgb);
+/* one fused pass of the checkBsdf-style inner loop (bin/checkBsdf.cpp:206-267):
+ *   s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)          */
+BBMCU_API int  bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                           const float* out_xyz, const float* xi_uv, size_t n,
+                           float* dir_xyz, float* sample_pdf, int32_t* flag, float* rgb, float* pdf);
+
+/* ---- linearizers (include/linearizer/merl_linearizer.h:50-123, spherical_linearizer.h:37-111) --------- */
+#define BBMCU_MERL_BINS 1458000u
+/* merl_linearizer(in, out): bin index, BBMCU_MERL_BINS for pairs below the horizon, 0xFFFFFFFF for NaN input */
+BBMCU_API int  bbmcu_merl_index(bbmcu_ctx* ctx, const float* in_xyz, const float* out_xyz, size_t n, uint32_t* index);
+/* merl_linearizer(idx) for idx = first .. first+n-1 */
+BBMCU_API int  bbmcu_merl_dirs(bbmcu_ctx* ctx, uint32_t first, size_t n, float* in_xyz, float* out_xyz);
+typedef struct {
+  uint32_t samples_in[2], samples_out[2];   /* (phi, theta) counts                                     */
+  float start_in[2], end_in[2];             /* (phi, theta) ranges; Hemisphere = (2 pi, pi/2)          */
+  float start_out[2], end_out[2];
+} bbmcu_spherical_grid;
+BBMCU_API void bbmcu_spherical_grid_default(bbmcu_spherical_grid* g, uint32_t in_phi, uint32_t in_theta, uint32_t out_phi, uint32_t out_theta);
+BBMCU_API int  bbmcu_spherical_dirs(bbmcu_ctx* ctx, const bbmcu_spherical_grid* grid, uint64_t first, size_t n, float* in_xyz, float* out_xyz);
+
+/* ---- measured data (include/staticmodel/merl.h:78-96,173-206) --------------------------------------------- */
+/* read a MERL binary (3 x u32 dims = 90,90,180 then 3 planar double[N]; negative -> 0; scaled by
+ * 1/1500, 1.15/1500, 1.66/1500) into `rgb` (3 planes of BBMCU_MERL_BINS floats, HOST memory) */
+BBMCU_API int  bbmcu_merl_read(bbmcu_ctx* ctx, const char* filename, float* rgb);
+BBMCU_API int  bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb);     /* inverse of the above */
+
+/* ---- losses (include/loss/*.h, include/bbm/sampledlossfunction.h:62-87) ---------------------------------- */
+/* The reference evaluates  loss = (1/N) sum_i e(in_i, out_i, fitted.eval(in_i,out_i), reference.eval(in_i,out_i))
+ * over a linearizer.  A bbmcu_loss fixes metric, linearizer, component and the reference operand; the
+ * reference values are tabulated once per sample index (they never change during a fit).
+ *   grid == NULL: merl_linearizer (N = BBMCU_MERL_BINS), else the spherical grid.
+ *   reference is ONE of: an analytic bsdf (reference_bsdf), or a measured MERL table
+ *   (reference_merl_rgb: 3 planes of BBMCU_MERL_BINS floats, host or device), looked up per sample with
+ *   merl_linearizer(in, out) exactly as merl_data::eval does.
+ *   first/count select the shard [first, first+count) of the sample axis this context owns (multi-GPU);
+ *   count == 0 means all N.  Losses and gradients are returned as SUMS over the shard divided by the
+ *   FULL N, so summing over shards (ncclAllReduce) gives the reference's mean. */
+BBMCU_API int  bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
+                       const bbmcu_bsdf* reference_bsdf, const float* reference_merl_rgb,
+                       uint64_t first, uint64_t count, bbmcu_loss** out);
+BBMCU_API void bbmcu_loss_free(bbmcu_loss* loss);
+BBMCU_API uint64_t bbmcu_loss_samples(const bbmcu_loss* loss);      /* N of the linearizer (sampledlossfunction::samples) */
+/* loss (and, if grad != NULL, d loss / d parameter) of `bsdf` at K parameter vectors.
+ * params: K x P row-major, P = bbmcu_bsdf_param_count(bsdf, BBMCU_ATTR_ALL), forward enumeration order;
+ * params == NULL with K == 1 evaluates the bsdf's current parameters.  loss: K doubles; grad: K x P doubles.
+ * Host pointers.  device_out (may be NULL): if given, a DEVICE buffer of K*(1+P) doubles that receives
+ * [loss_k, grad_k...] rows and no host copy/synchronisation is done (for the NCCL all-reduce). */
+BBMCU_API int  bbmcu_loss_eval(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
+                     double* loss_out, double* grad_out, double* device_out);
+/* per-sample terms l(idx) of the shard (sampledlossfunction::operator()(idx)); `terms` = count floats */
+BBMCU_API int  bbmcu_loss_terms(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, float* terms);
+
+/* ---- .fit files (include/io/fit.h:34-77) -------------------------------------------------------------- */
+typedef struct bbmcu_fit bbmcu_fit;
+BBMCU_API int  bbmcu_fit_import(bbmcu_ctx* ctx, const char* filename, bbmcu_fit** out);
+BBMCU_API int  bbmcu_fit_count(const bbmcu_fit* fit);
+BBMCU_API const char* bbmcu_fit_key(const bbmcu_fit* fit, int i);
+BBMCU_API int  bbmcu_fit_bsdf(const bbmcu_fit* fit, int i, bbmcu_bsdf** out);     /* a copy the caller frees */
+BBMCU_API int  bbmcu_fit_create(bbmcu_fit** out);
+BBMCU_API int  bbmcu_fit_add(bbmcu_fit* fit, const char* key, const bbmcu_bsdf* bsdf);
+BBMCU_API int  bbmcu_fit_export(bbmcu_ctx* ctx, const bbmcu_fit* fit, const char* filename, const char* comment);
+BBMCU_API void bbmcu_fit_free(bbmcu_fit* fit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBMCU_H_ */

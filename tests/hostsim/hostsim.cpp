@@ -1,0 +1,93 @@
+// TEST INFRASTRUCTURE ONLY.  The device headers of bbm_b200/csrc compiled for the HOST with g++
+// (every model function is __host__ __device__), so the model / linearizer / loss arithmetic can be
+// checked against the reference on a machine without a GPU.  Nothing in the product loads this
+// library; the product path is libbbmcu.so and fails without a CUDA device.
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include "bbmcu_desc.hpp"
+#include "bbmcu_kernels.cuh"
+#include "bbmcu_lossop.cuh"
+
+using namespace bbmcu;
+
+static thread_local std::string g_err;
+#define GUARD(...) try { __VA_ARGS__; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
+
+template<class Op> static void run(const Op& op, size_t n) { for(size_t i=0; i < n; i += kVec) op.group(i); }
+
+extern "C" {
+const char* hostsim_last_error() { return g_err.c_str(); }
+
+int hostsim_eval(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
+{ GUARD( EvalOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_pdf(const char* bsdf, int component, const float* in, const float* out, size_t n, float* pdf)
+{ GUARD( PdfOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.in = in; op.out = out; op.pdf = pdf; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_reflectance(const char* bsdf, int component, const float* out, size_t n, float* rgb)
+{ GUARD( ReflectanceOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_sample(const char* bsdf, int component, const float* out, const float* xi, size_t n, float* dir, float* pdf, int32_t* flag)
+{ GUARD( SampleOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.out = out; op.xi = xi; op.dir = dir; op.pdf = pdf; op.flag = flag; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_merl_index(const float* in, const float* out, size_t n, uint32_t* index)
+{ GUARD( MerlIndexOp op; op.in = in; op.out = out; op.index = index; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_merl_dirs(uint32_t first, size_t n, float* in, float* out)
+{ GUARD( MerlDirsOp op; op.first = first; op.in = in; op.out = out; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_spherical_dirs(const uint32_t* samples, const float* ranges, uint64_t first, size_t n, float* in, float* out)
+{
+  GUARD(
+    SphericalDirsOp op; SphericalGrid& g = op.grid;
+    g.n_in_phi = samples[0]; g.n_in_theta = samples[1]; g.n_out_phi = samples[2]; g.n_out_theta = samples[3];
+    g.start_in_phi = ranges[0]; g.start_in_theta = ranges[1]; g.size_in_phi = ranges[2] - ranges[0]; g.size_in_theta = ranges[3] - ranges[1];
+    g.start_out_phi = ranges[4]; g.start_out_theta = ranges[5]; g.size_out_phi = ranges[6] - ranges[4]; g.size_out_theta = ranges[7] - ranges[5];
+    op.first = first; op.in = in; op.out = out; op.n = n; op.aligned = false; run(op, n);
+  )
+}
+
+// glibc-port checks: the restated atan2f / sinf / cosf against this host's libm
+float hostsim_atan2f(float y, float x) { return glibc_atan2f(y, x); }
+float hostsim_sinf(float x) { return glibc_sinf(x); }
+float hostsim_cosf(float x) { return glibc_cosf(x); }
+size_t hostsim_libm_mismatches(int which, const float* a, const float* b, size_t n)
+{
+  size_t bad = 0;
+  for(size_t i=0; i < n; ++i)
+  {
+    float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : glibc_cosf(a[i]);
+    float ref = which == 0 ? atan2f(a[i], b[i]) : which == 1 ? sinf(a[i]) : cosf(a[i]);
+    uint32_t u, v; std::memcpy(&u, &mine, 4); std::memcpy(&v, &ref, 4);
+    bad += (u != v);
+  }
+  return bad;
+}
+
+// loss / gradient of ONE parameter set over explicit samples (directions + reference values), host loop
+int hostsim_loss(const char* bsdf, int metric, int component, const float* in, const float* out, const float* ref, size_t n, double inv_n,
+                 double* loss, double* grad, float* terms)
+{
+  GUARD(
+    auto b = bbmcu_host::parse_bsdf(bsdf);
+    BsdfDesc d = make_desc(b);
+    int P = b.param_count(15);
+    std::vector<double> acc(1 + P, 0.0);
+    for(size_t i=0; i < n; ++i)
+    {
+      f3 a = make_f3(in[i], in[n+i], in[2*n+i]), o = make_f3(out[i], out[n+i], out[2*n+i]);
+      Spec<float> r(ref[i], ref[n+i], ref[2*n+i]);
+      float g[kMaxParams];
+      float e = loss_sample_generic(d, metric, component, a, o, r, grad ? g : nullptr);
+      if(terms) terms[i] = e;
+      acc[0] += (double)e;
+      if(grad) for(int j=0; j < P; ++j) acc[1+j] += (double)g[j];
+    }
+    *loss = acc[0] * inv_n;
+    if(grad) for(int j=0; j < P; ++j) grad[j] = acc[1+j] * inv_n;
+  )
+}
+} // extern "C"
