@@ -34,9 +34,10 @@ template<class T> BBMCU_D T fresnel_cook(const T& eta, float c)
   return m_max(0.5f * (a*a) * (1.0f + b*b), 0.0f);
 }
 // Schlick of a reflectance at normal incidence: R0 + (1-R0) * pow(1-c, 5.0)  (fresnel_schlick.h:48-51).
-// The reference's pow(float, 5.0) runs in double and is rounded once.
-BBMCU_D float schlick_w(float c) { double w = 1.0 - (double)c; double w2 = w*w; return (float)(w2*w2*w); }
-template<class T> BBMCU_D T fresnel_schlick(const T& R0, float c) { return R0 + (1.0f - R0) * schlick_w(c); }
+// pow(float, 5.0) is a double, so the product and the sum run in double and are rounded once.
+BBMCU_D double schlick_w(float c) { double w = (double)(1.0f - c); double w2 = w*w; return w2*w2*w; }
+BBMCU_D float fresnel_schlick(float R0, float c) { return (float)((double)R0 + (double)(1.0f - R0) * schlick_w(c)); }
+template<int N> BBMCU_D Dual<N> fresnel_schlick(const Dual<N>& R0, float c) { float w = (float)schlick_w(c); Dual<N> r = R0 + (1.0f - R0) * w; r.v = fresnel_schlick(R0.v, c); return r; }
 
 // Conductor Fresnel, Shirley 1985 in real arithmetic (fresnel_complex.h:31-50)
 template<class T> BBMCU_D T fresnel_complex(const T& n, const T& k, float c)

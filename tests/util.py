@@ -1,0 +1,54 @@
+"""Parity comparison used by every test (SURVEY.md section 8c "Parity definitions")."""
+import numpy as np
+
+# models whose CUDA kernels exist in this build; the golden fixtures cover all 34
+IMPLEMENTED = None
+
+
+def implemented_models():
+    global IMPLEMENTED
+    if IMPLEMENTED is None:
+        import re, os
+        src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bbm_b200", "build.py")).read()
+        import bbm_b200 as bb
+        names = bb.model_names()
+        missing = set()
+        if "-DBBMCU_WITH_EPD" not in re.sub(r"#.*", "", src):
+            missing |= {"EPD"}
+        if "-DBBMCU_WITH_HE" not in re.sub(r"#.*", "", src):
+            missing |= {"He", "HeWestin", "HeHolzschuch", "NganHe"}
+        IMPLEMENTED = [n for n in names if n not in missing]
+    return IMPLEMENTED
+
+
+def uses_only_implemented(bsdf_string):
+    import re
+    names = re.findall(r"([A-Za-z]+)\(", bsdf_string)
+    ok = set(implemented_models()) | {"Aggregate"}
+    return all(n in ok for n in names)
+
+
+def mismatch(got, want, rel=1e-5, floor=1e-30):
+    """boolean array of elements violating: NaN matches NaN, +-Inf matches the same Inf, otherwise
+    |got - want| <= rel * |want| where |want| > floor, else |got| <= floor-scale absolute."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    nan_ok = np.isnan(got) & np.isnan(want)
+    inf_ok = np.isinf(got) & np.isinf(want) & (np.sign(got) == np.sign(want))
+    with np.errstate(invalid="ignore"):
+        close = np.abs(got - want) <= rel * np.abs(want) + floor
+    return ~(nan_ok | inf_ok | (close & np.isfinite(got) & np.isfinite(want)))
+
+
+def assert_parity(got, want, rel=1e-5, floor=1e-30, what="", max_bad=0):
+    bad = mismatch(got, want, rel, floor)
+    nbad = int(bad.sum())
+    if nbad > max_bad:
+        idx = np.argwhere(bad)[:5]
+        g, w = np.asarray(got), np.asarray(want)
+        lines = [f"  at {tuple(i)}: got {g[tuple(i)]!r} want {w[tuple(i)]!r}" for i in idx]
+        raise AssertionError(f"{what}: {nbad} of {bad.size} elements differ beyond rel {rel}\n" + "\n".join(lines))
+
+
+def soa(a):
+    return np.ascontiguousarray(np.asarray(a, np.float32).T)
