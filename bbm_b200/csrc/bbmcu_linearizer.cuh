@@ -157,11 +157,11 @@ BBMCU_D uint32_t merl_index(f3 in, f3 out)
   if(pd >= kPi) pd = pd - kPi;
   float iDp = floorf((pd / kPi + kEps) * 180.0f);
   float iDt = floorf((td / kHalfPi + kEps) * 90.0f);
-  float iHt = floorf(sqrtf(fmaxf(th / kHalfPi + kEps, 0.0f)) * 90.0f);
+  float iHt = floorf(m_safe_sqrt(th / kHalfPi + kEps) * 90.0f);
   // phi_h index: floor(safe_sqrt(ph / pi + eps) * 1) clamped to [0, 0]
-  iDp = fminf(fmaxf(iDp, 0.0f), 179.0f);
-  iDt = fminf(fmaxf(iDt, 0.0f), 89.0f);
-  iHt = fminf(fmaxf(iHt, 0.0f), 89.0f);
+  iDp = clampf(iDp, 0.0f, 179.0f);        // std::clamp: NaN stays NaN
+  iDt = clampf(iDt, 0.0f, 89.0f);
+  iHt = clampf(iHt, 0.0f, 89.0f);
   float idx = (iHt*90.0f + iDt)*180.0f + iDp;
   if(!(idx == idx)) return 0xFFFFFFFFu;
   return (uint32_t)idx;

@@ -36,8 +36,8 @@ BBMCU_D void lambert_sample(f3 out, f2 xi, int component, f3& dir, float& pdfv, 
   dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
   if(!(component & FLAG_DIFFUSE) || !xi_valid(xi)) return;
   float ph = xi.x * kTwoPi;
-  float sinT = (float)sqrt(fmax(1.0 - (double)xi.y, 0.0));
-  dir = make_f3(cosf(ph)*sinT, sinf(ph)*sinT, sqrtf(fmaxf(xi.y, 0.0f)));
+  float sinT = (float)safe_sqrt_d(1.0 - (double)xi.y);
+  dir = make_f3(cosf(ph)*sinT, sinf(ph)*sinT, m_safe_sqrt(xi.y));
   pdfv = lambert_pdf(dir, out, component);
   flag = FLAG_DIFFUSE;
 }
@@ -91,7 +91,7 @@ BBMCU_D f3 sample_power_lobe(f2 xi, float n)
 {
   float ph = xi.x * kTwoPi;
   float cosT = (float)pow((double)xi.y, 1.0 / (double)(n + 1.0f));
-  float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+  float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
   return make_f3(cosf(ph)*sinT, sinf(ph)*sinT, cosT);
 }
 
@@ -229,7 +229,7 @@ struct Ward
     float rn = 1.0f / sqrtf(cx*cx + cy*cy); cx *= rn; cy *= rn;
     float qx = cx/rx, qy = cy/ry;
     float cosT = (float)(1.0 / sqrt(1.0 - (double)(logf(xi.y) / (qx*qx + qy*qy))));
-    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     dir = reflect(out, make_f3(cx*sinT, cy*sinT, cosT));
     pdfv = pdf(dir, out, a, component);
     flag = FLAG_SPECULAR;
@@ -298,7 +298,7 @@ struct AshikhminShirley
       cp = cosf(ph); sp = sinf(ph);
       cosT = (float)pow((double)xi.y, 1.0 / ((double)a[OFF_N] + 1.0));
     }
-    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     dir = reflect(out, make_f3(cp*sinT, sp*sinT, cosT));
     pdfv = pdf(dir, out, a, component);
     flag = FLAG_SPECULAR;
@@ -383,7 +383,7 @@ struct LowSmooth
   {
     float sx = in.x + out.x, sy = in.y + out.y, dx = in.x - out.x, dy = in.y - out.y;
     float Dp2 = sx*sx + sy*sy;
-    float cosD = (float)sqrt(fmax(1.0 - 0.25*(double)(dx*dx + dy*dy), 0.0));
+    float cosD = (float)safe_sqrt_d(1.0 - 0.25*(double)(dx*dx + dy*dy));
     S = pow_s(a[3], a[4], Dp2);
     Q = fresnel_cook(a[5], cosD);
   }
@@ -403,7 +403,7 @@ struct LowSmooth
     if(!(component & FLAG_SPECULAR) || !((in.z >= 0.0f) && (out.z >= 0.0f))) return 0.0f;
     float B = a[3], ro2;
     float t = md_temp(out, B, ro2);
-    t = -logf(2.0f) + logf(1.0f + B*(1.0f - ro2) + sqrtf(fmaxf(t, 0.0f)));
+    t = -logf(2.0f) + logf(1.0f + B*(1.0f - ro2) + m_safe_sqrt(t));
     float Md = B * kInvPi * (1.0f / t);
     float sx = in.x + out.x, sy = in.y + out.y;
     float p = (float)((double)Md / (1.0 + (double)(B*(sx*sx + sy*sy))));
@@ -415,15 +415,15 @@ struct LowSmooth
     if(!(component & FLAG_SPECULAR) || !xi_valid(xi)) return;
     float B = a[3], ro2;
     float t = md_temp(out, B, ro2);
-    t = (float)(-log(2.0) + (double)logf(1.0f + B*(1.0f - ro2) + sqrtf(fmaxf(t, 0.0f))));
+    t = (float)(-log(2.0) + (double)logf(1.0f + B*(1.0f - ro2) + m_safe_sqrt(t)));
     float MdPi = B * (1.0f / t);
     float E = (float)(2.0 * (double)expf(xi.x * B * (1.0f / MdPi)));
-    float ri = sqrtf(fmaxf((E - 2.0f)*(E + 2.0f*B*ro2) / (2.0f*E*B), 0.0f));
+    float ri = m_safe_sqrt((E - 2.0f)*(E + 2.0f*B*ro2) / (2.0f*E*B));
     float ro = sqrtf(ro2);
     double rp = (double)(ri + ro), rm = (double)(ri - ro);
     float scale = (float)sqrt((1.0 + (double)B*(rp*rp)) / (1.0 + (double)B*(rm*rm)));
     float phi_i = (float)(2.0 * (double)atanf(tanf(xi.y * kPi) * scale) + (double)sph_phi(out));
-    dir = make_f3(cosf(phi_i)*ri, sinf(phi_i)*ri, (float)sqrt(fmax(1.0 - (double)(ri*ri), 0.0)));
+    dir = make_f3(cosf(phi_i)*ri, sinf(phi_i)*ri, (float)safe_sqrt_d(1.0 - (double)(ri*ri)));
     pdfv = pdf(dir, out, a, component);
     flag = FLAG_SPECULAR;
   }

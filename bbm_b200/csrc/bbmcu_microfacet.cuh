@@ -139,8 +139,8 @@ struct NdfBeckmann
       f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
       float tanT = tanTheta(vs);
       float maxval = erff(1.0f / tanT);
-      float x0 = fminf(fmaxf(xi.x, 1e-5f), (float)(1.0 - 10e-6));
-      float x1 = fminf(fmaxf(xi.y, 1e-5f), (float)(1.0 - 10e-6));
+      float x0 = clampf(xi.x, 1e-5f, (float)(1.0 - 10e-6));
+      float x1 = clampf(xi.y, 1e-5f, (float)(1.0 - 10e-6));
       float x = maxval - (maxval + 1.0f) * erff(sqrtf(-logf(x0)));
       float gauss = kInvSqrtPi * tanT * expf(-(vs.z*vs.z));
       x0 = (float)((double)x0 * (1.0 + (double)maxval + (double)gauss));
@@ -168,7 +168,7 @@ struct NdfBeckmann
       if(ANISO) { cp *= ax; sp *= ay; nrm = cp*cp + sp*sp; float r = 1.0f/sqrtf(nrm); cp *= r; sp *= r; }
       else nrm = ax*ax;
       float cosT = (float)(1.0 / sqrt(1.0 - (double)(nrm*logf(xi.y))));
-      float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+      float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
       return make_f3(cp*sinT, sp*sinT, cosT);
     }
   }
@@ -221,7 +221,7 @@ struct NdfGGX
     float P1 = r*cp;
     float P2 = (float)((lower ? 1.0 : (double)vs.z) * (double)r * (double)sp);
     // safe_sqrt(1.0 - P1*P1 - P2*P2) is a double, but double * float-array converts the scalar to float first
-    float w = (float)sqrt(fmax(1.0 - (double)(P1*P1) - (double)(P2*P2), 0.0));
+    float w = (float)safe_sqrt_d(1.0 - (double)(P1*P1) - (double)(P2*P2));
     f3 n = (T1*P1 + T2*P2) + vs*w;
     return normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
   }
@@ -252,7 +252,7 @@ struct NdfPhong
   {
     if(!xi_valid(xi)) return make_f3(0, 0, 0);
     float cosT = (float)pow((double)xi.x, 1.0 / (double)(a[0] + 2.0f));
-    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     float ph = xi.y * kTwoPi;
     return make_f3(cosf(ph)*sinT, sinf(ph)*sinT, cosT);
   }
@@ -283,7 +283,7 @@ struct NdfLow
                ? (float)exp((double)xi.x * log(1.0 + (double)B))
                : (float)pow(1.0 + (double)xi.x * (pow(1.0 + (double)B, 1.0 - (double)C) - 1.0), -1.0 / ((double)C - 1.0));
     float cosT = (float)((1.0 + (double)B - (double)term) / (double)B);
-    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     float ph = xi.y * kTwoPi;
     return make_f3(cosf(ph)*sinT, sinf(ph)*sinT, cosT);
   }
@@ -366,7 +366,7 @@ struct NdfStudentT
     else nrm = a[0]*a[0];
     float tan2 = (float)((pow((double)xi.y, 1.0 / (1.0 - (double)gamma)) - 1.0) * (double)(gamma - 1.0f) * (double)nrm);
     float cosT = (float)(1.0 / sqrt(1.0 + (double)tan2));
-    float sinT = (float)sqrt(fmax(1.0 - (double)(cosT*cosT), 0.0));
+    float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     return make_f3(cp*sinT, sp*sinT, cosT);
   }
 };
@@ -391,10 +391,21 @@ struct NdfSGD
     float c4pi = kPi * (float)((double)c2*(double)c2);   // Pi * pow(cos, 4.0)
     return Spec<T>(D1(tan2, c4pi, a[15], a[18], a[0]), D1(tan2, c4pi, a[16], a[19], a[1]), D1(tan2, c4pi, a[17], a[20], a[2]));
   }
-  template<class T> BBMCU_D static T G11(float theta, const T& Lambda, const T& c, const T& theta0, const T& k)
+  // 1 + Lambda (1 - exp(c (theta - theta0)^k)): the 1 - exp(.) cancels, so exp/pow are evaluated in double
+  // and rounded to float (what glibc's correctly rounded expf/powf return) before the float arithmetic
+  BBMCU_D static float G11(float theta, float Lambda, float c, float theta0, float k)
   {
-    if(!(theta > val(theta0))) return T(1.0f);
-    return 1.0f + Lambda*(1.0f - m_exp(c*m_pow(theta - theta0, k)));
+    if(!(theta > theta0)) return 1.0f;
+    float pw = (float)pow((double)(theta - theta0), (double)k);
+    float ex = (float)exp((double)(c*pw));
+    return 1.0f + Lambda*(1.0f - ex);
+  }
+  template<int N> BBMCU_D static Dual<N> G11(float theta, const Dual<N>& Lambda, const Dual<N>& c, const Dual<N>& theta0, const Dual<N>& k)
+  {
+    if(!(theta > theta0.v)) return Dual<N>(1.0f);
+    Dual<N> r = 1.0f + Lambda*(1.0f - m_exp(c*m_pow(theta - theta0, k)));
+    r.v = G11(theta, Lambda.v, c.v, theta0.v, k.v);
+    return r;
   }
   template<class T> BBMCU_D static Spec<T> G1(f3 v, f3 m, const T* a)
   {

@@ -51,7 +51,10 @@ def test_golden_sample(ctx, golden_models):
             ok = defined_samples(s, arr[f"{key}_refl_c{c}"], arr["xi"])
             assert np.array_equal(f[ok], arr[f"{key}_sflag_c{c}"].astype(np.int32)[ok]), f"sample flag {s} comp {c}"
             assert_parity(d.T[ok], arr[f"{key}_sdir_c{c}"][ok], 1e-5, floor=1e-5, what=f"sample dir {s} comp {c}")
-            assert_parity(p[ok], arr[f"{key}_spdf_c{c}"][ok], 2e-3, what=f"sample pdf {s} comp {c}")
+            # loose: the golden pdf was evaluated at the reference's own direction; a last-bit difference of the
+            # direction moves the pdf of a sharp lobe (B = 6e4 fits) by up to 1e-2.  The strict check is
+            # test_sample_pdf_consistency_on_gpu_direction (oracle pdf at the GPU's direction, 1e-5)
+            assert_parity(p[ok], arr[f"{key}_spdf_c{c}"][ok], 3e-2, what=f"sample pdf {s} comp {c}")
 
 
 def test_sample_pdf_consistency_on_gpu_direction(ctx, ref, golden_models):
@@ -60,10 +63,13 @@ def test_sample_pdf_consistency_on_gpu_direction(ctx, ref, golden_models):
     import bbm_b200 as bb
     arr, meta = golden_models
     out, xi = arr["out"], arr["xi"]
-    for s in ("GGX([0.1, 0.2, 0.3], 0.01, 1.5)", "CookTorrance([0.1, 0.2, 0.3], 0.02, 2.5)", "Phong([0.2, 0.3, 0.4], 800)", "Ward([0.3, 0.2, 0.1], [0.05, 0.3])"):
+    cases = ["GGX([0.1, 0.2, 0.3], 0.01, 1.5)", "CookTorrance([0.1, 0.2, 0.3], 0.02, 2.5)", "Phong([0.2, 0.3, 0.4], 800)", "Ward([0.3, 0.2, 0.1], [0.05, 0.3])"]
+    cases += [v for v in meta["fits"].values() if uses_only_implemented(v)]
+    for s in cases:
         d, p, f = ctx.sample(bb.Bsdf(s), soa(out), soa(xi))
         want = ref.pdf(s, d.T.copy(), out)
-        assert_parity(p, want, 1e-5, what=f"sample pdf at gpu direction {s}")
+        ok = f != 0                                  # masked samples return {0, 0, None}
+        assert_parity(p[ok], want[ok], 1e-5, what=f"sample pdf at gpu direction {s}")
 
 
 def test_device_and_host_pointers_agree(ctx):
@@ -174,7 +180,8 @@ def test_loss_batched_and_sharded(ctx):
     lk, gk = L(fitted, params, grad=True)
     for k in range(7):
         l1, g1 = L(fitted, params[k], grad=True)
-        assert l1[0] == lk[k] and np.array_equal(g1[0], gk[k])
+        # (the block count per parameter set depends on K, so the fixed summation order differs: equal to 1e-12)
+        assert abs(l1[0] - lk[k]) <= 1e-12*abs(lk[k]) and np.allclose(g1[0], gk[k], rtol=1e-10, atol=1e-14)
     A = ctx.loss("standardLog", truth, None, first=0, count=700001)
     B = ctx.loss("standardLog", truth, None, first=700001, count=1458000 - 700001)
     la, ga = A(fitted, params, grad=True)
