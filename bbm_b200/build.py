@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libbbmcu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-DEFINES = []  # ["-DBBMCU_WITH_EPD", "-DBBMCU_WITH_HE"] once those families land
+DEFINES = []  # ["-DBBMCU_WITH_HE"] once that family lands
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-diag-suppress", "20012,20011,20014,177,550"] + DEFINES
@@ -47,6 +47,16 @@ def build(force=False, verbose=False):
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr):
             todo.append(s)
+    # model data linked into the library: data/epd_g1.f32 -> _binary_epd_g1_f32_start/_end
+    data_obj = os.path.join(OBJ, "epd_g1.f32.o")
+    data_src = os.path.join(HERE, "data", "epd_g1.f32")
+    relink = False
+    if force or not os.path.exists(data_obj) or os.path.getmtime(data_obj) < os.path.getmtime(data_src):
+        r = subprocess.run(["ld", "-r", "-b", "binary", "-z", "noexecstack", "-o", data_obj, "epd_g1.f32"], cwd=os.path.join(HERE, "data"), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("embedding data/epd_g1.f32 failed:\n" + r.stdout + r.stderr)
+        relink = True
+    objs.append(data_obj)
     log = []
     if todo:
         with cf.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
@@ -54,7 +64,7 @@ def build(force=False, verbose=False):
                 log.append((src, out))
                 if rc != 0:
                     raise RuntimeError(f"compiling {src} failed:\n{out}")
-    if todo or not os.path.exists(LIB) or force:
+    if todo or relink or not os.path.exists(LIB) or force:
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-lineinfo"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

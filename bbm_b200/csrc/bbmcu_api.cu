@@ -4,6 +4,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <mutex>
 
 #include "bbmcu_launch.cuh"
 
@@ -21,6 +22,29 @@ bool is_device_pointer(const void* p)
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if(e != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// the Holzschuch-Pacanowski G1 table: bbm_b200/data/epd_g1.f32 linked into the library (build.py: ld -r -b binary)
+extern "C" { extern const unsigned char _binary_epd_g1_f32_start[]; extern const unsigned char _binary_epd_g1_f32_end[]; }
+const float* epd_table_device(int device)
+{
+  static std::mutex mtx;
+  static float* table[64] = {};
+  std::lock_guard<std::mutex> lock(mtx);
+  if(device < 0 || device >= 64) throw std::invalid_argument("BBM: device index out of range");
+  if(!table[device])
+  {
+    const size_t bytes = (size_t)(_binary_epd_g1_f32_end - _binary_epd_g1_f32_start);
+    if(bytes != sizeof(float)*kEpdRows*kEpdCols) throw std::runtime_error("BBM: embedded EPD G1 table has the wrong size");
+    int cur = 0; BBMCU_CUDA(cudaGetDevice(&cur));
+    BBMCU_CUDA(cudaSetDevice(device));
+    float* p = nullptr;
+    BBMCU_CUDA(cudaMalloc(&p, bytes));
+    BBMCU_CUDA(cudaMemcpy(p, _binary_epd_g1_f32_start, bytes, cudaMemcpyHostToDevice));
+    BBMCU_CUDA(cudaSetDevice(cur));
+    table[device] = p;
+  }
+  return table[device];
 }
 
 namespace {
@@ -129,7 +153,6 @@ void bbmcu_destroy(bbmcu_ctx* ctx)
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]); if(ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]); }
-  if(ctx->epd_g1) cudaFree(ctx->epd_g1);
   if(ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

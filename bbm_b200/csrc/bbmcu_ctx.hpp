@@ -19,7 +19,6 @@ struct bbmcu_ctx
   cudaStream_t slot_stream[kSlots] = {};           // host-pointer chunks round-robin here
   void* slot_buf[kSlots] = {};                     // device staging, one per slot
   size_t slot_bytes = 0;
-  float* epd_g1 = nullptr;                         // 100 x 1000 Holzschuch-Pacanowski G1 table (device)
   std::string error;
   uint64_t launches = 0;
 };

@@ -3,15 +3,18 @@
 #pragma once
 #include "bbmcu_ctx.hpp"
 #include "bbmcu_kernels.cuh"
+#include "bbmcu_tables.cuh"
 
 namespace bbmcu {
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template<class Op> void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, const Op& op, size_t n)
+// internal linkage: every translation unit keeps its own copy next to its own device symbols (bbmcu_tables.cuh)
+template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, const Op& op, size_t n)
 {
   if(n == 0) return;
   size_t groups = (n + kVec - 1) / kVec;
+  bind_device_tables();
   k_foreach4<Op><<<grid_for(ctx, groups), 256, 0, stream>>>(op, groups);
   BBMCU_CUDA(cudaGetLastError());
   ++ctx->launches;
@@ -19,7 +22,7 @@ template<class Op> void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, con
 
 // OpT<B> is one of the BSDF operators of bbmcu_kernels.cuh; fill(op) sets everything but op.bsdf
 template<template<class> class OpT, class Fill>
-void launch_bsdf_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& d, size_t n, Fill&& fill)
+static void launch_bsdf_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& d, size_t n, Fill&& fill)
 {
   auto go = [&](auto* tag) {
     using B = typename std::remove_pointer<decltype(tag)>::type;

@@ -237,6 +237,7 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
         done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)K) ||
                launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)K);
       }
+      if(!done) bind_device_tables();
       if(!done) k_loss_generic<<<dim3(bx, (unsigned)K), kLossThreads, (kLossThreads/32)*cols*sizeof(double), ctx->stream>>>(a, shape);
       BBMCU_CUDA(cudaGetLastError());
       ++ctx->launches;
@@ -276,6 +277,7 @@ int bbmcu_loss_terms(bbmcu_loss* L, const bbmcu_bsdf* bsdf, float* terms)
     const bool dev = is_device_pointer(terms);
     float* d_terms = terms;
     if(!dev) BBMCU_CUDA(cudaMalloc(&d_terms, L->count*sizeof(float)));
+    bind_device_tables();
     k_loss_terms<<<grid_for(ctx, L->count), 256, 0, ctx->stream>>>(a, shape, d_terms);
     BBMCU_CUDA(cudaGetLastError());
     ++ctx->launches;

@@ -5,9 +5,7 @@ bool launch_loss_pair_g3(int model, cudaStream_t s, const LossArgs& a, unsigned 
 {
   switch(model) {
     BBMCU_LOSS_CASE_PAIR(M_Bagher)
-#ifdef BBMCU_WITH_EPD
     BBMCU_LOSS_CASE_PAIR(M_EPD)
-#endif
 #ifdef BBMCU_WITH_HE
     BBMCU_LOSS_CASE_PAIR(M_He) BBMCU_LOSS_CASE_PAIR(M_HeWestin) BBMCU_LOSS_CASE_PAIR(M_HeHolzschuch) BBMCU_LOSS_CASE_PAIR(M_NganHe)
 #endif

@@ -10,6 +10,7 @@
 #pragma once
 #include "bbmcu_ctx.hpp"
 #include "bbmcu_lossop.cuh"
+#include "bbmcu_tables.cuh"
 
 namespace bbmcu {
 
@@ -76,8 +77,9 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_static(const LossArgs a)
   }
 }
 
-template<class LossT> void launch_loss_static(cudaStream_t s, const LossArgs& a, unsigned blocks_x, unsigned K)
+template<class LossT> static void launch_loss_static(cudaStream_t s, const LossArgs& a, unsigned blocks_x, unsigned K)
 {
+  bind_device_tables();
   k_loss_static<LossT><<<dim3(blocks_x, K), kLossThreads, 0, s>>>(a);
 }
 

@@ -3,9 +3,7 @@
 // reference's bbm_info prints (include/export/bbm_fromstring.h:48-49).
 #pragma once
 #include "bbmcu_lobes.cuh"
-#ifdef BBMCU_WITH_EPD
 #include "bbmcu_epd.cuh"
-#endif
 #ifdef BBMCU_WITH_HE
 #include "bbmcu_he.cuh"
 #endif
@@ -53,9 +51,7 @@ BBMCU_MODEL(M_LowSmooth, LowSmooth)
 BBMCU_MODEL(M_Ribardiere, Microfacet<NdfStudentT<false>, GUncorrelated, FresnelCookIor, 1, true>)
 BBMCU_MODEL(M_RibardiereAnisotropic, Microfacet<NdfStudentT<true>, GUncorrelated, FresnelCookIor, 1, true>)
 BBMCU_MODEL(M_Bagher, Microfacet<NdfSGD, GUncorrelated, FresnelBagher, 2, true>)          // bagher.h:62-68
-#ifdef BBMCU_WITH_EPD
 BBMCU_MODEL(M_EPD, Microfacet<NdfEPD, GVanGinneken, FresnelComplexScalar, 1, false>)      // holzschuchpacanowski.h:34-42
-#endif
 #ifdef BBMCU_WITH_HE
 BBMCU_MODEL(M_He, HeModel<HE_VARIANT_HE>)
 BBMCU_MODEL(M_HeWestin, HeModel<HE_VARIANT_WESTIN>)
@@ -64,11 +60,7 @@ BBMCU_MODEL(M_NganHe, HeModel<HE_VARIANT_NGAN>)
 #endif
 
 // uniform (per-launch) dispatch on a model id: calls f((ModelOf<id>::type*)nullptr)
-#ifdef BBMCU_WITH_EPD
 #define BBMCU_CASES_EPD BBMCU_CASE(M_EPD)
-#else
-#define BBMCU_CASES_EPD
-#endif
 #ifdef BBMCU_WITH_HE
 #define BBMCU_CASES_HE BBMCU_CASE(M_He) BBMCU_CASE(M_HeWestin) BBMCU_CASE(M_HeHolzschuch) BBMCU_CASE(M_NganHe)
 #else

@@ -35,6 +35,11 @@ class HostSim:
         self.lib = C.CDLL(build())
         self.lib.hostsim_last_error.restype = C.c_char_p
         self.lib.hostsim_libm_mismatches.restype = C.c_size_t
+        self.lib.hostsim_gamma_q_inv.restype = C.c_float
+        self.lib.hostsim_gamma_q_inv.argtypes = [C.c_float, C.c_float]
+        self._epd = np.fromfile(os.path.join(ROOT, "bbm_b200", "data", "epd_g1.f32"), np.float32)
+        assert self._epd.size == 100000
+        self.lib.hostsim_set_epd_table(self._epd.ctypes.data_as(C.c_void_p))
 
     def _chk(self, rc):
         if rc:

@@ -20,6 +20,9 @@ template<class Op> static void run(const Op& op, size_t n) { for(size_t i=0; i <
 
 extern "C" {
 const char* hostsim_last_error() { return g_err.c_str(); }
+// the EPD G1 table (bbm_b200/data/epd_g1.f32), owned by the caller
+void hostsim_set_epd_table(const float* table) { g_epd_g1_host = table; }
+float hostsim_gamma_q_inv(float a, float q) { return epd_gamma_q_inv(a, q); }
 
 int hostsim_eval(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
 { GUARD( EvalOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }

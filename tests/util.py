@@ -13,8 +13,6 @@ def implemented_models():
         import bbm_b200 as bb
         names = bb.model_names()
         missing = set()
-        if "-DBBMCU_WITH_EPD" not in re.sub(r"#.*", "", src):
-            missing |= {"EPD"}
         if "-DBBMCU_WITH_HE" not in re.sub(r"#.*", "", src):
             missing |= {"He", "HeWestin", "HeHolzschuch", "NganHe"}
         IMPLEMENTED = [n for n in names if n not in missing]
