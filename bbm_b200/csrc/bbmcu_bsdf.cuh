@@ -8,12 +8,14 @@
 namespace bbmcu {
 
 constexpr int kMaxLobes = 4;
-constexpr int kMaxAttrs = 64;
+constexpr int kMaxAttrs = 256;         // attribute floats + device-side tables (90 CDF bins per He lobe)
 
 struct BsdfDesc
 {
   int n_lobes;
   int aggregate;               // 1: wrapped in Aggregate(...) (weights / sum even for one lobe)
+  int n_tables;                // lobes whose block ends in a table the kernel prologue has to fill (He family)
+  int n_floats;                // used floats of attrs[]
   int model[kMaxLobes];
   int offset[kMaxLobes];       // first attribute of the lobe in attrs[]
   float attrs[kMaxAttrs];
@@ -47,6 +49,7 @@ BBMCU_D void lobe_sample(int model, const float* a, f3 out, f2 xi, int component
 // ---- run-time lobe list -----------------------------------------------------------------------
 struct BsdfGeneric
 {
+  static constexpr bool kTables = true;
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component)
   {
     if(!b.aggregate) return lobe_eval(b.model[0], b.attrs + b.offset[0], in, out, component);
@@ -96,10 +99,35 @@ struct BsdfGeneric
   }
 };
 
+// ---- device-side tables: the sampling CDF of He-family lobes (ndf/sampler.h:143-181) ------------------------
+// phase 1: thread `tid` of `nthreads` fills the un-normalised samples; phase 2 (after a barrier): one thread per
+// lobe runs the sequential partial sum + normalisation.  The host-compiled tests call both with (0, 1).
+BBMCU_D void bsdf_tables_phase1(BsdfDesc& b, int component, int tid, int nthreads)
+{
+  for(int l=0; l < b.n_lobes; ++l)
+    dispatch_model(b.model[l], [&](auto* tag) {
+      using M = typename std::remove_pointer<decltype(tag)>::type;
+      if constexpr (TableFloats<M>::N > 0)
+      {
+        float* a = b.attrs + b.offset[l];
+        for(int i = tid; i < kHeCdfBins; i += nthreads) a[M::NA + i] = M::cdf_sample(a, component, i);
+      }
+    });
+}
+BBMCU_D void bsdf_tables_phase2(BsdfDesc& b, int tid)
+{
+  if(tid < b.n_lobes)
+    dispatch_model(b.model[tid], [&](auto* tag) {
+      using M = typename std::remove_pointer<decltype(tag)>::type;
+      if constexpr (TableFloats<M>::N > 0) M::cdf_finish(b.attrs + b.offset[tid] + M::NA);
+    });
+}
+
 // ---- compile-time single model (no dispatch, smallest register footprint) ------------------------
 template<class M>
 struct BsdfSingle
 {
+  static constexpr bool kTables = TableFloats<M>::N > 0;
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component) { return M::template eval<float>(in, out, b.attrs, component); }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component) { return M::reflectance(out, b.attrs, component); }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component) { return M::pdf(in, out, b.attrs, component); }

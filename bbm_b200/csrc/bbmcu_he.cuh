@@ -1,0 +1,328 @@
+// The He-Torrance-Sillion-Greenberg directional-specular model in its four bbm flavours (He, HeWestin,
+// HeHolzschuch, NganHe) and the data-driven importance sampler the reference wraps them in.
+//
+// Behaviour follows (restated, not copied):
+//   include/bsdfmodel/he.h:141-170 (eval), :227-237 (reflectance), :266-291 (S, Eq. 24-25),
+//   :306-352 (G, Eq. 76), :365-400 (apparent roughness, Eq. 80, 4 Newton steps),
+//   :411-467 (D, Eq. 78-79: adaptive Taylor series blended with Beckmann's rough approximation), :489-496 (variants)
+//   include/bsdfmodel/ngan.h:166-167 (NganHe), include/bsdfmodel/scaledmodel.h:50-67
+//   include/bbm/ndf_sampler.h:79-156 (sample / pdf through a back-scatter "NDF" hsum(eval(h, h)))
+//   include/ndf/sampler.h:63-92 (sample), :102-128 (pdf), :143-181 (90-bin CDF), include/util/cdf.h
+//
+// The reference builds the CDF lazily on the host whenever the parameters change; here every thread block
+// rebuilds it in shared memory in its prologue (90 evaluations, one per thread; see bbmcu_kernels.cuh), so
+// there is no host mathematics, no cache to invalidate and nothing to upload.  The device attribute block of a He
+// lobe is [NA attributes][NT = 90 CDF entries].
+//
+// eval is a template over T: T = float reproduces the native backbone's float/double mix (the Taylor
+// series runs in double, he.h:418-455); T = Dual<N> carries parameter derivatives in float.
+#pragma once
+#include "bbmcu_microfacet.cuh"
+
+namespace bbmcu {
+
+enum : int { HE_VARIANT_HE = 0, HE_VARIANT_WESTIN, HE_VARIANT_HOLZSCHUCH, HE_VARIANT_NGAN };
+constexpr int kHeCdfBins = 90;
+
+// the working type of the spots the reference evaluates in double
+template<class T> struct WideOf { using type = T; };
+template<> struct WideOf<float> { using type = double; };
+BBMCU_D double he_wide(float a) { return (double)a; }
+template<int N> BBMCU_D Dual<N> he_wide(const Dual<N>& a) { return a; }
+BBMCU_D float he_narrow(double a) { return (float)a; }
+template<int N> BBMCU_D Dual<N> he_narrow(const Dual<N>& a) { return a; }
+BBMCU_D double m_exp(double a) { return exp(a); }
+BBMCU_D double m_log(double a) { return log(a); }
+BBMCU_D double m_sqrt(double a) { return sqrt(a); }
+BBMCU_D double m_safe_sqrt(double a) { return safe_sqrt_d(a); }
+BBMCU_D double val(double a) { return a; }
+
+template<int V> struct HeTraits;
+template<> struct HeTraits<HE_VARIANT_HE>         { static constexpr bool ERRATA = false, WESTIN = false, ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
+template<> struct HeTraits<HE_VARIANT_WESTIN>     { static constexpr bool ERRATA = true,  WESTIN = true,  ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
+template<> struct HeTraits<HE_VARIANT_HOLZSCHUCH> { static constexpr bool ERRATA = true,  WESTIN = false, ADAPTIVE = false, ROUGH = false, SCALED = false; static constexpr int TERMS = 10; using F = FresnelComplexRGB; };
+template<> struct HeTraits<HE_VARIANT_NGAN>       { static constexpr bool ERRATA = true,  WESTIN = true,  ADAPTIVE = true,  ROUGH = true,  SCALED = true;  static constexpr int TERMS = 64; using F = FresnelCookIor; };
+
+template<int V>
+struct HeModel
+{
+  using Tr = HeTraits<V>;
+  using F = typename Tr::F;
+  static constexpr int SCALE = Tr::SCALED ? 0 : -1;
+  static constexpr int OFF_R = Tr::SCALED ? 3 : 0;       // roughness (sigma0), then autocorrelation (tau)
+  static constexpr int OFF_F = OFF_R + 2;
+  static constexpr int NA = OFF_F + F::NA;
+  static constexpr int NT = kHeCdfBins;                  // device-side CDF appended to the attribute block
+
+  // ---- Eq. 24-25: mono-directional shadowing ---------------------------------------------------------
+  template<class T> BBMCU_D static T S1(f3 v, const T& rough, const T& tau)
+  {
+    using W = typename WideOf<T>::type;
+    if(val(rough) < kEps) return T(1.0f);
+    float cot = 1.0f / tanTheta(v);
+    T scaledCot = he_narrow(he_wide(tau * cot) / (he_wide(rough) * 2.0f));
+    T erfcv = he_narrow(he_wide(m_erfc(scaledCot)) * 0.5f);
+    T Lambda = he_narrow((W)(0.5f * he_wide(T(kInvSqrtPi))) / he_wide(scaledCot));
+    if(Tr::ERRATA) { W s = he_wide(scaledCot); Lambda = he_narrow(he_wide(Lambda) * m_exp(-(s*s))); }
+    Lambda = Lambda - erfcv;
+    return he_narrow((1.0f - he_wide(erfcv)) / (he_wide(Lambda) + 1.0f));
+  }
+
+  // ---- Eq. 76: geometrical factor (directions only) ---------------------------------------------------
+  BBMCU_D static float G(f3 in, f3 out)
+  {
+    f3 v = in + out;
+    double vs = (double)(dot(v, v) / v.z);
+    float v_scale = (float)(vs*vs);
+    float kixn2 = 1.0f - in.z*in.z, krxn2 = 1.0f - out.z*out.z;
+    float kikr = dot(-in, out);
+    float sikr = out.y*in.x - out.x*in.y, srki = in.y*out.x - in.x*out.y;
+    float pikr = out.z + kikr*in.z, prki = in.z + kikr*out.z;
+    double dd = 1.0 - (double)(kikr*kikr);
+    float denom = (float)(dd*dd);
+    float nom = (float)(((double)sikr*(double)sikr + (double)pikr*(double)pikr) * ((double)srki*(double)srki + (double)prki*(double)prki) / (double)(krxn2*kixn2));
+    return (denom > kEps) ? v_scale * nom / denom : 1.0f;
+  }
+
+  // ---- Eq. 80: apparent roughness, Newton-Raphson ------------------------------------------------------
+  template<class T> BBMCU_D static T sigma(f3 in, f3 out, const T& rough, const T& tau)
+  {
+    using W = typename WideOf<T>::type;
+    if(!(val(rough) > kEps)) return T(0.0f);
+    float ti = tanTheta(in), to = tanTheta(out);
+    T Ki = (ti > kEps) ? ti * m_erfc(tau / (2.0f * rough * ti)) : T(0.0f);
+    T Ko = (to > kEps) ? to * m_erfc(tau / (2.0f * rough * to)) : T(0.0f);
+    const float rs8pi = 1.0f / sqrtf((float)(8.0 * kPiD));
+    T f0 = rs8pi * (Ki + Ko);
+    T x = (val(f0) <= 1.0f) ? f0 : he_narrow(m_safe_sqrt(2.0f * he_wide(m_log(f0))));
+#pragma unroll
+    for(int step=0; step < 4; ++step)
+    {
+      W xw = he_wide(x);
+      T expn = he_narrow(m_exp((0.5f * xw) * xw));
+      T ev = x*expn - f0;
+      T grad = (1.0f + x*x) * expn;
+      if(val(grad) > kEps) x = x - ev / grad;
+    }
+    return rough / m_safe_sqrt(1.0f + x*x);
+  }
+
+  // ---- Eq. 78-79: distribution ------------------------------------------------------------------------
+  BBMCU_D static float lerpf(float a, float b, float t)            // std::lerp<float>
+  {
+    if((a <= 0.0f && b >= 0.0f) || (a >= 0.0f && b <= 0.0f)) return t*b + (1.0f - t)*a;
+    if(t == 1.0f) return b;
+    float x = a + t*(b - a);
+    return ((t > 1.0f) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
+  }
+  BBMCU_D static Spec<float> D(f3 in, f3 out, const float& rough, const float& tau)
+  {
+    const float wl[3] = {0.645f, 0.526f, 0.444f};            // floatRGB wavelengths (backbone/native/include/backbone.h:36)
+    const float thr = Tr::ROUGH ? 18.0f : 3.402823466e+38f;
+    float sx = in.x + out.x, sy = in.y + out.y;
+    float v_xy2 = sx*sx + sy*sy;
+    float base = kTwoPi * sigma<float>(in, out, rough, tau) * (in.z + out.z);
+    float tau2 = (float)((double)tau * (double)tau);
+    const float pi2q = (0.25f * kPi) * kPi, pi2x4 = (4.0f * kPi) * kPi;
+    double g[3], nrm[3]; float eb[3];
+#pragma unroll
+    for(int c=0; c < 3; ++c)
+    {
+      double q = (double)(base / wl[c]);  g[c] = q*q;
+      double w2 = (double)wl[c] * (double)wl[c];
+      nrm[c] = (double)(pi2q * tau2) / w2;
+      eb[c] = v_xy2 * tau2 / 4.0f;
+      if(Tr::WESTIN) eb[c] = (float)((double)eb[c] * ((double)pi2x4 / w2));
+    }
+    double gmin = fmin(fmin(g[0], g[1]), g[2]);
+    if(!(g[0] == g[0]) || !(g[1] == g[1]) || !(g[2] == g[2])) gmin = g[0] + g[1] + g[2];   // std::min_element keeps the first on NaN compare; a NaN g poisons everything anyway
+    float ra[3] = {0.0f, 0.0f, 0.0f}, weight = 0.0f;
+    if(gmin > (double)thr)
+    {
+#pragma unroll
+      for(int c=0; c < 3; ++c) ra[c] = (float)(exp((double)(-eb[c]) / g[c]) / g[c]);
+      double wv = gmin - (double)thr;
+      weight = (float)(wv < 0.0 ? 0.0 : (1.0 < wv ? 1.0 : wv));
+    }
+    float sum[3] = {0.0f, 0.0f, 0.0f}, gm[3] = {1.0f, 1.0f, 1.0f}, term[3] = {0.0f, 0.0f, 0.0f}, last_min = -1.0f;
+    bool converged = (gmin - 1.0) > (double)thr;
+    for(int m=1; m <= Tr::TERMS && !converged; ++m)
+    {
+      float tmin = 3.402823466e+38f;
+#pragma unroll
+      for(int c=0; c < 3; ++c)
+      {
+        gm[c] = (float)((double)gm[c] * (g[c] / (double)m));
+        term[c] = (float)(exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] / (double)m);
+        sum[c] += term[c];
+      }
+      tmin = term[0]; if(term[1] < tmin) tmin = term[1]; if(term[2] < tmin) tmin = term[2];      // std::min_element order
+      if(Tr::ADAPTIVE) converged = (tmin < kEps) && (tmin < last_min);
+      last_min = tmin;
+    }
+    return Spec<float>((float)(nrm[0] * (double)lerpf(sum[0], ra[0], weight)), (float)(nrm[1] * (double)lerpf(sum[1], ra[1], weight)),
+                       (float)(nrm[2] * (double)lerpf(sum[2], ra[2], weight)));
+  }
+  // derivative-carrying version (float arithmetic; same control flow, decided on the values)
+  template<int N> BBMCU_D static Spec<Dual<N>> D(f3 in, f3 out, const Dual<N>& rough, const Dual<N>& tau)
+  {
+    using T = Dual<N>;
+    const float wl[3] = {0.645f, 0.526f, 0.444f};
+    const float thr = Tr::ROUGH ? 18.0f : 3.402823466e+38f;
+    float sx = in.x + out.x, sy = in.y + out.y;
+    float v_xy2 = sx*sx + sy*sy;
+    T base = kTwoPi * sigma<T>(in, out, rough, tau) * (in.z + out.z);
+    T tau2 = tau * tau;
+    const float pi2q = (0.25f * kPi) * kPi, pi2x4 = (4.0f * kPi) * kPi;
+    T g[3], nrm[3], eb[3];
+#pragma unroll
+    for(int c=0; c < 3; ++c)
+    {
+      T q = base / wl[c];  g[c] = q*q;
+      float w2 = wl[c]*wl[c];
+      nrm[c] = (pi2q * tau2) / w2;
+      eb[c] = v_xy2 * tau2 / 4.0f;
+      if(Tr::WESTIN) eb[c] = eb[c] * (pi2x4 / w2);
+    }
+    float gmin = fminf(fminf(g[0].v, g[1].v), g[2].v);
+    int cmin = (g[0].v <= g[1].v && g[0].v <= g[2].v) ? 0 : (g[1].v <= g[2].v ? 1 : 2);
+    T ra[3] = {T(0.0f), T(0.0f), T(0.0f)}, weight(0.0f);
+    if(gmin > thr)
+    {
+#pragma unroll
+      for(int c=0; c < 3; ++c) ra[c] = m_exp(-eb[c] / g[c]) / g[c];
+      float wv = gmin - thr;
+      if(wv >= 1.0f) weight = T(1.0f); else weight = g[cmin] - thr;
+    }
+    T sum[3] = {T(0.0f), T(0.0f), T(0.0f)}, gm[3] = {T(1.0f), T(1.0f), T(1.0f)}, term[3] = {T(0.0f), T(0.0f), T(0.0f)};
+    float last_min = -1.0f;
+    bool converged = (gmin - 1.0f) > thr;
+    for(int m=1; m <= Tr::TERMS && !converged; ++m)
+    {
+#pragma unroll
+      for(int c=0; c < 3; ++c)
+      {
+        gm[c] = gm[c] * (g[c] / (float)m);
+        term[c] = m_exp(-g[c] - eb[c] / (float)m) * gm[c] / (float)m;
+        sum[c] = sum[c] + term[c];
+      }
+      float tmin = fminf(fminf(term[0].v, term[1].v), term[2].v);
+      if(Tr::ADAPTIVE) converged = (tmin < kEps) && (tmin < last_min);
+      last_min = tmin;
+    }
+    Spec<T> r;
+    r.r = nrm[0] * (sum[0] + weight*(ra[0] - sum[0]));
+    r.g = nrm[1] * (sum[1] + weight*(ra[1] - sum[1]));
+    r.b = nrm[2] * (sum[2] + weight*(ra[2] - sum[2]));
+    return r;
+  }
+
+  // ---- the BSDF concept ----------------------------------------------------------------------------------
+  template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<T>(T(0.0f));
+    const T& rough = a[OFF_R]; const T& tau = a[OFF_R + 1];
+    T S = S1<T>(in, rough, tau) * S1<T>(out, rough, tau);
+    float Gt = G(in, out);
+    Spec<T> Dt = D(in, out, rough, tau);
+    float cosHalf = (float)safe_sqrt_d((double)(1.0f + dot(in, out)) / 2.0);
+    Spec<T> Ft = to_spec(F::template eval<T>(a + OFF_F, cosHalf));
+    float nrm = 1.0f / (kPi * in.z * out.z);
+    return (((Ft * nrm) * S) * Gt) * Dt;
+  }
+  template<class T> BBMCU_D static Spec<T> eval(f3 in, f3 out, const T* a, int component)
+  {
+    Spec<T> r = eval_unscaled<T>(in, out, a, component);
+    if(Tr::SCALED) r = r * load_spec(a);
+    return r;
+  }
+  BBMCU_D static Spec<float> reflectance(f3 out, const float* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !(out.z > 0.0f)) return Spec<float>(0.0f);
+    Spec<float> f = to_spec(F::template eval<float>(a + OFF_F, out.z));
+    Spec<float> r((float)((double)(f.r / kPi) * 4.0), (float)((double)(f.g / kPi) * 4.0), (float)((double)(f.b / kPi) * 4.0));
+    if(Tr::SCALED) r = r * load_spec(a);
+    return r;
+  }
+
+  // ---- data-driven sampling (ndf::sampler<backscatter, 90, 1>) ----------------------------------------------
+  // un-normalised CDF sample of bin `idx` for `component` (sampler.h:143-175)
+  BBMCU_D static float cdf_sample(const float* a, int component, int idx)
+  {
+    float q = (float)idx / (float)kHeCdfBins;
+    float theta = (float)(((double)q*(double)q) * (double)kHalfPi);
+    f3 h = make_f3(1.0f*sinf(theta), 0.0f*sinf(theta), cosf(theta));
+    float s = 0.0f + hsum(eval_unscaled<float>(h, h, a, component));
+    s /= 1.0f;
+    float q1 = (float)(idx + 1) / (float)kHeCdfBins;
+    float theta1 = (float)(((double)q1*(double)q1) * (double)kHalfPi);
+    return s * (sinf(theta1) * sqrtf(theta1));
+  }
+  // cdf(samples): sequential partial sum, then normalise by the last entry (util/cdf.h:36-44)
+  BBMCU_D static void cdf_finish(float* cdf)
+  {
+    float run = cdf[0];
+    for(int i=1; i < kHeCdfBins; ++i) { run = run + cdf[i]; cdf[i] = run; }
+    float norm = cdf[kHeCdfBins - 1];
+    for(int i=0; i < kHeCdfBins; ++i) cdf[i] = cdf[i] / norm;
+  }
+  BBMCU_D static float cdf_pdf(const float* cdf, int idx) { return cdf[idx] - (idx >= 1 ? cdf[idx - 1] : 0.0f); }
+
+  // ndf::sampler::pdf(view, m)
+  BBMCU_D static float h_pdf(f3 m, const float* cdf)
+  {
+    if(!(m.z > 0.0f)) return 0.0f;
+    float theta = sph_theta(m);
+    float ti = (float)((double)(sqrtf(theta / kHalfPi) * (float)kHeCdfBins) - 0.5);
+    float fl = floorf(ti), ce = ceilf(ti);
+    float w = ti - fl;
+    // cast<size_t>(negative) wraps to a huge value on x86-64 and clamps to the LAST bin (sampler.h:119)
+    int lidx = (fl < 0.0f) ? (kHeCdfBins - 1) : (fl > (float)(kHeCdfBins - 1) ? kHeCdfBins - 1 : (int)fl);
+    int uidx = (ce < 0.0f) ? (kHeCdfBins - 1) : (ce > (float)(kHeCdfBins - 1) ? kHeCdfBins - 1 : (int)ce);
+    float p = cdf_pdf(cdf, lidx) * (1.0f - w) + cdf_pdf(cdf, uidx) * w;
+    float jac = (sqrtf(theta) * ((0.25f*kPi)*kPi) / (float)kHeCdfBins) * fabsf(sinf(theta)) * kTwoPi;
+    return (jac > kEps) ? p / jac : 0.0f;
+  }
+  // ndf::sampler::sample(view, xi)
+  BBMCU_D static f3 h_sample(f2 xi, const float* cdf)
+  {
+    // std::lower_bound with predicate (val < xi): first entry that is not < xi
+    int lo = 0, count = kHeCdfBins;
+    while(count > 0) { int step = count / 2, mid = lo + step; if(cdf[mid] < xi.x) { lo = mid + 1; count -= step + 1; } else count = step; }
+    int idx = lo;
+    float residual = 0.0f;
+    if(idx < kHeCdfBins)
+    {
+      float prev = (idx >= 1) ? cdf[idx - 1] : 0.0f;
+      float pdfv = cdf[idx] - prev;
+      residual = (xi.x - prev) / pdfv;
+    }
+    double rc = (double)residual - 0.5;
+    double xi_r = fabs(rc);
+    double offs = 1.0 - safe_sqrt_d(1.0 - 2.0*xi_r);
+    double q = ((double)idx + 0.5 + copysign(1.0, rc)*offs) / (double)kHeCdfBins;
+    float theta = (float)((q*q) * (double)kHalfPi);
+    float phi = kTwoPi * xi.y;
+    if(theta > kHalfPi) theta = kPi - theta;
+    return sph_to_vec(phi, theta);
+  }
+  BBMCU_D static float pdf(f3 in, f3 out, const float* a, int component)
+  {
+    (void)component;                                       // ndf_sampler::pdf has no component test (ndf_sampler.h:131)
+    if(!((out.z > 0.0f) && (in.z > 0.0f))) return 0.0f;
+    f3 h = halfway(in, out);
+    float p = h_pdf(h, a + NA);
+    return (float)((double)p / fabs(4.0 * (double)dot(out, h)));
+  }
+  BBMCU_D static void sample(f3 out, f2 xi, const float* a, int component, f3& dir, float& pdfv, int& flag)
+  {
+    dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
+    if(!xi_valid(xi) || !(out.z > 0.0f)) return;           // no Specular test (ndf_sampler.h:84-87)
+    f3 h = h_sample(xi, a + NA);
+    dir = reflect(out, h);
+    pdfv = pdf(dir, out, a, component);
+    flag = component;
+  }
+};
+
+} // namespace bbmcu

@@ -11,6 +11,7 @@
 #pragma once
 #include "bbmcu_bsdf.cuh"
 #include "bbmcu_linearizer.cuh"
+#include <cstddef>
 
 namespace bbmcu {
 
@@ -52,8 +53,9 @@ BBMCU_D void store4x3(float* p, size_t i, size_t n, bool aligned, const Lanes3& 
 // ---- operators --------------------------------------------------------------------------------------
 template<class B> struct EvalOp
 {
+  static constexpr bool kHasBsdf = true, kTables = false;     // eval never reads the sampling tables
   BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned;
-  BBMCU_D void group(size_t i) const
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned), r;
 #pragma unroll
@@ -64,8 +66,9 @@ template<class B> struct EvalOp
 
 template<class B> struct PdfOp
 {
+  static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned;
-  BBMCU_D void group(size_t i) const
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned); Lanes r;
 #pragma unroll
@@ -76,8 +79,9 @@ template<class B> struct PdfOp
 
 template<class B> struct ReflectanceOp
 {
+  static constexpr bool kHasBsdf = true, kTables = false;
   BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned;
-  BBMCU_D void group(size_t i) const
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 b = load4x3(out, i, n, aligned), r;
 #pragma unroll
@@ -88,8 +92,9 @@ template<class B> struct ReflectanceOp
 
 template<class B> struct SampleOp
 {
+  static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned;
-  BBMCU_D void group(size_t i) const
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 b = load4x3(out, i, n, aligned), d; Lanes u = load4(xi, i, n, aligned), v = load4(xi + n, i, n, aligned), p; int f[kVec];
 #pragma unroll
@@ -101,8 +106,9 @@ template<class B> struct SampleOp
 // s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)   (20 B in, 36 B out per element)
 template<class B> struct SampleEvalPdfOp
 {
+  static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned;
-  BBMCU_D void group(size_t i) const
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 b = load4x3(out, i, n, aligned), d, c; Lanes u = load4(xi, i, n, aligned), v = load4(xi + n, i, n, aligned), sp, p; int f[kVec];
 #pragma unroll
@@ -121,6 +127,7 @@ template<class B> struct SampleEvalPdfOp
 
 struct MerlIndexOp
 {
+  static constexpr bool kHasBsdf = false, kTables = false;
   const float* in; const float* out; uint32_t* index; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
   {
@@ -133,6 +140,7 @@ struct MerlIndexOp
 
 struct MerlDirsOp
 {
+  static constexpr bool kHasBsdf = false, kTables = false;
   uint32_t first; float* in; float* out; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
   {
@@ -145,6 +153,7 @@ struct MerlDirsOp
 
 struct SphericalDirsOp
 {
+  static constexpr bool kHasBsdf = false, kTables = false;
   SphericalGrid grid; uint64_t first; float* in; float* out; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
   {
@@ -158,6 +167,7 @@ struct SphericalDirsOp
 // gather the measured grid at the bin of each direction pair: merl_data::eval (staticmodel/merl.h:78-96)
 struct MerlLookupOp
 {
+  static constexpr bool kHasBsdf = false, kTables = false;
   const float* table; const float* in; const float* out; float* rgb; uint32_t* bad; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
   {
@@ -187,8 +197,28 @@ struct MerlLookupOp
 #ifdef __CUDACC__
 template<class Op> __global__ void __launch_bounds__(256) k_foreach4(const Op op, size_t groups)
 {
-  for(size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x)
-    op.group(g * kVec);
+  const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if constexpr (!Op::kHasBsdf) { for(size_t g = first; g < groups; g += stride) op.group(g * kVec); }
+  else
+  {
+    if constexpr (Op::kTables)
+    {
+      if(op.bsdf.n_tables)                       // uniform: a He-family lobe - build its CDF in shared memory first
+      {
+        __shared__ BsdfDesc sb;
+        const int words = (int)((offsetof(BsdfDesc, attrs) + sizeof(float)*op.bsdf.n_floats + 3) / 4);
+        for(int i = threadIdx.x; i < words; i += blockDim.x) reinterpret_cast<uint32_t*>(&sb)[i] = reinterpret_cast<const uint32_t*>(&op.bsdf)[i];
+        __syncthreads();
+        bsdf_tables_phase1(sb, op.component, threadIdx.x, blockDim.x);
+        __syncthreads();
+        bsdf_tables_phase2(sb, threadIdx.x);
+        __syncthreads();
+        for(size_t g = first; g < groups; g += stride) op.group(g * kVec, sb);
+        return;
+      }
+    }
+    for(size_t g = first; g < groups; g += stride) op.group(g * kVec, op.bsdf);
+  }
 }
 #endif
 

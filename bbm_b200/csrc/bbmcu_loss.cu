@@ -192,7 +192,7 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     const int P = bsdf->b.param_count(BBMCU_ATTR_ALL);
     if(P > kMaxParams) throw std::invalid_argument("BBM: more than " + std::to_string(kMaxParams) + " fit parameters");
     BsdfDesc shape = make_desc(bsdf->b);
-    const int A = bsdf->b.attr_floats();
+    const int A = shape.n_floats;                 // device floats per parameter set (He lobes carry an unused table gap)
     const bool want_grad = (grad_out != nullptr) || (device_out != nullptr);
     const int cols = 1 + P;
     // attribute blocks for the K parameter sets
@@ -209,8 +209,11 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
       for(size_t k=0; k < K; ++k)
       {
         if(params) tmp.set_params(BBMCU_ATTR_ALL, params + k*P, P);
-        size_t off = 0;
-        for(auto& l : tmp.lobes) for(double v : l.values) L->h_attrs[k*A + off++] = (float)v;
+        for(size_t l=0; l < tmp.lobes.size(); ++l)
+        {
+          size_t off = (size_t)shape.offset[l];
+          for(double v : tmp.lobes[l].values) L->h_attrs[k*A + off++] = (float)v;
+        }
       }
     }
     BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, L->h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));

@@ -6,9 +6,7 @@ bool launch_loss_pair_g3(int model, cudaStream_t s, const LossArgs& a, unsigned 
   switch(model) {
     BBMCU_LOSS_CASE_PAIR(M_Bagher)
     BBMCU_LOSS_CASE_PAIR(M_EPD)
-#ifdef BBMCU_WITH_HE
     BBMCU_LOSS_CASE_PAIR(M_He) BBMCU_LOSS_CASE_PAIR(M_HeWestin) BBMCU_LOSS_CASE_PAIR(M_HeHolzschuch) BBMCU_LOSS_CASE_PAIR(M_NganHe)
-#endif
     default: return false;
   }
 }

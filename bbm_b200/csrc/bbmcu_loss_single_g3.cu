@@ -6,9 +6,7 @@ bool launch_loss_single_g3(int model, cudaStream_t s, const LossArgs& a, unsigne
   switch(model) {
     BBMCU_LOSS_CASE_SINGLE(M_Bagher)
     BBMCU_LOSS_CASE_SINGLE(M_EPD)
-#ifdef BBMCU_WITH_HE
     BBMCU_LOSS_CASE_SINGLE(M_He) BBMCU_LOSS_CASE_SINGLE(M_HeWestin) BBMCU_LOSS_CASE_SINGLE(M_HeHolzschuch) BBMCU_LOSS_CASE_SINGLE(M_NganHe)
-#endif
     default: return false;
   }
 }

@@ -4,9 +4,7 @@
 #pragma once
 #include "bbmcu_lobes.cuh"
 #include "bbmcu_epd.cuh"
-#ifdef BBMCU_WITH_HE
 #include "bbmcu_he.cuh"
-#endif
 
 namespace bbmcu {
 
@@ -52,20 +50,19 @@ BBMCU_MODEL(M_Ribardiere, Microfacet<NdfStudentT<false>, GUncorrelated, FresnelC
 BBMCU_MODEL(M_RibardiereAnisotropic, Microfacet<NdfStudentT<true>, GUncorrelated, FresnelCookIor, 1, true>)
 BBMCU_MODEL(M_Bagher, Microfacet<NdfSGD, GUncorrelated, FresnelBagher, 2, true>)          // bagher.h:62-68
 BBMCU_MODEL(M_EPD, Microfacet<NdfEPD, GVanGinneken, FresnelComplexScalar, 1, false>)      // holzschuchpacanowski.h:34-42
-#ifdef BBMCU_WITH_HE
 BBMCU_MODEL(M_He, HeModel<HE_VARIANT_HE>)
 BBMCU_MODEL(M_HeWestin, HeModel<HE_VARIANT_WESTIN>)
 BBMCU_MODEL(M_HeHolzschuch, HeModel<HE_VARIANT_HOLZSCHUCH>)
 BBMCU_MODEL(M_NganHe, HeModel<HE_VARIANT_NGAN>)
-#endif
+
+// floats of device-side tables appended to a lobe's attribute block (the He family's 90-bin sampling CDF)
+template<class M> struct TableFloats { static constexpr int N = 0; };
+template<int V> struct TableFloats<HeModel<V>> { static constexpr int N = HeModel<V>::NT; };
+BBMCU_HD constexpr int table_floats_of(int model) { return (model >= M_He && model <= M_NganHe) ? kHeCdfBins : 0; }
 
 // uniform (per-launch) dispatch on a model id: calls f((ModelOf<id>::type*)nullptr)
 #define BBMCU_CASES_EPD BBMCU_CASE(M_EPD)
-#ifdef BBMCU_WITH_HE
 #define BBMCU_CASES_HE BBMCU_CASE(M_He) BBMCU_CASE(M_HeWestin) BBMCU_CASE(M_HeHolzschuch) BBMCU_CASE(M_NganHe)
-#else
-#define BBMCU_CASES_HE
-#endif
 #define BBMCU_ALL_CASES \
     BBMCU_CASE(M_Lambertian) BBMCU_CASE(M_OrenNayar) BBMCU_CASE(M_Phong) BBMCU_CASE(M_NganBlinnPhong) \
     BBMCU_CASE(M_Lafortune) BBMCU_CASE(M_NganLafortune) BBMCU_CASE(M_Ward) BBMCU_CASE(M_WardDuer) \

@@ -16,7 +16,16 @@ using namespace bbmcu;
 static thread_local std::string g_err;
 #define GUARD(...) try { __VA_ARGS__; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
 
-template<class Op> static void run(const Op& op, size_t n) { for(size_t i=0; i < n; i += kVec) op.group(i); }
+template<class Op> static void run(const Op& op, size_t n)
+{
+  if constexpr (Op::kHasBsdf)
+  {
+    BsdfDesc b = op.bsdf;                       // what the kernel prologue does per thread block
+    if(b.n_tables) { bsdf_tables_phase1(b, op.component, 0, 1); for(int l=0; l < b.n_lobes; ++l) bsdf_tables_phase2(b, l); }
+    for(size_t i=0; i < n; i += kVec) op.group(i, b);
+  }
+  else for(size_t i=0; i < n; i += kVec) op.group(i);
+}
 
 extern "C" {
 const char* hostsim_last_error() { return g_err.c_str(); }
