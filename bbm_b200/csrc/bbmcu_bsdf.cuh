@@ -50,6 +50,8 @@ BBMCU_D void lobe_sample(int model, const float* a, f3 out, f2 xi, int component
 struct BsdfGeneric
 {
   static constexpr bool kTables = true;
+  static constexpr bool kFusedSample = false;
+  BBMCU_D static void sample_dir(const BsdfDesc&, f3, f2, int, f3&, int&) {}
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component)
   {
     if(!b.aggregate) return lobe_eval(b.model[0], b.attrs + b.offset[0], in, out, component);
@@ -123,11 +125,18 @@ BBMCU_D void bsdf_tables_phase2(BsdfDesc& b, int tid)
     });
 }
 
+// models whose sample() returns pdf(direction, out) as the sample's pdf, and expose the direction-only half
+template<class M, class = void> struct SamplePdfIsPdf { static constexpr bool value = false; };
+template<class M> struct SamplePdfIsPdf<M, typename std::enable_if<M::kSamplePdfIsPdf>::type> { static constexpr bool value = true; };
+
 // ---- compile-time single model (no dispatch, smallest register footprint) ------------------------
 template<class M>
 struct BsdfSingle
 {
   static constexpr bool kTables = TableFloats<M>::N > 0;
+  static constexpr bool kFusedSample = SamplePdfIsPdf<M>::value;
+  BBMCU_D static void sample_dir(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag)
+  { if constexpr (kFusedSample) M::sample_dir(out, xi, b.attrs, component, dir, flag); }
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component) { return M::template eval<float>(in, out, b.attrs, component); }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component) { return M::reflectance(out, b.attrs, component); }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component) { return M::pdf(in, out, b.attrs, component); }

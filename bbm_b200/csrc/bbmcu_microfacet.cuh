@@ -33,6 +33,14 @@ template<class T> BBMCU_D T fresnel_cook(const T& eta, float c)
   T b = (c*(g + c) - 1.0f) / (c*(g - c) + 1.0f);
   return m_max(0.5f * (a*a) * (1.0f + b*b), 0.0f);
 }
+// float overload: g keeps the IEEE square root (g - c cancels for eta -> 1), the two quotients are final values
+BBMCU_D float fresnel_cook(const float& eta, float c)
+{
+  float g = m_safe_sqrt(eta*eta + c*c - 1.0f);
+  float a = q_div(g - c, g + c);
+  float b = q_div(c*(g + c) - 1.0f, c*(g - c) + 1.0f);
+  return m_max(0.5f * (a*a) * (1.0f + b*b), 0.0f);
+}
 // Schlick of a reflectance at normal incidence: R0 + (1-R0) * pow(1-c, 5.0)  (fresnel_schlick.h:48-51).
 // pow(float, 5.0) is a double, so the product and the sum run in double and are rounded once.
 BBMCU_D double schlick_w(float c) { double w = (double)(1.0f - c); double w2 = w*w; return w2*w2*w; }
@@ -183,47 +191,70 @@ struct NdfGGX
   {
     if(!(h.z > 0.0f)) return T(0.0f);
     T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
-    T sx = h.x/ax, sy = h.y/ay;
-    T t = (sx*sx + sy*sy) + h.z*h.z;
-    return m_rcp(kPi * (ax*ay) * (t*t));
+    if constexpr (std::is_same<T, float>::value)
+    {
+      float sx = h.x * q_rcp(ax), sy = ANISO ? h.y * q_rcp(ay) : h.y * q_rcp(ax);
+      float t = (sx*sx + sy*sy) + h.z*h.z;
+      return q_rcp(kPi * (ax*ay) * (t*t));
+    }
+    else
+    {
+      T sx = h.x/ax, sy = h.y/ay;
+      T t = (sx*sx + sy*sy) + h.z*h.z;
+      return m_rcp(kPi * (ax*ay) * (t*t));
+    }
   }
   template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
   {
     if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
     T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     T r2 = ax*ay;
-    return g1_tail(r2 * tanTheta2(v));
+    if constexpr (std::is_same<T, float>::value) return g1_tail(r2 * q_div(sinTheta2(v), v.z*v.z));
+    else return g1_tail(r2 * tanTheta2(v));
   }
-  // 2.0 / (1.0 + sqrt(1.0 + x)) evaluated in double by the reference (ggx.h:184-187)
-  BBMCU_D static float g1_tail(float x) { return (float)(2.0 / (double)(float)(1.0 + sqrt(1.0 + (double)x))); }
+  // 2.0 / (1.0 + sqrt(1.0 + x)): the reference evaluates this in double (ggx.h:184-187); a final value, so quick ops
+  BBMCU_D static float g1_tail(float x) { return 2.0f * q_rcp(1.0f + q_sqrt(1.0f + x)); }
   template<int N> BBMCU_D static Dual<N> g1_tail(const Dual<N>& x) { float s = sqrtf(1.0f + x.v); float den = 1.0f + s; return chain(x, 2.0f/den, -1.0f/(den*den*s)); }
 
   BBMCU_D static float pdf(f3 view, f3 m, const float* a)
   {
     if(!(m.z > 0.0f)) return 0.0f;
     float p = D<float>(m, a);
-    p *= G1<float>(view, m, a) * fabsf(dot(view, m)) / view.z;
+    p *= q_div(G1<float>(view, m, a) * fabsf(dot(view, m)), view.z);
     return (p > 0.0f) ? p : 0.0f;
   }
-  // Heitz 2017 visible-normal sampling (ggx.h:86-107)
+  // Heitz 2017 visible-normal sampling (ggx.h:86-107).  Every step up to the normal n reproduces the reference's
+  // roundings (no FMA, IEEE sqrt / divide, its float-double mix): the two differences in it - (xi1 - a)/(1 - a) for
+  // grazing views and 1 - P1^2 - P2^2 for xi0 -> 1 - cancel, so a last-bit change upstream would move the sampled
+  // direction by far more than 1e-5.  Spots where a float operation provably returns the reference's double result
+  // rounded to float use the float operation:
+  //   * cross(vs, z) and cross(T1, vs) with their exact zeros removed;
+  //   * a = (float)(1.0 / (1.0 + (double)vs.z)): 1 + vs.z = hi + lo exactly (Fast2Sum), one Newton step on the IEEE
+  //     reciprocal of hi with fused residuals gives the correctly rounded quotient;
+  //   * (double)(xi1 / a) * pi and 1.0 * r * sin(phi): products of two floats are exact in double, so the float
+  //     product is the same single rounding;
+  //   * cos / sin(phi): the host libm's values (bbmcu_libm.cuh), one shared quadrant reduction.
+  // Only the final normalisation of the stretched normal is a quick op (nothing cancels after it).
   BBMCU_D static f3 sample(f3 view, f2 xi, const float* a)
   {
     if(!xi_valid(xi)) return make_f3(0, 0, 0);
     float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
-    f3 T1 = (vs.z < 0.99999988079071044921875f) ? normalize(cross(vs, make_f3(0, 0, 1))) : make_f3(1, 0, 0);
-    f3 T2 = cross(T1, vs);
-    float aa = (float)(1.0 / (1.0 + (double)vs.z));
+    f3 T1 = make_f3(1, 0, 0);
+    if(vs.z < 0.99999988079071044921875f) { float rr = 1.0f / sqrtf(vs.y*vs.y + vs.x*vs.x); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
+    f3 T2 = make_f3(T1.y*vs.z, -(T1.x*vs.z), T1.x*vs.y - T1.y*vs.x);
+    float hi = 1.0f + vs.z, lo = vs.z - (hi - 1.0f);
+    float r0 = 1.0f / hi;
+    float aa = fmaf(r0, fmaf(-lo, r0, fmaf(-hi, r0, 1.0f)), r0);
     float r = sqrtf(xi.x);
     bool lower = xi.y < aa;
-    float phi = (float)((lower ? (double)(xi.y/aa) : 1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
-    float cp = cosf(phi), sp = sinf(phi);
+    float phi = lower ? (xi.y / aa) * kPi : (float)((1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
+    float cp, sp; glibc_sincosf_both(phi, sp, cp);
     float P1 = r*cp;
-    float P2 = (float)((lower ? 1.0 : (double)vs.z) * (double)r * (double)sp);
-    // safe_sqrt(1.0 - P1*P1 - P2*P2) is a double, but double * float-array converts the scalar to float first
+    float P2 = lower ? r*sp : (float)((double)vs.z * (double)r * (double)sp);
     float w = (float)safe_sqrt_d(1.0 - (double)(P1*P1) - (double)(P2*P2));
     f3 n = (T1*P1 + T2*P2) + vs*w;
-    return normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
+    return q_normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
   }
 };
 
@@ -494,8 +525,9 @@ struct Microfacet
   }
   BBMCU_D static Spec<float> divide_out(const Spec<float>& s, float zz)
   {
-    double n = norm(), z = zz;
-    return Spec<float>((float)((double)s.r / n / z), (float)((double)s.g / n / z), (float)((double)s.b / n / z));
+    // a double division chain in the reference (microfacet.h:100); a final value here: one quick reciprocal
+    float k = q_rcp((float)norm() * zz);
+    return Spec<float>(s.r*k, s.g*k, s.b*k);
   }
   template<int N> BBMCU_D static Spec<Dual<N>> divide_out(const Spec<Dual<N>>& s, float zz)
   {
@@ -517,16 +549,22 @@ struct Microfacet
     if(!(component & FLAG_SPECULAR) || !((out.z > 0.0f) && (in.z > 0.0f))) return 0.0f;
     f3 h = halfway(in, out);
     if(h.z < 0.0f) h = -h;
-    return (float)((double)NDF::pdf(out, h, a + OFF_NDF) / (4.0 * (double)fabsf(dot(out, h))));
+    return q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(dot(out, h)));
   }
-  BBMCU_D static void sample(f3 out, f2 xi, const float* a, int component, f3& dir, float& pdfv, int& flag)
+  // sample.pdf is pdf(sample.direction, out) (microfacet.h:138): fused sample -> eval -> pdf passes evaluate it once
+  static constexpr bool kSamplePdfIsPdf = true;
+  BBMCU_D static void sample_dir(f3 out, f2 xi, const float* a, int component, f3& dir, int& flag)
   {
-    dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
+    dir = make_f3(0, 0, 0); flag = FLAG_NONE;
     if(!(component & FLAG_SPECULAR) || !xi_valid(xi) || !(out.z > 0.0f)) return;
     f3 m = NDF::sample(out, xi, a + OFF_NDF);
     dir = reflect(out, m);
-    pdfv = pdf(dir, out, a, component);
     flag = FLAG_SPECULAR;
+  }
+  BBMCU_D static void sample(f3 out, f2 xi, const float* a, int component, f3& dir, float& pdfv, int& flag)
+  {
+    sample_dir(out, xi, a, component, dir, flag);
+    pdfv = (flag != FLAG_NONE) ? pdf(dir, out, a, component) : 0.0f;
   }
   // perfect-mirror approximation F(eta, out.z) / N * 4.0 (microfacet.h:186-199), times scale
   BBMCU_D static Spec<float> reflectance(f3 out, const float* a, int component)

@@ -119,7 +119,7 @@ BBMCU_API int  bbmcu_spherical_dirs(bbmcu_ctx* ctx, const bbmcu_spherical_grid* 
 BBMCU_API int  bbmcu_merl_read(bbmcu_ctx* ctx, const char* filename, float* rgb);
 BBMCU_API int  bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb);     /* inverse of the above */
 
-/* ---- losses (include/loss/*.h, include/bbm/sampledlossfunction.h:62-87) ---------------------------------- */
+/* ---- losses (include/loss/{cosine_weighted_l2,cosine_weighted_log}.h, include/bbm/sampledlossfunction.h:62-87) ---------------------------------- */
 /* The reference evaluates  loss = (1/N) sum_i e(in_i, out_i, fitted.eval(in_i,out_i), reference.eval(in_i,out_i))
  * over a linearizer.  A bbmcu_loss fixes metric, linearizer, component and the reference operand; the
  * reference values are tabulated once per sample index (they never change during a fit).
