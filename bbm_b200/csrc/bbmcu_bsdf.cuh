@@ -52,6 +52,7 @@ struct BsdfGeneric
   static constexpr bool kTables = true;
   static constexpr bool kFusedSample = false;
   BBMCU_D static void sample_dir(const BsdfDesc&, f3, f2, int, f3&, int&) {}
+  BBMCU_D static void eval_pdf(const BsdfDesc&, f3, f3, int, Spec<float>&, float&) {}
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component)
   {
     if(!b.aggregate) return lobe_eval(b.model[0], b.attrs + b.offset[0], in, out, component);
@@ -137,6 +138,8 @@ struct BsdfSingle
   static constexpr bool kFusedSample = SamplePdfIsPdf<M>::value;
   BBMCU_D static void sample_dir(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag)
   { if constexpr (kFusedSample) M::sample_dir(out, xi, b.attrs, component, dir, flag); }
+  BBMCU_D static void eval_pdf(const BsdfDesc& b, f3 in, f3 out, int component, Spec<float>& e, float& p)
+  { if constexpr (kFusedSample) M::eval_pdf(in, out, b.attrs, component, e, p); }
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component) { return M::template eval<float>(in, out, b.attrs, component); }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component) { return M::reflectance(out, b.attrs, component); }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component) { return M::pdf(in, out, b.attrs, component); }

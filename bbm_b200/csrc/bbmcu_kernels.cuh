@@ -115,18 +115,19 @@ template<class B> struct SampleEvalPdfOp
     for(int k=0; k < kVec; ++k)
     {
       f3 o = b.get(k), dd;
+      Spec<float> s;
       if constexpr (B::kFusedSample)
       {
         B::sample_dir(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, f[k]);
-        p.v[k] = B::pdf(bsdf, dd, o, component);
+        B::eval_pdf(bsdf, dd, o, component, s, p.v[k]);
         sp.v[k] = (f[k] != FLAG_NONE) ? p.v[k] : 0.0f;
       }
       else
       {
         B::sample(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, sp.v[k], f[k]);
         p.v[k] = B::pdf(bsdf, dd, o, component);
+        s = B::eval(bsdf, dd, o, component);
       }
-      Spec<float> s = B::eval(bsdf, dd, o, component);
       d.set(k, dd); c.set(k, make_f3(s.r, s.g, s.b));
     }
     store4x3(dir, i, n, aligned, d); store4(spdf, i, n, aligned, sp); store4i(flag, i, n, aligned, f);

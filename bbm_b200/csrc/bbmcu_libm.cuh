@@ -123,28 +123,34 @@ template<bool COS> BBMCU_D float glibc_sincosf(float y)
   }
   return COS ? cosf(y) : sinf(y);                    // never reached by the linearizers (angles in [-2pi, 2pi])
 }
-// sinf and cosf of the same argument with one quadrant reduction (each result identical to the separate calls)
+// sinf and cosf of the same argument with one quadrant reduction; each result is bit-identical to the separate calls.
+// Round-to-nearest is symmetric under negation, so "polynomial with negated constants" (glibc's second table) and
+// "odd polynomial of a negated argument" are exactly the negated plain polynomials: the signs are applied at the end.
 BBMCU_D void glibc_sincosf_both(float y, float& sn, float& cs)
 {
+  const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
+  const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
   double x = y;
   uint32_t top = (f2u(y) >> 20) & 0x7ff;
-  if(top < 0x3f4) {
-    if(top < 0x398) { sn = y; cs = 1.0f; return; }
-    double x2 = x*x;
-    sn = glibc_sincos_poly(x, x2, false, 0); cs = glibc_sincos_poly(x, x2, false, 1);
-    return;
-  }
-  if(top < 0x42f) {
+  int n = 0;
+  if(top < 0x3f4) { if(top < 0x398) { sn = y; cs = 1.0f; return; } }
+  else if(top < 0x42f)
+  {
     double r = x * 0x1.45F306DC9C883p+23;
-    int n = ((int32_t)r + 0x800000) >> 24;
+    n = ((int32_t)r + 0x800000) >> 24;
     x = x - (double)n * 0x1.921FB54442D18p0;
-    double sg = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-    double xs = x*sg, x2 = x*x;
-    sn = glibc_sincos_poly(xs, x2, (n & 2) != 0, n);
-    cs = glibc_sincos_poly(xs, x2, (n & 2) != 0, n ^ 1);
-    return;
   }
-  sn = sinf(y); cs = cosf(y);
+  else { sn = sinf(y); cs = cosf(y); return; }
+  double x2 = x*x;
+  double x3 = x*x2, ts = s2 + x2*s3, x7 = x3*x2, ss = x + x3*s1;
+  float A = (float)(ss + x7*ts);                                  // sin polynomial of the reduced argument
+  double x4 = x2*x2, t2 = c3 + x2*c4, t1 = c0 + x2*c1, x6 = x4*x2, cc = t1 + x4*c2;
+  float B = (float)(cc + x6*t2);                                  // cos polynomial
+  const bool flip_a = ((n & 3) == 1) || ((n & 3) == 2);           // sign[n & 3] = {+, -, -, +}
+  const bool flip_b = (n & 2) != 0;                               // the negated-constant table
+  if(flip_a) A = -A;
+  if(flip_b) B = -B;
+  if(n & 1) { sn = B; cs = A; } else { sn = A; cs = B; }
 }
 BBMCU_D float glibc_sinf(float y) { return glibc_sincosf<false>(y); }
 BBMCU_D float glibc_cosf(float y) { return glibc_sincosf<true>(y); }

@@ -219,14 +219,16 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, L->h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     // launch shape: about 8 resident blocks per SM over all K
     const size_t n = L->count;
+    const bool static_shape = (shape.n_lobes == 1 && !shape.aggregate) || (shape.n_lobes == 2 && shape.aggregate && shape.model[0] == M_Lambertian);
     unsigned max_bx = (unsigned)std::max<size_t>(1, (n + kLossThreads - 1) / kLossThreads);
     unsigned bx = (unsigned)std::max<size_t>(1, ((size_t)ctx->sm_count*8 + K - 1) / K);
     if(bx > max_bx) bx = max_bx;
+    if(static_shape) bx = (unsigned)std::max<size_t>(1, (n + kTileSamples - 1) / kTileSamples);     // one partial row per sample tile
     grow(L->d_partial, L->partial_cap, K*(size_t)bx*cols);
     grow(L->d_result, L->result_cap, K*(size_t)cols);
     LossArgs a;
     a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = n; a.attrs = L->d_attrs; a.attr_stride = A; a.n_attrs = A;
-    a.metric = L->metric; a.component = L->component; a.want_grad = want_grad ? 1 : 0; a.partial = L->d_partial; a.P = P;
+    a.metric = L->metric; a.component = L->component; a.want_grad = want_grad ? 1 : 0; a.partial = L->d_partial; a.P = P; a.sm_count = ctx->sm_count;
     bool done = false;
     if(n > 0)
     {

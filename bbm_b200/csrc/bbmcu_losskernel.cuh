@@ -2,11 +2,12 @@
 // evaluate the fitted BSDF (and its parameter jacobian through dual numbers), apply the metric and
 // reduce - replaces the scalar loop of include/bbm/sampledlossfunction.h:78-87.
 //
-// Launch shape: grid (blocks_x, K) - block (bx, k) handles parameter set k over a strided slice of
-// the shard's samples.  Reduction: FP64 per-thread accumulators -> warp shuffle -> shared ->
-// one partial row per block; a second tiny kernel adds the partial rows in fixed order, so the
-// result is deterministic and independent of scheduling (totals are judged
-// against a double accumulation of the per-sample terms).
+// Two launch shapes.  Compile-time BSDF shapes (one model, or Aggregate(Lambertian, model) - every entry of the
+// reference's fits/*.fit): the sample-stationary tile kernel below.  Arbitrary run-time aggregates: k_loss_generic
+// (bbmcu_loss.cu), grid (blocks_x, K), block (bx, k) = parameter set k over a strided slice of the samples.
+// Either way one partial row per block, and a second tiny kernel adds the rows in fixed order, so the result is
+// deterministic and independent of scheduling (totals are judged against a double accumulation
+// of the per-sample terms).
 #pragma once
 #include "bbmcu_ctx.hpp"
 #include "bbmcu_lossop.cuh"
@@ -27,60 +28,118 @@ struct LossArgs
   int want_grad;
   double* partial;        // K x blocks_x x (1 + P)
   int P;
+  int sm_count;
 };
 
 constexpr int kLossThreads = 256;
 
 // LossT::sample(attrs, metric, component, in, out, ref, grad[P], want_grad) -> e   (LossSingle / LossPair)
-template<class LossT>
-__global__ void __launch_bounds__(kLossThreads) k_loss_static(const LossArgs a)
+// ---- sample-stationary variant: the launch shape for batched passes --------------------------------
+// A block owns a tile of kTileSPT * 256 samples, loads them ONCE into registers and loops over its range of parameter
+// sets (attribute blocks staged in shared memory).  Everything that depends on the directions only - half vector,
+// dots, geometric terms, metric weights - is loop invariant and hoisted out of the parameter loop by the compiler, and
+// the 36 B/sample of L2 traffic are paid once per tile instead of once per parameter set.  Per-thread sums are float
+// over the thread's kTileSPT samples, warp-shuffled in float (128 terms), and enter FP64 at the cross-warp step; block
+// partials are written per (parameter set, tile) and added in fixed order by k_loss_finish: deterministic, and a
+// parameter set's result does not depend on which other sets share the launch.
+constexpr int kTileSPT = 4;
+constexpr int kTileKChunk = 8;
+constexpr int kTileSamples = kTileSPT * kLossThreads;
+
+template<class LossT, bool WG>
+__global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, int K, int k_per_block)
 {
   constexpr int P = LossT::P;
-  __shared__ float s_attr[kMaxAttrs];
-  __shared__ double s_red[kLossThreads/32][1 + P];
-  const int k = blockIdx.y;
-  for(int i = threadIdx.x; i < a.n_attrs; i += blockDim.x) s_attr[i] = a.attrs[(size_t)k*a.attr_stride + i];
-  __syncthreads();
-  double acc[1 + P];
+  constexpr int C = WG ? 1 + P : 1;
+  extern __shared__ float s_attr_tile[];                       // (k1 - k0) x n_attrs
+  __shared__ float s_red[kTileKChunk][kLossThreads/32][C];
+  const int tile = blockIdx.x;
+  const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
+  for(int i = threadIdx.x; i < (k1 - k0)*a.n_attrs; i += blockDim.x)
+    s_attr_tile[i] = a.attrs[(size_t)(k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs)];
+  f3 in[kTileSPT], out[kTileSPT]; Spec<float> ref[kTileSPT]; bool valid[kTileSPT];
 #pragma unroll
-  for(int j=0; j <= P; ++j) acc[j] = 0.0;
-  const bool wg = a.want_grad != 0;
-  for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x*blockDim.x)
+  for(int s=0; s < kTileSPT; ++s)
   {
-    f3 in = make_f3(__ldg(a.in + i), __ldg(a.in + a.n + i), __ldg(a.in + 2*a.n + i));
-    f3 out = make_f3(__ldg(a.out + i), __ldg(a.out + a.n + i), __ldg(a.out + 2*a.n + i));
-    Spec<float> ref(__ldg(a.ref + i), __ldg(a.ref + a.n + i), __ldg(a.ref + 2*a.n + i));
-    float g[P];
-    float e = LossT::sample(s_attr, a.metric, a.component, in, out, ref, g, wg);
-    acc[0] += (double)e;
-    if(wg) {
-#pragma unroll
-      for(int j=0; j < P; ++j) acc[1 + j] += (double)g[j];
-    }
+    const size_t i = (size_t)tile*kTileSamples + (size_t)s*kLossThreads + threadIdx.x;
+    valid[s] = i < a.n;
+    const size_t ii = valid[s] ? i : 0;
+    in[s] = make_f3(__ldg(a.in + ii), __ldg(a.in + a.n + ii), __ldg(a.in + 2*a.n + ii));
+    out[s] = make_f3(__ldg(a.out + ii), __ldg(a.out + a.n + ii), __ldg(a.out + 2*a.n + ii));
+    ref[s] = Spec<float>(__ldg(a.ref + ii), __ldg(a.ref + a.n + ii), __ldg(a.ref + 2*a.n + ii));
   }
+  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for(int j=0; j <= P; ++j)
+  for(int kc = k0; kc < k1; kc += kTileKChunk)
   {
-    double v = acc[j];
+    const int nkk = min(kTileKChunk, k1 - kc);
+    for(int kk=0; kk < nkk; ++kk)
+    {
+      const float* at = s_attr_tile + (size_t)(kc + kk - k0)*a.n_attrs;
+      float acc[C];
 #pragma unroll
-    for(int o=16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if(lane == 0) s_red[warp][j] = v;
-  }
-  __syncthreads();
-  if(threadIdx.x <= P)
-  {
-    double v = 0.0;
+      for(int j=0; j < C; ++j) acc[j] = 0.0f;
 #pragma unroll
-    for(int w=0; w < kLossThreads/32; ++w) v += s_red[w][threadIdx.x];
-    a.partial[((size_t)k*gridDim.x + blockIdx.x)*(1 + a.P) + threadIdx.x] = v;
+      for(int s=0; s < kTileSPT; ++s)
+      {
+        if(!valid[s]) continue;
+        float g[P];
+        const float e = LossT::sample(at, a.metric, a.component, in[s], out[s], ref[s], g, WG);
+        acc[0] += e;
+        if(WG) {
+#pragma unroll
+          for(int j=0; j < P; ++j) acc[1 + j] += g[j];
+        }
+      }
+#pragma unroll
+      for(int j=0; j < C; ++j)
+      {
+        float v = acc[j];
+#pragma unroll
+        for(int o=16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if(lane == 0) s_red[kk][warp][j] = v;
+      }
+    }
+    __syncthreads();
+    if((int)threadIdx.x < nkk*(1 + a.P))
+    {
+      const int kk = threadIdx.x / (1 + a.P), j = threadIdx.x % (1 + a.P);
+      double v = 0.0;
+      if(j < C) {
+#pragma unroll
+        for(int w=0; w < kLossThreads/32; ++w) v += (double)s_red[kk][w][j];
+      }
+      a.partial[((size_t)(kc + kk)*gridDim.x + tile)*(1 + a.P) + j] = v;
+    }
+    __syncthreads();
   }
 }
 
+// launch shape of the tile kernel for n samples, K parameter sets of n_attrs floats: tiles x k-splits
+inline void loss_tile_shape(size_t n, size_t K, int n_attrs, int sm_count, unsigned& tiles, unsigned& ksplit, int& k_per_block)
+{
+  tiles = (unsigned)((n + kTileSamples - 1) / kTileSamples);
+  if(tiles < 1) tiles = 1;
+  const size_t smem_k = (size_t)(40*1024) / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the static shared-memory budget
+  size_t split_fit = (K + smem_k - 1) / (smem_k ? smem_k : 1);
+  size_t split_fill = ((size_t)sm_count*16 + tiles - 1) / tiles;                        // ~16 blocks per SM over the launch
+  size_t sp = split_fit > split_fill ? split_fit : split_fill;
+  if(sp > K) sp = K;
+  if(sp < 1) sp = 1;
+  k_per_block = (int)((K + sp - 1) / sp);
+  ksplit = (unsigned)((K + k_per_block - 1) / k_per_block);
+}
+
+// internal linkage (see bbmcu_tables.cuh).  blocks_x is the tile count the caller sized `partial` with.
 template<class LossT> static void launch_loss_static(cudaStream_t s, const LossArgs& a, unsigned blocks_x, unsigned K)
 {
   bind_device_tables();
-  k_loss_static<LossT><<<dim3(blocks_x, K), kLossThreads, 0, s>>>(a);
+  unsigned tiles, ksplit; int kpb;
+  loss_tile_shape(a.n, K, a.n_attrs, a.sm_count, tiles, ksplit, kpb);
+  const size_t smem = (size_t)kpb*a.n_attrs*sizeof(float);
+  (void)blocks_x;
+  if(a.want_grad) k_loss_tile<LossT, true><<<dim3(tiles, ksplit), kLossThreads, smem, s>>>(a, (int)K, kpb);
+  else            k_loss_tile<LossT, false><<<dim3(tiles, ksplit), kLossThreads, smem, s>>>(a, (int)K, kpb);
 }
 
 // one translation unit per group of models (compile time); returns false if `model` is not in that group

@@ -20,12 +20,14 @@ constexpr int kMaxParams = 32;      // fit parameters per BSDF (Aggregate(Lamber
 
 enum : int { METRIC_NGAN_L2 = 0, METRIC_LOW_L2, METRIC_BIERON_L2, METRIC_LOW_LOG, METRIC_BIERON_LOG, METRIC_STANDARD_LOG };
 
-BBMCU_D double metric_weight(int metric, double s, f3 in, f3 out)
+// w(in, out): sin_i sin_o (ngan, standardLog), sin_i (low*), max(cos_o, 0) sin_i sin_o (bieron*).  The reference forms
+// e * w left to right in double and rounds once; every factor is non-negative, so float products are within 3e-7.
+BBMCU_D float metric_weight(int metric, f3 in, f3 out)
 {
   switch(metric) {
-    case METRIC_NGAN_L2: case METRIC_STANDARD_LOG: return s * (double)sinTheta(in) * (double)sinTheta(out);
-    case METRIC_LOW_L2: case METRIC_LOW_LOG:       return s * (double)sinTheta(in);
-    default:                                       return s * (double)fmaxf(out.z, 0.0f) * (double)sinTheta(in) * (double)sinTheta(out);
+    case METRIC_NGAN_L2: case METRIC_STANDARD_LOG: return q_sinTheta(in) * q_sinTheta(out);
+    case METRIC_LOW_L2: case METRIC_LOW_LOG:       return q_sinTheta(in);
+    default:                                       return fmaxf(out.z, 0.0f) * q_sinTheta(in) * q_sinTheta(out);
   }
 }
 
@@ -33,18 +35,19 @@ BBMCU_D double metric_weight(int metric, double s, f3 in, f3 out)
 BBMCU_D float loss_term(int metric, f3 in, f3 out, const Spec<float>& v, const Spec<float>& r, Spec<float>* dv)
 {
   float c = fmaxf(in.z, 0.0f);
+  float w = metric_weight(metric, in, out);
   if(metric <= METRIC_BIERON_L2)
   {
     float tr = (v.r - r.r)*c, tg = (v.g - r.g)*c, tb = (v.b - r.b)*c;
-    double s = ((0.0 + (double)tr*(double)tr) + (double)tg*(double)tg) + (double)tb*(double)tb;
-    if(dv) { float k = (float)metric_weight(metric, 2.0, in, out) * c; *dv = Spec<float>(k*tr, k*tg, k*tb); }
-    return (float)metric_weight(metric, s, in, out);
+    float s = (tr*tr + tg*tg) + tb*tb;
+    if(dv) { float k = 2.0f * w * c; *dv = Spec<float>(k*tr, k*tg, k*tb); }
+    return s * w;
   }
   float ar = 1.0f + v.r*c, ag = 1.0f + v.g*c, ab = 1.0f + v.b*c;
   float dr = logf(ar) - logf(1.0f + r.r*c), dg = logf(ag) - logf(1.0f + r.g*c), db = logf(ab) - logf(1.0f + r.b*c);
-  double s = ((0.0 + (double)dr*(double)dr) + (double)dg*(double)dg) + (double)db*(double)db;
-  if(dv) { float k = (float)metric_weight(metric, 2.0, in, out) * c; *dv = Spec<float>(k*dr/ar, k*dg/ag, k*db/ab); }
-  return (float)metric_weight(metric, s, in, out);
+  float s = (dr*dr + dg*dg) + db*db;
+  if(dv) { float k = 2.0f * w * c; *dv = Spec<float>(k*q_div(dr, ar), k*q_div(dg, ag), k*q_div(db, ab)); }
+  return s * w;
 }
 
 // ---- fit-parameter layout of a model: which attribute floats are fit parameters ----------------------

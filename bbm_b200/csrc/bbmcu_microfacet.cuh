@@ -33,8 +33,10 @@ template<class T> BBMCU_D T fresnel_cook(const T& eta, float c)
   T b = (c*(g + c) - 1.0f) / (c*(g - c) + 1.0f);
   return m_max(0.5f * (a*a) * (1.0f + b*b), 0.0f);
 }
-// float overload: g keeps the IEEE square root (g - c cancels for eta -> 1), the two quotients are final values
-BBMCU_D float fresnel_cook(const float& eta, float c)
+// quick variant for eval: g keeps the IEEE square root (g - c cancels for eta -> 1), the two quotients are final values.
+// reflectance() keeps the IEEE template above: it feeds the lobe-selection weights of Aggregate sampling, where a
+// last-bit change of a weight moves the renormalised xi and with it the sampled direction.
+BBMCU_D float fresnel_cook_q(const float& eta, float c)
 {
   float g = m_safe_sqrt(eta*eta + c*c - 1.0f);
   float a = q_div(g - c, g + c);
@@ -62,16 +64,20 @@ template<class T> BBMCU_D T fresnel_complex(const T& n, const T& k, float c)
 }
 
 // Fresnel policies: NA attribute floats; eval returns T (scalar) or Spec<T> (spectral).
-struct FresnelCookIor      { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_cook(a[0], c); } };
-struct FresnelSchlickR0    { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_schlick(a[0], c); } };
-struct FresnelComplexScalar{ static constexpr int NA = 2; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_complex(a[0], a[1], c); } };
+struct FresnelCookIor      { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_cook(a[0], c); }
+                             template<class T> BBMCU_D static T evalq(const T* a, float c) { if constexpr (std::is_same<T, float>::value) return fresnel_cook_q(a[0], c); else return fresnel_cook(a[0], c); } };
+struct FresnelSchlickR0    { static constexpr int NA = 1; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_schlick(a[0], c); }  template<class T> BBMCU_D static T evalq(const T* a, float c) { return eval<T>(a, c); } };
+struct FresnelComplexScalar{ static constexpr int NA = 2; template<class T> BBMCU_D static T eval(const T* a, float c) { return fresnel_complex(a[0], a[1], c); }  template<class T> BBMCU_D static T evalq(const T* a, float c) { return eval<T>(a, c); } };
 struct FresnelComplexRGB   { static constexpr int NA = 6; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
-    return Spec<T>(fresnel_complex(a[0], a[3], c), fresnel_complex(a[1], a[4], c), fresnel_complex(a[2], a[5], c)); } };
+    return Spec<T>(fresnel_complex(a[0], a[3], c), fresnel_complex(a[1], a[4], c), fresnel_complex(a[2], a[5], c)); }
+                             template<class T> BBMCU_D static Spec<T> evalq(const T* a, float c) { return eval<T>(a, c); } };
 struct FresnelSchlickRGB   { static constexpr int NA = 3; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
-    return Spec<T>(fresnel_schlick(a[0], c), fresnel_schlick(a[1], c), fresnel_schlick(a[2], c)); } };
+    return Spec<T>(fresnel_schlick(a[0], c), fresnel_schlick(a[1], c), fresnel_schlick(a[2], c)); }
+                             template<class T> BBMCU_D static Spec<T> evalq(const T* a, float c) { return eval<T>(a, c); } };
 // fresnel::bagher: schlick(F0) - F1*cos   (bagher.h:47-50); attribute = [F0 rgb, F1 rgb]
 struct FresnelBagher       { static constexpr int NA = 6; template<class T> BBMCU_D static Spec<T> eval(const T* a, float c) {
-    return Spec<T>(fresnel_schlick(a[0], c) - a[3]*c, fresnel_schlick(a[1], c) - a[4]*c, fresnel_schlick(a[2], c) - a[5]*c); } };
+    return Spec<T>(fresnel_schlick(a[0], c) - a[3]*c, fresnel_schlick(a[1], c) - a[4]*c, fresnel_schlick(a[2], c) - a[5]*c); }
+                             template<class T> BBMCU_D static Spec<T> evalq(const T* a, float c) { return eval<T>(a, c); } };
 
 // scalar-or-spectrum helpers
 template<class T> BBMCU_D Spec<T> to_spec(const T& a) { return Spec<T>(a); }
@@ -82,8 +88,7 @@ template<class T> BBMCU_D Spec<T> to_spec(const Spec<T>& a) { return a; }
 BBMCU_D float smith_rational(float a)
 {
   if(!(a < 1.6f)) return 1.0f;
-  double x = a;
-  return (float)((3.535*x + 2.181*x*x) / (1.0 + 2.276*x + 2.577*x*x));
+  return q_div(3.535f*a + 2.181f*a*a, 1.0f + 2.276f*a + 2.577f*a*a);       // positive terms only: no cancellation
 }
 template<int N> BBMCU_D Dual<N> smith_rational(const Dual<N>& a)
 {
@@ -117,7 +122,13 @@ struct NdfBeckmann
     T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     float c2 = h.z*h.z;
     T sx = h.x/ax, sy = h.y/ay;
-    T d = m_exp(-(sx*sx + sy*sy) / c2) / (ax*ay*c2*c2);
+    T d;
+    if constexpr (std::is_same<T, float>::value)
+      // the exponent keeps the reference's IEEE operations (exp amplifies its relative error by |exponent|, 10^2..10^4
+      // for fitted roughness 0.003-0.02); the quotient outside is a final value
+      d = q_div(m_exp(-(sx*sx + sy*sy) / c2), ax*ay*c2*c2);
+    else
+      d = m_exp(-(sx*sx + sy*sy) / c2) / (ax*ay*c2*c2);
     if(NORMALIZE) d = d * kInvPi;
     return d;
   }
@@ -126,6 +137,7 @@ struct NdfBeckmann
     if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
     T aa;
     if(ANISO) { T sx = v.x*a[0], sy = v.y*a[1]; aa = m_rsqrt((sx*sx + sy*sy) / (v.z*v.z)); }
+    else if constexpr (std::is_same<T, float>::value) aa = q_rcp(a[0] * q_tanTheta(v));
     else aa = m_rcp(a[0] * tanTheta(v));
     return smith_rational(aa);
   }
@@ -133,7 +145,7 @@ struct NdfBeckmann
   {
     if(!(m.z > 0.0f)) return 0.0f;
     float p = D<float>(m, a);
-    if(SAMPLE_VISIBLE) p *= G1<float>(view, m, a) * fabsf(dot(view, m)) / view.z;
+    if(SAMPLE_VISIBLE) p *= q_div(G1<float>(view, m, a) * fabsf(dot(view, m)), view.z);
     else p *= m.z;
     return (p > 0.0f) ? p : 0.0f;
   }
@@ -187,6 +199,7 @@ template<bool ANISO>
 struct NdfGGX
 {
   static constexpr int NA = ANISO ? 2 : 1;
+  static constexpr bool kQuickHalfway = true;      // D is algebraic in h: a 2-ulp half vector moves it by < 1e-6
   template<class T> BBMCU_D static T D(f3 h, const T* a)
   {
     if(!(h.z > 0.0f)) return T(0.0f);
@@ -239,16 +252,18 @@ struct NdfGGX
   {
     if(!xi_valid(xi)) return make_f3(0, 0, 0);
     float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
-    f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
+    // (*_nr: IEEE results through the library's own fast path, see bbmcu_math.cuh; operands here are in range
+    // unless the caller passes degenerate directions, which take the general operators)
+    f3 vs = normalize_nr(make_f3(view.x*ax, view.y*ay, view.z));
     f3 T1 = make_f3(1, 0, 0);
-    if(vs.z < 0.99999988079071044921875f) { float rr = 1.0f / sqrtf(vs.y*vs.y + vs.x*vs.x); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
+    if(vs.z < 0.99999988079071044921875f) { float rr = ieee_rcp_nr(ieee_sqrt_nr(vs.y*vs.y + vs.x*vs.x)); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
     f3 T2 = make_f3(T1.y*vs.z, -(T1.x*vs.z), T1.x*vs.y - T1.y*vs.x);
     float hi = 1.0f + vs.z, lo = vs.z - (hi - 1.0f);
-    float r0 = 1.0f / hi;
+    float r0 = ieee_rcp_nr(hi);
     float aa = fmaf(r0, fmaf(-lo, r0, fmaf(-hi, r0, 1.0f)), r0);
-    float r = sqrtf(xi.x);
+    float r = ieee_sqrt_nr(xi.x);
     bool lower = xi.y < aa;
-    float phi = lower ? (xi.y / aa) * kPi : (float)((1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
+    float phi = lower ? ieee_div_nr(xi.y, aa) * kPi : (float)((1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
     float cp, sp; glibc_sincosf_both(phi, sp, cp);
     float P1 = r*cp;
     float P2 = lower ? r*sp : (float)((double)vs.z * (double)r * (double)sp);
@@ -459,10 +474,11 @@ struct GVGroove {
   {
     using R = decltype(NDF::template G1<T>(in, m, a));
     if(!g_mask(in, out, m)) return R(T(0.0f));
-    // min(1.0, min(2.0*m.z*in.z/(in.m), 2.0*m.z*out.z/(out.m))) in double, rounded (vgroove.h:41-46)
-    double gi = 2.0*(double)m.z*(double)in.z/(double)dot(in, m);
-    double go = 2.0*(double)m.z*(double)out.z/(double)dot(out, m);
-    return R(T((float)fmin(1.0, fmin(gi, go))));
+    // min(1.0, min(2.0*m.z*in.z/(in.m), 2.0*m.z*out.z/(out.m))): double in the reference (vgroove.h:41-46), a final
+    // value here (products and one quotient)
+    float gi = q_div(2.0f*m.z*in.z, dot(in, m));
+    float go = q_div(2.0f*m.z*out.z, dot(out, m));
+    return R(T(fminf(1.0f, fminf(gi, go))));
   }
 };
 struct GUncorrelated {
@@ -501,6 +517,11 @@ struct GVanGinneken {
 // Attribute block: [scale rgb (if SCALED)] [NDF attributes] [Fresnel attributes]
 // NORM: 0 Unnormalized (1.0), 1 Walter (4.0), 2 Cook (pi as double)   (microfacet.h:31-36)
 // =============================================================================================
+// half vector for eval / pdf: IEEE normalisation unless the NDF declares itself insensitive (kQuickHalfway)
+template<class NDF, class = void> struct QuickHalfway { static constexpr bool value = false; };
+template<class NDF> struct QuickHalfway<NDF, typename std::enable_if<NDF::kQuickHalfway>::type> { static constexpr bool value = true; };
+template<class NDF> BBMCU_D f3 quick_halfway(f3 a, f3 b) { if constexpr (QuickHalfway<NDF>::value) return q_normalize(a + b); else return halfway(a, b); }
+
 template<class NDF, class G, class F, int NORM, bool SCALED>
 struct Microfacet
 {
@@ -514,11 +535,11 @@ struct Microfacet
   template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
   {
     if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<T>(T(0.0f));
-    f3 h = halfway(in, out);
+    f3 h = std::is_same<T, float>::value ? quick_halfway<NDF>(in, out) : halfway(in, out);
     float inh = dot(in, h), outh = dot(out, h);
     auto D = NDF::template D<T>(h, a + OFF_NDF);
     auto Gv = G::template eval<NDF, T>(in, out, h, a + OFF_NDF);
-    auto Fv = F::template eval<T>(a + OFF_F, 0.5f*(inh + outh));
+    auto Fv = F::template evalq<T>(a + OFF_F, 0.5f*(inh + outh));
     // D*G*F / NormalizationFactor / (z_in z_out): the division chain runs in double in the reference
     Spec<T> dgf = to_spec(D) * to_spec(Gv) * to_spec(Fv);
     return divide_out(dgf, in.z*out.z);
@@ -547,9 +568,24 @@ struct Microfacet
   BBMCU_D static float pdf(f3 in, f3 out, const float* a, int component)
   {
     if(!(component & FLAG_SPECULAR) || !((out.z > 0.0f) && (in.z > 0.0f))) return 0.0f;
-    f3 h = halfway(in, out);
+    f3 h = quick_halfway<NDF>(in, out);
     if(h.z < 0.0f) h = -h;
     return q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(dot(out, h)));
+  }
+  // eval and pdf of ONE direction pair sharing the half vector, D and G1 (the fused sample -> eval -> pdf pass).
+  // in.z > 0 and out.z > 0 imply h.z > 0, so pdf's flip of h (microfacet.h:163) never triggers here.
+  BBMCU_D static void eval_pdf(f3 in, f3 out, const float* a, int component, Spec<float>& e, float& p)
+  {
+    e = Spec<float>(0.0f); p = 0.0f;
+    if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return;
+    f3 h = quick_halfway<NDF>(in, out);
+    float inh = dot(in, h), outh = dot(out, h);
+    auto D = NDF::template D<float>(h, a + OFF_NDF);
+    auto Gv = G::template eval<NDF, float>(in, out, h, a + OFF_NDF);
+    auto Fv = F::template evalq<float>(a + OFF_F, 0.5f*(inh + outh));
+    e = divide_out(to_spec(D) * to_spec(Gv) * to_spec(Fv), in.z*out.z);
+    if(SCALED) e = e * load_spec(a);
+    p = q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(outh));
   }
   // sample.pdf is pdf(sample.direction, out) (microfacet.h:138): fused sample -> eval -> pdf passes evaluate it once
   static constexpr bool kSamplePdfIsPdf = true;

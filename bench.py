@@ -42,6 +42,15 @@ TRUTH = "Aggregate(Lambertian([0.2, 0.1, 0.05]), CookTorrance([0.3, 0.3, 0.3], 0
 METRIC = "BSDF sample+eval+pdf throughput, Walter GGX, 2^26 (direction, xi) pairs per step per GPU"
 
 
+def measured_traffic(n):
+    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu --set full capture,
+    scaled from the capture's launch size to this launch (profiles/ncu_traffic.json); None if absent"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    return float(json.load(open(p))["dram_bytes_per_pair"]) * n
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -308,7 +317,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "Walter GGX sample + eval + pdf on 2^%d (out, xi) pairs per GPU (BASELINE configs[1])" % args.log2_pairs,
                            "bsdf": BSDF, "pairs_per_gpu": n, "bytes_per_pair": BYTES_PER_PAIR, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (BYTES_PER_PAIR * n / 1e9)},
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(n), "peak_source": peak_src,
                              "kernel": "k_foreach4<SampleEvalPdfOp<BsdfSingle<GGX>>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info}
         print(json.dumps(line))

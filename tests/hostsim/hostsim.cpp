@@ -71,8 +71,9 @@ size_t hostsim_libm_mismatches(int which, const float* a, const float* b, size_t
   size_t bad = 0;
   for(size_t i=0; i < n; ++i)
   {
-    float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : glibc_cosf(a[i]);
-    float ref = which == 0 ? atan2f(a[i], b[i]) : which == 1 ? sinf(a[i]) : cosf(a[i]);
+    float both_s, both_c; glibc_sincosf_both(a[i], both_s, both_c);     // which 3 / 4: the shared-reduction variant
+    float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : which == 2 ? glibc_cosf(a[i]) : which == 3 ? both_s : both_c;
+    float ref = which == 0 ? atan2f(a[i], b[i]) : (which == 1 || which == 3) ? sinf(a[i]) : cosf(a[i]);
     uint32_t u, v; std::memcpy(&u, &mine, 4); std::memcpy(&v, &ref, 4);
     bad += (u != v);
   }

@@ -180,13 +180,14 @@ def test_loss_batched_and_sharded(ctx):
     lk, gk = L(fitted, params, grad=True)
     for k in range(7):
         l1, g1 = L(fitted, params[k], grad=True)
-        # (the block count per parameter set depends on K, so the fixed summation order differs: equal to 1e-12)
-        assert abs(l1[0] - lk[k]) <= 1e-12*abs(lk[k]) and np.allclose(g1[0], gk[k], rtol=1e-10, atol=1e-14)
+        # the tile kernel reduces every (parameter set, sample tile) in the same order whatever K is: bit-identical
+        assert l1[0] == lk[k] and np.array_equal(g1[0], gk[k])
     A = ctx.loss("standardLog", truth, None, first=0, count=700001)
     B = ctx.loss("standardLog", truth, None, first=700001, count=1458000 - 700001)
     la, ga = A(fitted, params, grad=True)
     lb, gb = B(fitted, params, grad=True)
-    assert np.allclose(la + lb, lk, rtol=1e-12) and np.allclose(ga + gb, gk, rtol=1e-10, atol=1e-15)
+    # a shard boundary moves the 1024-sample tiles, i.e. which samples share a float partial sum: equal to ~1e-6
+    assert np.allclose(la + lb, lk, rtol=2e-6) and np.allclose(ga + gb, gk, rtol=2e-5, atol=1e-7*np.abs(gk).max())
 
 
 def test_loss_against_measured_table(ctx, ref, tmp_path):

@@ -16,6 +16,10 @@ def test_glibc_trig_ports_match_host_libm(hostsim):
     a[::5] *= np.float32(1e-2)
     assert hostsim.libm_mismatches(1, a) == 0
     assert hostsim.libm_mismatches(2, a) == 0
+    assert hostsim.libm_mismatches(3, a) == 0          # glibc_sincosf_both (shared reduction, signs applied last)
+    assert hostsim.libm_mismatches(4, a) == 0
+    z = np.float32(2 * np.pi) * rng.random(n, dtype=np.float32)       # the sampler's phi range
+    assert hostsim.libm_mismatches(3, z) == 0 and hostsim.libm_mismatches(4, z) == 0
 
 
 def test_merl_index_bit_exact(hostsim, golden_lin):
