@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
     out[s] = make_f3(__ldg(a.out + ii), __ldg(a.out + a.n + ii), __ldg(a.out + 2*a.n + ii));
     ref[s] = Spec<float>(__ldg(a.ref + ii), __ldg(a.ref + a.n + ii), __ldg(a.ref + 2*a.n + ii));
   }
+  typename LossT::Geom geo[kTileSPT];                          // direction-only work, once per sample
+#pragma unroll
+  for(int s=0; s < kTileSPT; ++s) geo[s] = LossT::geom(a.metric, in[s], out[s]);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for(int kc = k0; kc < k1; kc += kTileKChunk)
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
       {
         if(!valid[s]) continue;
         float g[P];
-        const float e = LossT::sample(at, a.metric, a.component, in[s], out[s], ref[s], g, WG);
+        const float e = LossT::sample(at, a.metric, a.component, geo[s], in[s], out[s], ref[s], g, WG);
         acc[0] += e;
         if(WG) {
 #pragma unroll

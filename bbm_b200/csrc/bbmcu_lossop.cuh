@@ -31,11 +31,9 @@ BBMCU_D float metric_weight(int metric, f3 in, f3 out)
   }
 }
 
-// e and (optionally) de/dv per channel
-BBMCU_D float loss_term(int metric, f3 in, f3 out, const Spec<float>& v, const Spec<float>& r, Spec<float>* dv)
+// e and (optionally) de/dv per channel, given c = max(cos_i, 0) and the metric weight w of the direction pair
+BBMCU_D float loss_term_g(int metric, float c, float w, const Spec<float>& v, const Spec<float>& r, Spec<float>* dv)
 {
-  float c = fmaxf(in.z, 0.0f);
-  float w = metric_weight(metric, in, out);
   if(metric <= METRIC_BIERON_L2)
   {
     float tr = (v.r - r.r)*c, tg = (v.g - r.g)*c, tb = (v.b - r.b)*c;
@@ -49,6 +47,9 @@ BBMCU_D float loss_term(int metric, f3 in, f3 out, const Spec<float>& v, const S
   if(dv) { float k = 2.0f * w * c; *dv = Spec<float>(k*q_div(dr, ar), k*q_div(dg, ag), k*q_div(db, ab)); }
   return s * w;
 }
+
+BBMCU_D float loss_term(int metric, f3 in, f3 out, const Spec<float>& v, const Spec<float>& r, Spec<float>* dv)
+{ return loss_term_g(metric, fmaxf(in.z, 0.0f), metric_weight(metric, in, out), v, r, dv); }
 
 // ---- fit-parameter layout of a model: which attribute floats are fit parameters ----------------------
 // Default: every attribute float, in order.  Bagher keeps 15 Dependent floats (K, Lambda, c, theta0, k)
@@ -68,20 +69,74 @@ template<> struct FitMap<BagherModel>
 // number of fit parameters of a model that are NOT its leading RGB scale
 template<class M> struct NonLinear { static constexpr int N = FitMap<M>::NFIT - (M::SCALE >= 0 ? 3 : 0); };
 
-// One lobe: value v (added into `v`) and, through `emit(k, dv_r, dv_g, dv_b)`, dv/dtheta_k for each of the
-// lobe's fit parameters k = 0 .. NFIT-1 (forward enumeration order).
-template<class M, class Emit>
-BBMCU_D Spec<float> lobe_value_and_jacobian(const float* a, f3 in, f3 out, int component, Emit&& emit)
+// ---- direction-only precomputation ("geometry") -------------------------------------------------------------------
+// A model may declare `struct Geom`, `geom(in, out)` and `eval_unscaled_g<T>(geom, in, out, a, component)`: everything
+// that depends on the direction pair alone (half vector, dots).  The batched loss kernels compute it once per sample,
+// outside their loop over parameter sets.
+template<class...> struct VoidT { using type = void; };
+template<class M, class = void> struct GeomOf
+{
+  struct type {};
+  BBMCU_D static type make(f3, f3) { return type(); }
+  template<class T> BBMCU_D static Spec<T> eval_unscaled(const type&, f3 in, f3 out, const T* a, int component) { return M::template eval_unscaled<T>(in, out, a, component); }
+  BBMCU_D static Spec<float> eval(const type&, f3 in, f3 out, const float* a, int component) { return M::template eval<float>(in, out, a, component); }
+};
+template<class M> struct GeomOf<M, typename VoidT<typename M::Geom>::type>
+{
+  using type = typename M::Geom;
+  BBMCU_D static type make(f3 in, f3 out) { return M::geom(in, out); }
+  template<class T> BBMCU_D static Spec<T> eval_unscaled(const type& g, f3 in, f3 out, const T* a, int component) { return M::template eval_unscaled_g<T>(g, in, out, a, component); }
+  BBMCU_D static Spec<float> eval(const type& g, f3 in, f3 out, const float* a, int component)
+  { Spec<float> r = M::template eval_unscaled_g<float>(g, in, out, a, component); if(M::SCALE >= 0) r = r * load_spec(a + (M::SCALE >= 0 ? M::SCALE : 0)); return r; }
+};
+// models whose unscaled value has three identical channels (scalar D, G and F): the jacobian is one column
+template<class M, class = void> struct GrayUnscaled { static constexpr bool value = false; };
+template<class M> struct GrayUnscaled<M, typename std::enable_if<M::kGrayUnscaled>::type> { static constexpr bool value = true; };
+
+// value and parameter jacobian of one lobe.  Scale parameters (a leading RGB attribute) touch one channel each and are
+// kept as the three unscaled values `us`; the NL non-linear parameters carry a full RGB column.
+template<class M> struct LobeJac
+{
+  static constexpr int NL = NonLinear<M>::N;
+  static constexpr bool SCALED = (M::SCALE >= 0);
+  Spec<float> v;
+  float us[3];
+  float jr[NL > 0 ? NL : 1], jg[NL > 0 ? NL : 1], jb[NL > 0 ? NL : 1];
+  // d e / d theta_k for this lobe's NFIT parameters, given d e / d v
+  BBMCU_D void combine(const Spec<float>& dv, const float* a, float* grad) const
+  {
+    constexpr int S = SCALED ? 3 : 0;
+    if(SCALED) { grad[0] = dv.r*us[0]; grad[1] = dv.g*us[1]; grad[2] = dv.b*us[2]; }
+    if constexpr (NL > 0)
+    {
+      if constexpr (SCALED && GrayUnscaled<M>::value)
+      {
+        const float sdv = (dv.r*a[0] + dv.g*a[1]) + dv.b*a[2];
+#pragma unroll
+        for(int j=0; j < NL; ++j) grad[S + j] = sdv*jr[j];               // jr holds d u / d theta (unscaled) here
+      }
+      else
+      {
+#pragma unroll
+        for(int j=0; j < NL; ++j) grad[S + j] = (dv.r*jr[j] + dv.g*jg[j]) + dv.b*jb[j];
+      }
+    }
+  }
+};
+
+template<class M>
+BBMCU_D LobeJac<M> lobe_jacobian(const typename GeomOf<M>::type& geom, const float* a, f3 in, f3 out, int component)
 {
   constexpr int NL = NonLinear<M>::N;
   constexpr int NFIT = FitMap<M>::NFIT;
   constexpr bool SCALED = (M::SCALE >= 0);
   static_assert(!SCALED || M::SCALE == 0, "leading scale expected at offset 0");
+  LobeJac<M> J;
   if constexpr (NL == 0)
   {
-    Spec<float> u = M::template eval_unscaled<float>(in, out, a, component);
-    emit(0, u.r, 0.0f, 0.0f); emit(1, 0.0f, u.g, 0.0f); emit(2, 0.0f, 0.0f, u.b);
-    return Spec<float>(a[0]*u.r, a[1]*u.g, a[2]*u.b);
+    Spec<float> u = GeomOf<M>::template eval_unscaled<float>(geom, in, out, a, component);
+    J.us[0] = u.r; J.us[1] = u.g; J.us[2] = u.b;
+    J.v = Spec<float>(a[0]*u.r, a[1]*u.g, a[2]*u.b);
   }
   else
   {
@@ -91,13 +146,22 @@ BBMCU_D Spec<float> lobe_value_and_jacobian(const float* a, f3 in, f3 out, int c
     for(int i=0; i < M::NA; ++i) ad[i] = D(a[i]);
 #pragma unroll
     for(int k = (SCALED ? 3 : 0); k < NFIT; ++k) ad[FitMap<M>::attr_of(k)].d[k - (SCALED ? 3 : 0)] = 1.0f;
-    Spec<D> u = M::template eval_unscaled<D>(in, out, ad, component);
-    float sr = SCALED ? a[0] : 1.0f, sg = SCALED ? a[1] : 1.0f, sb = SCALED ? a[2] : 1.0f;
-    if constexpr (SCALED) { emit(0, u.r.v, 0.0f, 0.0f); emit(1, 0.0f, u.g.v, 0.0f); emit(2, 0.0f, 0.0f, u.b.v); }
+    Spec<D> u = GeomOf<M>::template eval_unscaled<D>(geom, in, out, ad, component);
+    const float sr = SCALED ? a[0] : 1.0f, sg = SCALED ? a[1] : 1.0f, sb = SCALED ? a[2] : 1.0f;
+    J.us[0] = u.r.v; J.us[1] = u.g.v; J.us[2] = u.b.v;
+    if constexpr (SCALED && GrayUnscaled<M>::value)
+    {
 #pragma unroll
-    for(int j=0; j < NL; ++j) emit((SCALED ? 3 : 0) + j, sr*u.r.d[j], sg*u.g.d[j], sb*u.b.d[j]);
-    return Spec<float>(sr*u.r.v, sg*u.g.v, sb*u.b.v);
+      for(int j=0; j < NL; ++j) J.jr[j] = u.r.d[j];
+    }
+    else
+    {
+#pragma unroll
+      for(int j=0; j < NL; ++j) { J.jr[j] = sr*u.r.d[j]; J.jg[j] = sg*u.g.d[j]; J.jb[j] = sb*u.b.d[j]; }
+    }
+    J.v = Spec<float>(sr*u.r.v, sg*u.g.v, sb*u.b.v);
   }
+  return J;
 }
 
 template<class M> struct NFitOf { static constexpr int N = FitMap<M>::NFIT; };
@@ -117,7 +181,8 @@ BBMCU_D float loss_sample_generic(const BsdfDesc& b, int metric, int component, 
       const float* a = b.attrs + b.offset[l];
       dispatch_model(b.model[l], [&](auto* tag) {
         using M = typename std::remove_pointer<decltype(tag)>::type;
-        lobe_value_and_jacobian<M>(a, in, out, component, [&](int k, float jr, float jg, float jb) { grad[base + k] = dv.r*jr + dv.g*jg + dv.b*jb; });
+        LobeJac<M> J = lobe_jacobian<M>(GeomOf<M>::make(in, out), a, in, out, component);
+        J.combine(dv, a, grad + base);
         base += NFitOf<M>::N;
       });
     }
@@ -125,20 +190,24 @@ BBMCU_D float loss_sample_generic(const BsdfDesc& b, int metric, int component, 
   return e;
 }
 
+// per-sample quantities of the metric that do not depend on the fitted model
+struct TermGeom { float c, w; };
+BBMCU_D TermGeom term_geom(int metric, f3 in, f3 out) { TermGeom t; t.c = fmaxf(in.z, 0.0f); t.w = metric_weight(metric, in, out); return t; }
+
 // ---- compile-time one- and two-lobe BSDFs: single pass, everything in registers --------------------------
 template<class M>
 struct LossSingle
 {
   static constexpr int P = NFitOf<M>::N;
-  BBMCU_D static float sample(const float* attrs, int metric, int component, f3 in, f3 out, const Spec<float>& ref, float (&grad)[P], bool want_grad)
+  struct Geom { typename GeomOf<M>::type g; TermGeom t; };
+  BBMCU_D static Geom geom(int metric, f3 in, f3 out) { Geom G; G.g = GeomOf<M>::make(in, out); G.t = term_geom(metric, in, out); return G; }
+  BBMCU_D static float sample(const float* attrs, int metric, int component, const Geom& G, f3 in, f3 out, const Spec<float>& ref, float (&grad)[P], bool want_grad)
   {
-    if(!want_grad) { Spec<float> v = M::template eval<float>(in, out, attrs, component); return loss_term(metric, in, out, v, ref, nullptr); }
-    float jr[P], jg[P], jb[P];
-    Spec<float> v = lobe_value_and_jacobian<M>(attrs, in, out, component, [&](int k, float r, float g, float b) { jr[k] = r; jg[k] = g; jb[k] = b; });
+    if(!want_grad) { Spec<float> v = GeomOf<M>::eval(G.g, in, out, attrs, component); return loss_term_g(metric, G.t.c, G.t.w, v, ref, nullptr); }
+    LobeJac<M> J = lobe_jacobian<M>(G.g, attrs, in, out, component);
     Spec<float> dv;
-    float e = loss_term(metric, in, out, v, ref, &dv);
-#pragma unroll
-    for(int k=0; k < P; ++k) grad[k] = dv.r*jr[k] + dv.g*jg[k] + dv.b*jb[k];
+    float e = loss_term_g(metric, G.t.c, G.t.w, J.v, ref, &dv);
+    J.combine(dv, attrs, grad);
     return e;
   }
 };
@@ -148,21 +217,22 @@ template<class M0, class M1>
 struct LossPair
 {
   static constexpr int P0 = NFitOf<M0>::N, P = P0 + NFitOf<M1>::N;
-  BBMCU_D static float sample(const float* attrs, int metric, int component, f3 in, f3 out, const Spec<float>& ref, float (&grad)[P], bool want_grad)
+  struct Geom { typename GeomOf<M0>::type g0; typename GeomOf<M1>::type g1; TermGeom t; };
+  BBMCU_D static Geom geom(int metric, f3 in, f3 out) { Geom G; G.g0 = GeomOf<M0>::make(in, out); G.g1 = GeomOf<M1>::make(in, out); G.t = term_geom(metric, in, out); return G; }
+  BBMCU_D static float sample(const float* attrs, int metric, int component, const Geom& G, f3 in, f3 out, const Spec<float>& ref, float (&grad)[P], bool want_grad)
   {
     const float* a0 = attrs; const float* a1 = attrs + M0::NA;
     if(!want_grad)
     {
-      Spec<float> v = (Spec<float>(0.0f) + M0::template eval<float>(in, out, a0, component)) + M1::template eval<float>(in, out, a1, component);
-      return loss_term(metric, in, out, v, ref, nullptr);
+      Spec<float> v = (Spec<float>(0.0f) + GeomOf<M0>::eval(G.g0, in, out, a0, component)) + GeomOf<M1>::eval(G.g1, in, out, a1, component);
+      return loss_term_g(metric, G.t.c, G.t.w, v, ref, nullptr);
     }
-    float jr[P], jg[P], jb[P];
-    Spec<float> v0 = lobe_value_and_jacobian<M0>(a0, in, out, component, [&](int k, float r, float g, float b) { jr[k] = r; jg[k] = g; jb[k] = b; });
-    Spec<float> v1 = lobe_value_and_jacobian<M1>(a1, in, out, component, [&](int k, float r, float g, float b) { jr[P0 + k] = r; jg[P0 + k] = g; jb[P0 + k] = b; });
+    LobeJac<M0> J0 = lobe_jacobian<M0>(G.g0, a0, in, out, component);
+    LobeJac<M1> J1 = lobe_jacobian<M1>(G.g1, a1, in, out, component);
     Spec<float> dv;
-    float e = loss_term(metric, in, out, v0 + v1, ref, &dv);
-#pragma unroll
-    for(int k=0; k < P; ++k) grad[k] = dv.r*jr[k] + dv.g*jg[k] + dv.b*jb[k];
+    float e = loss_term_g(metric, G.t.c, G.t.w, J0.v + J1.v, ref, &dv);
+    J0.combine(dv, a0, grad);
+    J1.combine(dv, a1, grad + P0);
     return e;
   }
 };

@@ -531,6 +531,26 @@ struct Microfacet
   static constexpr int NA = OFF_F + F::NA;
   BBMCU_HD static constexpr double norm() { return NORM == 0 ? 1.0 : (NORM == 1 ? 4.0 : kPiD); }
 
+  // direction-only part of eval, hoisted out of the parameter loop of the batched loss kernels
+  struct Geom { f3 h; float inh, outh; };
+  BBMCU_D static Geom geom(f3 in, f3 out)
+  {
+    Geom g; g.h = make_f3(0, 0, 1); g.inh = 0.0f; g.outh = 0.0f;
+    if((in.z > 0.0f) && (out.z > 0.0f)) { g.h = halfway(in, out); g.inh = dot(in, g.h); g.outh = dot(out, g.h); }
+    return g;
+  }
+  // three identical channels before the scale whenever D, G and F are scalars
+  static constexpr bool kGrayUnscaled = std::is_same<decltype(NDF::template D<float>(f3(), (const float*)nullptr)), float>::value
+                                     && std::is_same<decltype(F::template eval<float>((const float*)nullptr, 0.0f)), float>::value;
+  template<class T> BBMCU_D static Spec<T> eval_unscaled_g(const Geom& g, f3 in, f3 out, const T* a, int component)
+  {
+    if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<T>(T(0.0f));
+    auto D = NDF::template D<T>(g.h, a + OFF_NDF);
+    auto Gv = G::template eval<NDF, T>(in, out, g.h, a + OFF_NDF);
+    auto Fv = F::template evalq<T>(a + OFF_F, 0.5f*(g.inh + g.outh));
+    Spec<T> dgf = to_spec(D) * to_spec(Gv) * to_spec(Fv);
+    return divide_out(dgf, in.z*out.z);
+  }
   // eval without the leading scale (microfacet.h:74-102)
   template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
   {

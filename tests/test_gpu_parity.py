@@ -232,3 +232,27 @@ def test_full_size_properties(ctx):
     assert float(rel.max()) < 1e-4
     nrm = (d*d).sum(0)[f == 2]
     assert float((nrm - 1).abs().max()) < 1e-5
+
+
+def test_fit_sweep_small(ctx):
+    """BASELINE configs[4] in miniature: synthetic MERL-shaped materials x models x metrics, batched compass per fit;
+    two ranks' shares are disjoint and cover every job (no collective)."""
+    import bbm_b200 as bb
+    from bbm_b200.fit import run_sweep, sweep_jobs, fit
+    i, o = ctx.merl_dirs(0, bb.MERL_BINS)
+    mats = {"matA": "Aggregate(Lambertian([0.2,0.1,0.05]), GGX([0.3,0.3,0.3], 0.2, 1.5))",
+            "matB": "Aggregate(Lambertian([0.05,0.1,0.2]), Phong([0.2,0.2,0.2], 40))"}
+    tables = {k: ctx.eval(bb.Bsdf(v), i, o) for k, v in mats.items()}
+    models, metrics = ["GGX", "Phong"], ["nganL2", "standardLog"]
+    r0 = run_sweep(ctx, tables, models, metrics, rank=0, world=2, max_steps=8)
+    r1 = run_sweep(ctx, tables, models, metrics, rank=1, world=2, max_steps=8)
+    jobs, _ = sweep_jobs(sorted(tables), models, metrics)
+    assert set(r0) | set(r1) == set(jobs) and not (set(r0) & set(r1))
+    for key, (s, loss, steps) in {**r0, **r1}.items():
+        assert np.isfinite(loss) and steps == 8
+        bb.Bsdf(s)                                            # the result is a valid BSDF string
+    # the matching model gets (much) closer than the wrong one
+    assert r0.get(("matA", "GGX", "nganL2"), r1.get(("matA", "GGX", "nganL2")))[1] < {**r0, **r1}[("matA", "Phong", "nganL2")][1]
+    # a longer fit of the right model recovers the material
+    b, trace = fit(ctx, "Aggregate(Lambertian(), GGX())", tables["matA"], "nganL2", max_steps=60)
+    assert trace[-1] < 1e-2 * trace[0]
