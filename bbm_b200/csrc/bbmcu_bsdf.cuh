@@ -51,6 +51,7 @@ struct BsdfGeneric
 {
   static constexpr bool kTables = true;
   static constexpr bool kFusedSample = false;
+  static constexpr bool kHandFused = false;
   BBMCU_D static void sample_dir(const BsdfDesc&, f3, f2, int, f3&, int&) {}
   BBMCU_D static void eval_pdf(const BsdfDesc&, f3, f3, int, Spec<float>&, float&) {}
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component)
@@ -127,6 +128,8 @@ BBMCU_D void bsdf_tables_phase2(BsdfDesc& b, int tid)
 }
 
 // models whose sample() returns pdf(direction, out) as the sample's pdf, and expose the direction-only half
+template<class M, class = void> struct HandFused { static constexpr bool value = false; };
+template<class M> struct HandFused<M, typename std::enable_if<M::kHandFusedEvalPdf>::type> { static constexpr bool value = true; };
 template<class M, class = void> struct SamplePdfIsPdf { static constexpr bool value = false; };
 template<class M> struct SamplePdfIsPdf<M, typename std::enable_if<M::kSamplePdfIsPdf>::type> { static constexpr bool value = true; };
 
@@ -136,6 +139,7 @@ struct BsdfSingle
 {
   static constexpr bool kTables = TableFloats<M>::N > 0;
   static constexpr bool kFusedSample = SamplePdfIsPdf<M>::value;
+  static constexpr bool kHandFused = HandFused<M>::value;
   BBMCU_D static void sample_dir(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag)
   { if constexpr (kFusedSample) M::sample_dir(out, xi, b.attrs, component, dir, flag); }
   BBMCU_D static void eval_pdf(const BsdfDesc& b, f3 in, f3 out, int component, Spec<float>& e, float& p)

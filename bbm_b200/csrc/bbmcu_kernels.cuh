@@ -53,6 +53,7 @@ BBMCU_D void store4x3(float* p, size_t i, size_t n, bool aligned, const Lanes3& 
 // ---- operators --------------------------------------------------------------------------------------
 template<class B> struct EvalOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = false;     // eval never reads the sampling tables
   BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -66,6 +67,7 @@ template<class B> struct EvalOp
 
 template<class B> struct PdfOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -79,6 +81,7 @@ template<class B> struct PdfOp
 
 template<class B> struct ReflectanceOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = false;
   BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -92,6 +95,7 @@ template<class B> struct ReflectanceOp
 
 template<class B> struct SampleOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -106,6 +110,7 @@ template<class B> struct SampleOp
 // s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)   (20 B in, 36 B out per element)
 template<class B> struct SampleEvalPdfOp
 {
+  static constexpr int kBlock = B::kHandFused ? 512 : 256, kMinBlocks = B::kHandFused ? 2 : 1;     // launch shape (see Microfacet::kHandFusedEvalPdf)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -137,6 +142,7 @@ template<class B> struct SampleEvalPdfOp
 
 struct MerlIndexOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
   const float* in; const float* out; uint32_t* index; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
@@ -150,6 +156,7 @@ struct MerlIndexOp
 
 struct MerlDirsOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
   uint32_t first; float* in; float* out; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
@@ -163,6 +170,7 @@ struct MerlDirsOp
 
 struct SphericalDirsOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
   SphericalGrid grid; uint64_t first; float* in; float* out; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
@@ -177,6 +185,7 @@ struct SphericalDirsOp
 // gather the measured grid at the bin of each direction pair: merl_data::eval (staticmodel/merl.h:78-96)
 struct MerlLookupOp
 {
+  static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
   const float* table; const float* in; const float* out; float* rgb; uint32_t* bad; size_t n; bool aligned;
   BBMCU_D void group(size_t i) const
@@ -205,7 +214,7 @@ struct MerlLookupOp
 };
 
 #ifdef __CUDACC__
-template<class Op> __global__ void __launch_bounds__(256) k_foreach4(const Op op, size_t groups)
+template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks) k_foreach4(const Op op, size_t groups)
 {
   const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   if constexpr (!Op::kHasBsdf) { for(size_t g = first; g < groups; g += stride) op.group(g * kVec); }

@@ -15,7 +15,7 @@ template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stre
   if(n == 0) return;
   size_t groups = (n + kVec - 1) / kVec;
   bind_device_tables();
-  k_foreach4<Op><<<grid_for(ctx, groups), 256, 0, stream>>>(op, groups);
+  k_foreach4<Op><<<grid_for(ctx, groups, Op::kBlock, 8*256/Op::kBlock), Op::kBlock, 0, stream>>>(op, groups);
   BBMCU_CUDA(cudaGetLastError());
   ++ctx->launches;
 }

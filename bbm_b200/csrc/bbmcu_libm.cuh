@@ -131,16 +131,13 @@ BBMCU_D void glibc_sincosf_both(float y, float& sn, float& cs)
   const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5, c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
   const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
   double x = y;
-  uint32_t top = (f2u(y) >> 20) & 0x7ff;
-  int n = 0;
-  if(top < 0x3f4) { if(top < 0x398) { sn = y; cs = 1.0f; return; } }
-  else if(top < 0x42f)
-  {
-    double r = x * 0x1.45F306DC9C883p+23;
-    n = ((int32_t)r + 0x800000) >> 24;
-    x = x - (double)n * 0x1.921FB54442D18p0;
-  }
-  else { sn = sinf(y); cs = cosf(y); return; }
+  const float ay = fabsf(y);
+  if(!(ay < 120.0f)) { sn = sinf(y); cs = cosf(y); return; }          // (abstop12 < 0x42f in glibc; never taken by the samplers)
+  // glibc skips the reduction below pi/4; the reduction then yields n = 0 and x - 0 * (pi/2) = x exactly, so one path
+  // serves both.  Below 2^-12 it returns (y, 1) without the polynomials.
+  double r = x * 0x1.45F306DC9C883p+23;
+  const int n = ((int32_t)r + 0x800000) >> 24;
+  x = x - (double)n * 0x1.921FB54442D18p0;
   double x2 = x*x;
   double x3 = x*x2, ts = s2 + x2*s3, x7 = x3*x2, ss = x + x3*s1;
   float A = (float)(ss + x7*ts);                                  // sin polynomial of the reduced argument
@@ -151,6 +148,7 @@ BBMCU_D void glibc_sincosf_both(float y, float& sn, float& cs)
   if(flip_a) A = -A;
   if(flip_b) B = -B;
   if(n & 1) { sn = B; cs = A; } else { sn = A; cs = B; }
+  if(ay < 0x1p-12f) { sn = y; cs = 1.0f; }
 }
 BBMCU_D float glibc_sinf(float y) { return glibc_sincosf<false>(y); }
 BBMCU_D float glibc_cosf(float y) { return glibc_sincosf<true>(y); }

@@ -46,6 +46,52 @@ constexpr int kTileSPT = 4;
 constexpr int kTileKChunk = 8;
 constexpr int kTileSamples = kTileSPT * kLossThreads;
 
+// Warp reduction of C values per lane with a halving butterfly: at each offset a lane keeps one half of its values
+// and ships the other half to its partner, so C values cost CP/2 + CP/4 + ... + 1 (+ the remaining plain steps)
+// shuffles instead of 5 C.  Afterwards the lane with (lane & rest) == 0 holds the full sum of value `idx`.
+template<int CNT, int OFF> struct WarpButterfly
+{
+  static __device__ __forceinline__ void run(float* w, int lane, int& idx)
+  {
+    if constexpr (OFF >= 1)
+    {
+      if constexpr (CNT > 1)
+      {
+        constexpr int H = CNT / 2;
+        const bool bit = (lane & OFF) != 0;
+#pragma unroll
+        for(int i=0; i < H; ++i)
+        {
+          const float send = bit ? w[i] : w[i + H];
+          const float keep = bit ? w[i + H] : w[i];
+          w[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        if(bit) idx += H;
+        WarpButterfly<H, OFF/2>::run(w, lane, idx);
+      }
+      else
+      {
+        w[0] += __shfl_xor_sync(0xffffffffu, w[0], OFF);
+        WarpButterfly<1, OFF/2>::run(w, lane, idx);
+      }
+    }
+  }
+};
+// sums v[0..C) over the warp; lane_is_writer lanes get (idx, value) with idx < CP (idx >= C: padding, skip)
+template<int C> __device__ __forceinline__ void warp_reduce_multi(const float (&v)[C], int lane, int& idx, float& value, bool& writer)
+{
+  constexpr int CP = C <= 1 ? 1 : C <= 2 ? 2 : C <= 4 ? 4 : C <= 8 ? 8 : C <= 16 ? 16 : 32;
+  float w[CP];
+#pragma unroll
+  for(int i=0; i < CP; ++i) w[i] = (i < C) ? v[i < C ? i : 0] : 0.0f;
+  idx = 0;
+  WarpButterfly<CP, 16>::run(w, lane, idx);
+  value = w[0];
+  // offsets 16, 8, ... were used for halving while the count was > 1: log2(CP) of them; the rest were plain sums
+  constexpr int used = CP == 1 ? 0 : CP == 2 ? 16 : CP == 4 ? 24 : CP == 8 ? 28 : CP == 16 ? 30 : 31;
+  writer = (lane & ~used & 31) == 0;
+}
+
 template<class LossT, bool WG>
 __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, int K, int k_per_block)
 {
@@ -94,14 +140,9 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
           for(int j=0; j < P; ++j) acc[1 + j] += g[j];
         }
       }
-#pragma unroll
-      for(int j=0; j < C; ++j)
-      {
-        float v = acc[j];
-#pragma unroll
-        for(int o=16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if(lane == 0) s_red[kk][warp][j] = v;
-      }
+      int ridx; float rval; bool rwriter;
+      warp_reduce_multi<C>(acc, lane, ridx, rval, rwriter);
+      if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
     }
     __syncthreads();
     if((int)threadIdx.x < nkk*(1 + a.P))

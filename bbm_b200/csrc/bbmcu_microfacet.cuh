@@ -232,10 +232,11 @@ struct NdfGGX
   BBMCU_D static float pdf(f3 view, f3 m, const float* a)
   {
     if(!(m.z > 0.0f)) return 0.0f;
-    float p = D<float>(m, a);
-    p *= q_div(G1<float>(view, m, a) * fabsf(dot(view, m)), view.z);
-    return (p > 0.0f) ? p : 0.0f;
+    return pdf_visible(D<float>(m, a), G1<float>(view, m, a), fabsf(dot(view, m)), view.z);
   }
+  // the visible-normal pdf from an already evaluated D(m) and G1(view, m) (the fused eval + pdf path has both)
+  static constexpr bool kHasPdfVisible = true;
+  BBMCU_D static float pdf_visible(float Dm, float G1v, float abs_vm, float vz) { float p = Dm * q_div(G1v * abs_vm, vz); return (p > 0.0f) ? p : 0.0f; }
   // Heitz 2017 visible-normal sampling (ggx.h:86-107).  Every step up to the normal n reproduces the reference's
   // roundings (no FMA, IEEE sqrt / divide, its float-double mix): the two differences in it - (xi1 - a)/(1 - a) for
   // grazing views and 1 - P1^2 - P2^2 for xi0 -> 1 - cancel, so a last-bit change upstream would move the sampled
@@ -248,25 +249,50 @@ struct NdfGGX
   //     product is the same single rounding;
   //   * cos / sin(phi): the host libm's values (bbmcu_libm.cuh), one shared quadrant reduction.
   // Only the final normalisation of the stretched normal is a quick op (nothing cancels after it).
-  BBMCU_D static f3 sample(f3 view, f2 xi, const float* a)
+  BBMCU_D static f3 sample(f3 view, f2 xi, const float* a) { return xi_valid(xi) ? sample_unchecked(view, xi, a) : make_f3(0, 0, 0); }
+  static constexpr bool kHasSampleUnchecked = true;
+  // xi already validated by the caller
+  BBMCU_D static f3 sample_unchecked(f3 view, f2 xi, const float* a)
   {
-    if(!xi_valid(xi)) return make_f3(0, 0, 0);
     float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
-    // (*_nr: IEEE results through the library's own fast path, see bbmcu_math.cuh; operands here are in range
-    // unless the caller passes degenerate directions, which take the general operators)
+    // (*_nr / *_raw: IEEE results through the math library's own fast path, see bbmcu_math.cuh.  Ranges: the stretched
+    // view is range-tested once in normalize_nr; vs.x^2 + vs.y^2 is in (1.19e-7, 1] inside the branch; hi is in [1, 2],
+    // a in [0.5, 1]; xi0 in [0, 1] needs the lower test only)
     f3 vs = normalize_nr(make_f3(view.x*ax, view.y*ay, view.z));
     f3 T1 = make_f3(1, 0, 0);
-    if(vs.z < 0.99999988079071044921875f) { float rr = ieee_rcp_nr(ieee_sqrt_nr(vs.y*vs.y + vs.x*vs.x)); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
+    if(vs.z < 0.99999988079071044921875f) { float rr = ieee_rcp_raw(ieee_sqrt_raw(vs.y*vs.y + vs.x*vs.x)); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
     f3 T2 = make_f3(T1.y*vs.z, -(T1.x*vs.z), T1.x*vs.y - T1.y*vs.x);
     float hi = 1.0f + vs.z, lo = vs.z - (hi - 1.0f);
-    float r0 = ieee_rcp_nr(hi);
+    float r0 = ieee_rcp_raw(hi);
     float aa = fmaf(r0, fmaf(-lo, r0, fmaf(-hi, r0, 1.0f)), r0);
-    float r = ieee_sqrt_nr(xi.x);
+    float r = (xi.x > 1e-30f) ? ieee_sqrt_raw(xi.x) : sqrtf(xi.x);
     bool lower = xi.y < aa;
-    float phi = lower ? ieee_div_nr(xi.y, aa) * kPi : (float)((1.0 + (double)(xi.y - aa) / (1.0 - (double)aa)) * (double)kPi);
+    float phi;
+    if(lower) phi = ieee_div_raw(xi.y, aa) * kPi;
+    else
+    {
+      // (float)((1.0 + (double)(xi1 - a) / (1.0 - (double)a)) * pi) in float-float arithmetic: numerator and
+      // denominator are exact floats, the quotient, 1 + q and the product are carried as hi + lo pairs (~2^-46) and
+      // rounded once.  Differs from the double evaluation only where the double path itself rounds twice across a float
+      // tie (1.6e-5 of a grazing-biased test set, ~1e-7 of uniform inputs; one ulp of phi each).
+      float num = xi.y - aa, den = 1.0f - aa;
+      float qh = ieee_div_raw(num, den);
+      float ql = q_div(fmaf(-qh, den, num), den);
+      float sh = 1.0f + qh, sl = ((1.0f - sh) + qh) + ql;
+      float ph = sh * kPi;
+      phi = ph + fmaf(sl, kPi, fmaf(sh, kPi, -ph));
+    }
     float cp, sp; glibc_sincosf_both(phi, sp, cp);
     float P1 = r*cp;
-    float P2 = lower ? r*sp : (float)((double)vs.z * (double)r * (double)sp);
+    float P2;
+    if(lower) P2 = r*sp;
+    else
+    {
+      // (float)((double)vs.z * r * sp): the same product as hi + lo pairs, rounded once (2e-8 tie cases)
+      float hi2 = vs.z * r, lo2 = fmaf(vs.z, r, -hi2);
+      float t = hi2 * sp;
+      P2 = t + fmaf(lo2, sp, fmaf(hi2, sp, -t));
+    }
     float w = (float)safe_sqrt_d(1.0 - (double)(P1*P1) - (double)(P2*P2));
     f3 n = (T1*P1 + T2*P2) + vs*w;
     return q_normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
@@ -520,6 +546,10 @@ struct GVanGinneken {
 // half vector for eval / pdf: IEEE normalisation unless the NDF declares itself insensitive (kQuickHalfway)
 template<class NDF, class = void> struct QuickHalfway { static constexpr bool value = false; };
 template<class NDF> struct QuickHalfway<NDF, typename std::enable_if<NDF::kQuickHalfway>::type> { static constexpr bool value = true; };
+template<class NDF, class = void> struct HasPdfVisible { static constexpr bool value = false; };
+template<class NDF> struct HasPdfVisible<NDF, typename std::enable_if<NDF::kHasPdfVisible>::type> { static constexpr bool value = true; };
+template<class NDF, class = void> struct HasSampleUnchecked { static constexpr bool value = false; };
+template<class NDF> struct HasSampleUnchecked<NDF, typename std::enable_if<NDF::kHasSampleUnchecked>::type> { static constexpr bool value = true; };
 template<class NDF> BBMCU_D f3 quick_halfway(f3 a, f3 b) { if constexpr (QuickHalfway<NDF>::value) return q_normalize(a + b); else return halfway(a, b); }
 
 template<class NDF, class G, class F, int NORM, bool SCALED>
@@ -592,12 +622,57 @@ struct Microfacet
     if(h.z < 0.0f) h = -h;
     return q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(dot(out, h)));
   }
+  // Walter's GGX has a hand-merged eval + pdf below; its fused kernel is launched 512 x 2 (64 registers, measured best)
+  static constexpr bool kHandFusedEvalPdf = std::is_same<NDF, NdfGGX<false>>::value && std::is_same<G, GUncorrelated>::value && std::is_same<F, FresnelCookIor>::value && NORM == 1;
   // eval and pdf of ONE direction pair sharing the half vector, D and G1 (the fused sample -> eval -> pdf pass).
   // in.z > 0 and out.z > 0 imply h.z > 0, so pdf's flip of h (microfacet.h:163) never triggers here.
   BBMCU_D static void eval_pdf(f3 in, f3 out, const float* a, int component, Spec<float>& e, float& p)
   {
     e = Spec<float>(0.0f); p = 0.0f;
     if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return;
+    if constexpr (kHandFusedEvalPdf)
+    {
+      // Walter's GGX (isotropic, uncorrelated Smith G, Cook Fresnel, N = 4) - the BASELINE headline model - with the
+      // quotients of D, G1, F and the 1/(4 z_i z_o) chain merged algebraically: 9 MUFU operations for eval AND pdf.
+      //   D   = alpha^2 / (pi (hx^2 + hy^2 + alpha^2 hz^2)^2)
+      //   G1  = 2 z / (z + sqrt(z^2 + alpha^2 (1 - z^2)))
+      //   F   = 1/2 a^2 (1 + b^2),  a = A d2 R,  b = n2 B R,  A = g - c, B = g + c, n2 = c B - 1, d2 = c A + 1, R = 1/(B d2)
+      //   pdf = D G1(out) |o.h| / z_o / (4 |o.h|) = D G1(out) z_i / (4 z_i z_o)
+      // Same mathematics as the generic path below, different (and fewer) roundings: final values, ~3e-7 relative.
+      const float al = a[OFF_NDF], al2 = al*al, eta = a[OFF_F];
+      f3 h = q_normalize(in + out);
+      const float inh = q_dot(in, h), outh = q_dot(out, h);
+      const float den = fmaf(al2, h.z*h.z, fmaf(h.x, h.x, h.y*h.y));
+      const float Dv = (h.z > 0.0f) ? al2 * q_rcp(kPi * den * den) : 0.0f;
+      const float gi = (inh > 0.0f) ? 2.0f*in.z * q_rcp(in.z + q_sqrt(fmaf(al2, sinTheta2(in), in.z*in.z))) : 0.0f;
+      const float go = (outh > 0.0f) ? 2.0f*out.z * q_rcp(out.z + q_sqrt(fmaf(al2, sinTheta2(out), out.z*out.z))) : 0.0f;
+      const float c = 0.5f*(inh + outh);
+      const float g = m_safe_sqrt(eta*eta + c*c - 1.0f);
+      const float A = g - c, B = g + c, n2 = fmaf(c, B, -1.0f), d2 = fmaf(c, A, 1.0f);
+      const float R = q_rcp(B * d2);
+      const float fa = A*d2*R, fb = n2*B*R;
+      const float Fv = fmaxf(0.5f * (fa*fa) * fmaf(fb, fb, 1.0f), 0.0f);
+      const float R4 = q_rcp(4.0f * in.z * out.z);
+      const float u = Dv * (gi*go) * Fv * R4;
+      e = Spec<float>(u*a[0], u*a[1], u*a[2]);
+      const float pv = Dv * go * in.z * R4;
+      p = (pv > 0.0f) ? pv : 0.0f;
+      return;
+    }
+    if constexpr (std::is_same<G, GUncorrelated>::value && HasPdfVisible<NDF>::value && QuickHalfway<NDF>::value)
+    {
+      // scalar D and G1, uncorrelated G, visible-normal pdf (GGX): D, G1(out) and both dots are evaluated once
+      f3 h = q_normalize(in + out);
+      float inh = q_dot(in, h), outh = q_dot(out, h);
+      auto D = NDF::template D<float>(h, a + OFF_NDF);
+      auto gi = NDF::template G1<float>(in, h, a + OFF_NDF), go = NDF::template G1<float>(out, h, a + OFF_NDF);
+      auto Gv = ((inh > 0.0f) && (outh > 0.0f)) ? gi*go : decltype(gi)(0.0f);
+      auto Fv = F::template evalq<float>(a + OFF_F, 0.5f*(inh + outh));
+      e = divide_out(to_spec(D) * to_spec(Gv) * to_spec(Fv), in.z*out.z);
+      if(SCALED) e = e * load_spec(a);
+      p = q_div(NDF::pdf_visible(D, go, fabsf(outh), out.z), 4.0f * fabsf(outh));
+      return;
+    }
     f3 h = quick_halfway<NDF>(in, out);
     float inh = dot(in, h), outh = dot(out, h);
     auto D = NDF::template D<float>(h, a + OFF_NDF);
@@ -613,7 +688,9 @@ struct Microfacet
   {
     dir = make_f3(0, 0, 0); flag = FLAG_NONE;
     if(!(component & FLAG_SPECULAR) || !xi_valid(xi) || !(out.z > 0.0f)) return;
-    f3 m = NDF::sample(out, xi, a + OFF_NDF);
+    f3 m;
+    if constexpr (HasSampleUnchecked<NDF>::value) m = NDF::sample_unchecked(out, xi, a + OFF_NDF);
+    else m = NDF::sample(out, xi, a + OFF_NDF);
     dir = reflect(out, m);
     flag = FLAG_SPECULAR;
   }

@@ -265,14 +265,16 @@ def main():
         params = fitted.parameter_values()[None] * (1 + 0.1 * rng.random((LOSS_K, P)))
         params[:, 7] = 1.2 + rng.random(LOSS_K)
         res = torch.zeros((LOSS_K, 1 + P), device=dev, dtype=torch.float64)
-        ev = torch.cuda.Event()
+        ev, ev_back = torch.cuda.Event(), torch.cuda.Event()
 
         def loss_step():
-            L.eval_device(fitted, params, res)
+            L.eval_device(fitted, params, res)                       # on the library's stream
             if world > 1:
                 ev.record(stream)
-                torch.cuda.current_stream().wait_event(ev)
+                torch.cuda.current_stream().wait_event(ev)           # the all-reduce starts after this step's kernels ...
                 dist.all_reduce(res)
+                ev_back.record(torch.cuda.current_stream())
+                stream.wait_event(ev_back)                           # ... and the next step's kernels after the all-reduce
 
         for _ in range(3):
             loss_step()
@@ -291,10 +293,54 @@ def main():
         kern_ms = max_over_ranks(f0.elapsed_time(f1))
         step_ms = max(wall_ms, kern_ms) / nl if world > 1 else kern_ms / nl
         passes = LOSS_K / (step_ms * 1e-3)
-        loss_info = {"value": passes, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
+        by_k = {}
+        for kk in (1, 16):
+            pk = params[:kk]
+            rk = torch.zeros((kk, 1 + P), device=dev, dtype=torch.float64)
+            for _ in range(3):
+                L.eval_device(fitted, pk, rk)
+            ctx.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record(stream)
+            for _ in range(20):
+                L.eval_device(fitted, pk, rk)
+            h1.record(stream)
+            ctx.synchronize()
+            by_k[str(kk)] = kk / (max_over_ranks(h0.elapsed_time(h1)) / 20 * 1e-3)       # this rank's shard only, no collective
+        loss_info = {"value": passes, "passes_per_s_by_K_no_collective": by_k, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
                      "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": "nccl all_reduce of K x (1+P) doubles" if world > 1 else None,
                      "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / peak,
                      "gpu_launches": ctx.launches - l0, "loss0": float(res[0, 0].item())}
+
+    # ---- extra (BASELINE configs[0], GPU side): Cook-Torrance eval over the MERL-grid directions ---------------------
+    # materialised SoA directions, 24 B in + 12 B out = 36 B/eval; the 1 458 000 grid directions are tiled 32x so the
+    # working set (1.7 GB) is far beyond L2
+    eval_info = None
+    if not args.no_loss:
+        N = bb.MERL_BINS
+        gi, go = ctx.merl_dirs(0, N, like=out)
+        ctx.synchronize()
+        reps = 32
+        gi, go = gi.repeat(1, reps).contiguous(), go.repeat(1, reps).contiguous()
+        ne = N * reps
+        rgb = torch.empty((3, ne), device=dev)
+        ct = bb.Bsdf("CookTorrance()")
+        torch.cuda.synchronize()
+        for _ in range(3):
+            ctx.eval(ct, gi, go, rgb=rgb)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            ctx.eval(ct, gi, go, rgb=rgb)
+        g1.record(stream)
+        ctx.synchronize()
+        ms_e = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+        ev_s = world * ne / (ms_e * 1e-3) / 1e9
+        eval_info = {"value": ev_s, "unit": "G evals/s", "bsdf": "CookTorrance()", "evals_per_gpu": ne, "bytes_per_eval": 36,
+                     "achieved_gbs_per_gpu": 36 * ne / (ms_e * 1e-3) / 1e9, "frac_of_hbm_roofline": 36 * ne / (ms_e * 1e-3) / 1e9 / peak,
+                     "kernel": "k_foreach4<EvalOp<BsdfSingle<CookTorrance>>>"}
+        del gi, go, rgb
 
     # ---- CPU baseline: the unmodified reference on this box's host cores (rank 0, N = 1 only) -------------
     cpu = None
@@ -319,7 +365,7 @@ def main():
                            "bsdf": BSDF, "pairs_per_gpu": n, "bytes_per_pair": BYTES_PER_PAIR, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (BYTES_PER_PAIR * n / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(n), "peak_source": peak_src,
                              "kernel": "k_foreach4<SampleEvalPdfOp<BsdfSingle<GGX>>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info}
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info, "eval_merl_grid": eval_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,54 @@
+// Stand-alone timing of the headline kernel (k_foreach4<SampleEvalPdfOp<BsdfSingle<GGX>>>) for quick iteration on
+// launch shape and code changes without rebuilding libbbmcu.so:  nvcc ... -DBLOCK=256 -DMINB=3 ggx_bench.cu -o ggx_bench
+// Development tool only; bench.py measures the shipped library.
+#include <cstdio>
+#include <vector>
+#include "bbmcu_launch.cuh"
+namespace bbmcu { const float* epd_table_device(int) { return nullptr; } }
+using namespace bbmcu;
+#ifndef BLOCK
+#define BLOCK 256
+#endif
+#ifndef MINB
+#define MINB 1
+#endif
+using GGXM = ModelOf<M_GGX>::type;
+using Op = SampleEvalPdfOp<BsdfSingle<GGXM>>;
+__global__ void __launch_bounds__(BLOCK, MINB) k_var(const Op op, size_t groups)
+{
+  for(size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) op.group(g * kVec, op.bsdf);
+}
+__global__ void k_init(float* out, float* xi, size_t n)
+{
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    uint32_t s = (uint32_t)i * 747796405u + 2891336453u; auto rnd = [&]() { s ^= s >> 17; s *= 0xed5ad4bbu; s ^= s >> 11; s *= 0xac4c1b51u; s ^= s >> 15; return (s >> 8) * (1.0f / 16777216.0f); };
+    float z = rnd(), ph = rnd() * 6.2831853f, r = sqrtf(fmaxf(1 - z*z, 0.f));
+    out[i] = r*cosf(ph); out[n + i] = r*sinf(ph); out[2*n + i] = z; xi[i] = rnd(); xi[n + i] = rnd();
+  }
+}
+int main(int argc, char** argv)
+{
+  const size_t n = size_t(1) << (argc > 1 ? atoi(argv[1]) : 26);
+  const int blocks_per_sm = argc > 2 ? atoi(argv[2]) : 32;
+  float *out, *xi, *dir, *sp, *rgb, *pdf; int32_t* flag;
+  cudaMalloc(&out, 3*n*4); cudaMalloc(&xi, 2*n*4); cudaMalloc(&dir, 3*n*4); cudaMalloc(&sp, n*4); cudaMalloc(&rgb, 3*n*4); cudaMalloc(&pdf, n*4); cudaMalloc(&flag, n*4);
+  k_init<<<1184, 256>>>(out, xi, n);
+  Op op; memset(&op.bsdf, 0, sizeof(op.bsdf));
+  op.bsdf.n_lobes = 1; op.bsdf.model[0] = M_GGX; float a[5] = {0.5f, 0.5f, 0.5f, 0.1f, 1.3f}; memcpy(op.bsdf.attrs, a, sizeof(a)); op.bsdf.n_floats = 5;
+  op.component = 3; op.out = out; op.xi = xi; op.dir = dir; op.spdf = sp; op.flag = flag; op.rgb = rgb; op.pdf = pdf; op.n = n; op.aligned = true;
+  size_t groups = n / kVec;
+  unsigned grid = (unsigned)std::min<size_t>((groups + BLOCK - 1) / BLOCK, (size_t)148 * blocks_per_sm);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for(int i=0; i < 3; ++i) k_var<<<grid, BLOCK>>>(op, groups);
+  cudaEventRecord(e0);
+  const int reps = 10;
+  for(int i=0; i < reps; ++i) k_var<<<grid, BLOCK>>>(op, groups);
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k_var);
+  std::vector<float> h(8); cudaMemcpy(h.data(), pdf, 32, cudaMemcpyDeviceToHost);
+  printf("BLOCK=%d MINB=%d KVEC=%d grid=%u regs=%d  %.3f ms  %.2f G pairs/s  %.1f GB/s (%.1f%% of 6549)  pdf[1]=%g err=%s\n", BLOCK, MINB, kVec, grid, fa.numRegs, ms,
+         n / ms / 1e6, 56.0 * n / ms / 1e6, 56.0 * n / ms / 1e6 / 65.491, h[1], cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
