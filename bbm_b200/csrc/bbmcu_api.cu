@@ -47,6 +47,30 @@ const float* epd_table_device(int device)
   return table[device];
 }
 
+// device copies of MERL tables: created on first use per device, released with the MerlData (its `release` hook)
+static void merl_release(int device, void* ptr)
+{
+  int cur = 0;
+  if(cudaGetDevice(&cur) != cudaSuccess) return;          // driver already shut down
+  cudaSetDevice(device); cudaFree(ptr); cudaSetDevice(cur);
+}
+const float* merl_device_table(const bbmcu_host::MerlData& m, int device)
+{
+  static std::mutex mtx;
+  std::lock_guard<std::mutex> lock(mtx);
+  auto it = m.device.find(device);
+  if(it != m.device.end()) return static_cast<const float*>(it->second);
+  int cur = 0; BBMCU_CUDA(cudaGetDevice(&cur));
+  BBMCU_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  BBMCU_CUDA(cudaMalloc(&p, m.rgb.size()*sizeof(float)));
+  BBMCU_CUDA(cudaMemcpy(p, m.rgb.data(), m.rgb.size()*sizeof(float), cudaMemcpyHostToDevice));
+  BBMCU_CUDA(cudaSetDevice(cur));
+  m.device[device] = p;
+  m.release = merl_release;
+  return static_cast<const float*>(p);
+}
+
 namespace {
 
 struct ArrayArg { const void* ptr; int planes; bool input; };    // 4-byte elements, SoA planes of n
@@ -199,7 +223,7 @@ int bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out)
     if(!str || !out) throw std::invalid_argument("BBM: null argument");
     std::unique_ptr<bbmcu_bsdf> b(new bbmcu_bsdf);
     b->b = bbmcu_host::parse_bsdf(str);
-    make_desc(b->b);                                    // validates lobe/attribute limits early
+    make_desc(b->b, -1);                                // validates lobe/attribute limits early (no device touched)
     *out = b.release();
   });
 }
@@ -239,7 +263,9 @@ int bbmcu_eval(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, 
     if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
     check_flags(component, unit);
     if(n == 0) return;
-    BsdfDesc d = make_desc(bsdf->b);
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
     run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {rgb, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_eval(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], cn); });
   });
@@ -251,7 +277,9 @@ int bbmcu_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, c
     if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
     check_flags(component, unit);
     if(n == 0) return;
-    BsdfDesc d = make_desc(bsdf->b);
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
     run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {pdf, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], cn); });
   });
@@ -263,7 +291,9 @@ int bbmcu_reflectance(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int
     if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
     check_flags(component, unit);
     if(n == 0) return;
-    BsdfDesc d = make_desc(bsdf->b);
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
     run_any(ctx, n, {{out, 3, true}, {rgb, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_reflectance(ctx, s, d, component, (const float*)p[0], (float*)p[1], cn); });
   });
@@ -275,7 +305,9 @@ int bbmcu_sample(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit
     if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
     check_flags(component, unit);
     if(n == 0) return;
-    BsdfDesc d = make_desc(bsdf->b);
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
     run_any(ctx, n, {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {pdf, 1, false}, {flag, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_sample(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], cn); });
   });
@@ -288,7 +320,9 @@ int bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component,
     if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
     check_flags(component, unit);
     if(n == 0) return;
-    BsdfDesc d = make_desc(bsdf->b);
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
     run_any(ctx, n, {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}},
             [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_sample_eval_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn); });
@@ -363,19 +397,8 @@ int bbmcu_merl_read(bbmcu_ctx* ctx, const char* filename, float* rgb)
 {
   return guarded(ctx, [&] {
     if(!filename || !rgb) throw std::invalid_argument("BBM: null argument");
-    std::ifstream ifs(filename, std::ios_base::binary);
-    if(!ifs) throw std::runtime_error(std::string("BBM: unable to open MERL BRDF: ") + filename);
-    uint32_t dims[3] = {0, 0, 0};
-    ifs.read(reinterpret_cast<char*>(dims), sizeof(dims));
-    if(!ifs || dims[0] != 90 || dims[1] != 90 || dims[2] != 180) throw std::runtime_error(std::string("BBM: not a recognized MERL BRDF: ") + filename);
-    const size_t N = BBMCU_MERL_BINS;
-    std::vector<double> buf(3*N);
-    ifs.read(reinterpret_cast<char*>(buf.data()), 3*N*sizeof(double));
-    if(!ifs) throw std::runtime_error(std::string("BBM: truncated MERL BRDF: ") + filename);
-    const double scale[3] = {1.0, 1.15, 1.66};
-    for(int c=0; c < 3; ++c)
-      for(size_t i=0; i < N; ++i)
-        rgb[c*N + i] = (float)std::fmax(0.0, buf[c*N + i] * scale[c] / 1500.0);     // stored as double, read back as float
+    std::vector<float> t = bbmcu_host::read_merl(filename);
+    std::memcpy(rgb, t.data(), t.size()*sizeof(float));
   });
 }
 
@@ -383,15 +406,7 @@ int bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb)
 {
   return guarded(ctx, [&] {
     if(!filename || !rgb) throw std::invalid_argument("BBM: null argument");
-    std::ofstream ofs(filename, std::ios_base::binary);
-    if(!ofs) throw std::runtime_error(std::string("BBM: unable to write MERL BRDF: ") + filename);
-    uint32_t dims[3] = {90, 90, 180};
-    ofs.write(reinterpret_cast<const char*>(dims), sizeof(dims));
-    const size_t N = BBMCU_MERL_BINS;
-    std::vector<double> buf(3*N);
-    const double scale[3] = {1.0, 1.15, 1.66};
-    for(int c=0; c < 3; ++c) for(size_t i=0; i < N; ++i) buf[c*N + i] = (double)rgb[c*N + i] * 1500.0 / scale[c];
-    ofs.write(reinterpret_cast<const char*>(buf.data()), 3*N*sizeof(double));
+    bbmcu_host::write_merl(filename, rgb);
   });
 }
 

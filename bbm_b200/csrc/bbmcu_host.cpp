@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
 #include <fstream>
 #include <set>
 #include <sstream>
@@ -83,6 +84,8 @@ std::vector<ModelInfo> build_table()
   add("HeWestin", {param("roughness", 1, 0.18), param("autocorrelation", 1, 3.0), cior("eta", 3)});
   add("HeHolzschuch", {param("roughness", 1, 0.18), param("autocorrelation", 1, 3.0), cior("eta", 3)});
   add("NganHe", {scale("albedo", SS), param("roughness", 1, 0.18), param("autocorrelation", 1, 3.0), ior("eta")});
+  // the measured model (include/staticmodel/merl.h): one string attribute (the file name), nothing to fit
+  add("Merl", {});
   return t;
 }
 
@@ -195,6 +198,22 @@ Lobe parse_lobe(const std::string& str)
   const ModelInfo* m = find_model(kw.first);
   if(!m) throw std::invalid_argument("BBM: unrecognized BSDF model: " + kw.first + " in: " + str);
   Lobe l; l.model = m;
+  if(m->name == "Merl")
+  {
+    // Merl("file") / Merl(filename = "file"): string_converter<std::string>::fromString strips quotes and blanks
+    // (include/core/stringconvert.h:233-245)
+    std::string arg = remove_brackets(kw.second);
+    auto kv = split_eq(arg);
+    if(!kv.first.empty() && kv.first != "filename") throw std::invalid_argument("BBM: invalid argument name: " + kv.first + "(" + kv.second + ") in: " + kw.second);
+    const char* quotes = "\"' \r\n\t\v";
+    size_t b = kv.second.find_first_not_of(quotes), e = kv.second.find_last_not_of(quotes);
+    if(b == std::string::npos || b > e) throw std::invalid_argument("BBM: connect convert to string; unbalanced quotes in: " + kv.second);
+    auto data = std::make_shared<MerlData>();
+    data->filename = kv.second.substr(b, e - b + 1);
+    data->rgb = read_merl(data->filename);
+    l.merl = data;
+    return l;
+  }
   auto args = split_args(remove_brackets(kw.second));
   const size_t NA = m->attrs.size();
   if(args.size() > NA) throw std::invalid_argument("BBM: expected at most " + std::to_string(NA) + " arguments, found " + std::to_string(args.size()) + " in: " + kw.second);
@@ -260,6 +279,7 @@ Bsdf parse_bsdf(const std::string& str)
 std::string Bsdf::to_string() const
 {
   auto one = [](const Lobe& l) {
+    if(l.merl) return l.model->name + "(\"" + l.merl->filename + "\")";          // merl_data::toString (merl.h:161-164)
     std::string s = l.model->name + "(";
     int off = 0;
     for(size_t i=0; i < l.model->attrs.size(); ++i)
@@ -314,6 +334,40 @@ void Bsdf::set_params(int flags, const double* v, int n)
       off += a.width;
     }
   }
+}
+
+// merl_data::import (include/staticmodel/merl.h:173-206): three u32 dimensions (90, 90, 180), then three planes of
+// doubles; negative values clamp to 0; channels scale by 1/1500, 1.15/1500, 1.66/1500; stored as double, read as float
+std::vector<float> read_merl(const std::string& filename)
+{
+  std::ifstream ifs(filename.c_str(), std::ios_base::binary);
+  if(!ifs) throw std::runtime_error("BBM: unable to open MERL BRDF: \"" + filename + "\"");
+  uint32_t dims[3] = {0, 0, 0};
+  ifs.read(reinterpret_cast<char*>(dims), sizeof(dims));
+  if(!ifs || dims[0] != 90 || dims[1] != 90 || dims[2] != 180) throw std::runtime_error("BBM: not a recognized MERL BRDF: \"" + filename + "\"");
+  const size_t N = size_t(90)*90*180;
+  std::vector<double> buf(3*N);
+  ifs.read(reinterpret_cast<char*>(buf.data()), 3*N*sizeof(double));
+  if(!ifs) throw std::runtime_error("BBM: truncated MERL BRDF: \"" + filename + "\"");
+  const double scale[3] = {1.0, 1.15, 1.66};
+  std::vector<float> rgb(3*N);
+  for(int c=0; c < 3; ++c)
+    for(size_t i=0; i < N; ++i)
+      rgb[c*N + i] = (float)std::fmax(0.0, buf[c*N + i] * scale[c] / 1500.0);
+  return rgb;
+}
+
+void write_merl(const std::string& filename, const float* rgb)
+{
+  std::ofstream ofs(filename.c_str(), std::ios_base::binary);
+  if(!ofs) throw std::runtime_error("BBM: unable to write MERL BRDF: " + filename);
+  uint32_t dims[3] = {90, 90, 180};
+  ofs.write(reinterpret_cast<const char*>(dims), sizeof(dims));
+  const size_t N = size_t(90)*90*180;
+  std::vector<double> buf(3*N);
+  const double scale[3] = {1.0, 1.15, 1.66};
+  for(int c=0; c < 3; ++c) for(size_t i=0; i < N; ++i) buf[c*N + i] = (double)rgb[c*N + i] * 1500.0 / scale[c];
+  ofs.write(reinterpret_cast<const char*>(buf.data()), 3*N*sizeof(double));
 }
 
 std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename)

@@ -39,10 +39,25 @@ struct ModelInfo
 const std::vector<ModelInfo>& model_table();
 const ModelInfo* find_model(const std::string& name);
 
+// a loaded MERL measurement (include/staticmodel/merl.h:173-206): 3 planes of 1 458 000 floats on the host, plus
+// lazily created per-device copies (uploaded and released by the CUDA side through the two hooks, so that this file
+// stays free of CUDA)
+struct MerlData
+{
+  std::string filename;
+  std::vector<float> rgb;
+  mutable std::map<int, void*> device;                       // device index -> device copy
+  mutable void (*release)(int device, void* ptr) = nullptr;  // set by whoever created the copies
+  ~MerlData() { if(release) for(auto& d : device) release(d.first, d.second); }
+};
+std::vector<float> read_merl(const std::string& filename);                        // throws std::runtime_error like merl_data::import
+void write_merl(const std::string& filename, const float* rgb);
+
 struct Lobe
 {
   const ModelInfo* model;
   std::vector<double> values;        // full attribute block (all attributes incl. Dependent), reflection order
+  std::shared_ptr<const MerlData> merl;   // only for the measured model Merl("file")
 };
 
 // bsdf_ptr equivalent: one model, or Aggregate(...) of several

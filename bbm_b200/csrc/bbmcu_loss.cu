@@ -73,18 +73,28 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_generic(const LossArgs a,
   {
     double v = 0.0;
     for(int w=0; w < kLossThreads/32; ++w) v += s_red[w*(1 + P) + threadIdx.x];
-    a.partial[((size_t)k*gridDim.x + blockIdx.x)*(1 + P) + threadIdx.x] = v;
+    a.partial[((size_t)k*(1 + P) + threadIdx.x)*gridDim.x + blockIdx.x] = v;
   }
 }
 
-// second pass: fixed-order sum of the per-block partial rows, times 1/N
-__global__ void k_loss_finish(const double* partial, int blocks_x, int cols, double inv_n, double* result)
+// second pass: block (k, column) adds that column's per-block partials - strided per thread, then a fixed shared-memory
+// tree - and scales by 1/N.  The order depends only on the launch shape: deterministic.
+constexpr int kFinishThreads = 128;
+__global__ void __launch_bounds__(kFinishThreads) k_loss_finish(const double* partial, int blocks_x, int cols, double inv_n, double* result)
 {
-  const int k = blockIdx.x, j = threadIdx.x;
-  if(j >= cols) return;
+  __shared__ double s[kFinishThreads];
+  const int k = blockIdx.x, j = blockIdx.y;
+  const double* p = partial + ((size_t)k*cols + j)*blocks_x;
   double v = 0.0;
-  for(int b=0; b < blocks_x; ++b) v += partial[((size_t)k*blocks_x + b)*cols + j];
-  result[(size_t)k*cols + j] = v * inv_n;
+  for(int b = threadIdx.x; b < blocks_x; b += kFinishThreads) v += p[b];
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for(int o = kFinishThreads/2; o > 0; o >>= 1)
+  {
+    if((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if(threadIdx.x == 0) result[(size_t)k*cols + j] = s[0] * inv_n;
 }
 
 // per-sample terms l(idx) (sampledlossfunction::operator()(idx))
@@ -146,7 +156,7 @@ int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* gr
     // 2. the reference operand tabulated at those directions (it never changes during a fit)
     if(reference_bsdf)
     {
-      BsdfDesc d = make_desc(reference_bsdf->b);
+      BsdfDesc d = make_desc(reference_bsdf->b, ctx->device);
       launch_eval(ctx, ctx->stream, d, component, L->d_in, L->d_out, L->d_ref, n);
     }
     else
@@ -191,7 +201,7 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     const int P = bsdf->b.param_count(BBMCU_ATTR_ALL);
     if(P > kMaxParams) throw std::invalid_argument("BBM: more than " + std::to_string(kMaxParams) + " fit parameters");
-    BsdfDesc shape = make_desc(bsdf->b);
+    BsdfDesc shape = make_desc(bsdf->b, ctx->device);
     const int A = shape.n_floats;                 // device floats per parameter set (He lobes carry an unused table gap)
     const bool want_grad = (grad_out != nullptr) || (device_out != nullptr);
     const int cols = 1 + P;
@@ -249,7 +259,7 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     }
     else BBMCU_CUDA(cudaMemsetAsync(L->d_partial, 0, K*(size_t)bx*cols*sizeof(double), ctx->stream));
     double* result = device_out ? device_out : L->d_result;
-    k_loss_finish<<<(unsigned)K, 64, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
+    k_loss_finish<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
     BBMCU_CUDA(cudaGetLastError());
     ++ctx->launches;
     if(device_out) return;                       // caller all-reduces / reads it on the stream
@@ -276,7 +286,7 @@ int bbmcu_loss_terms(bbmcu_loss* L, const bbmcu_bsdf* bsdf, float* terms)
     if(!L || !bsdf || !terms) throw std::invalid_argument("BBM: null argument");
     if(L->count == 0) return;
     BBMCU_CUDA(cudaSetDevice(ctx->device));
-    BsdfDesc shape = make_desc(bsdf->b);
+    BsdfDesc shape = make_desc(bsdf->b, ctx->device);
     LossArgs a{};
     a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = L->count; a.metric = L->metric; a.component = L->component;
     const bool dev = is_device_pointer(terms);

@@ -26,7 +26,7 @@ struct LossArgs
   int n_attrs;
   int metric, component;
   int want_grad;
-  double* partial;        // K x blocks_x x (1 + P)
+  double* partial;        // K x (1 + P) x blocks_x
   int P;
   int sm_count;
 };
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
 #pragma unroll
         for(int w=0; w < kLossThreads/32; ++w) v += (double)s_red[kk][w][j];
       }
-      a.partial[((size_t)(kc + kk)*gridDim.x + tile)*(1 + a.P) + j] = v;
+      a.partial[((size_t)(kc + kk)*(1 + a.P) + j)*gridDim.x + tile] = v;          // [k][column][tile]: the finish kernel reads tiles coalesced
     }
     __syncthreads();
   }

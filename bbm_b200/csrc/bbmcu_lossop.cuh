@@ -59,6 +59,7 @@ template<class M> struct FitMap
   static constexpr int NFIT = M::NA;
   BBMCU_HD static constexpr int attr_of(int k) { return k; }
 };
+template<> struct FitMap<MerlModel> { static constexpr int NFIT = 0; BBMCU_HD static constexpr int attr_of(int k) { return k; } };   // measured data: nothing to fit
 using BagherModel = Microfacet<NdfSGD, GUncorrelated, FresnelBagher, 2, true>;
 template<> struct FitMap<BagherModel>
 {
@@ -106,6 +107,7 @@ template<class M> struct LobeJac
   BBMCU_D void combine(const Spec<float>& dv, const float* a, float* grad) const
   {
     constexpr int S = SCALED ? 3 : 0;
+    if constexpr (FitMap<M>::NFIT == 0) { (void)dv; (void)a; (void)grad; return; }
     if(SCALED) { grad[0] = dv.r*us[0]; grad[1] = dv.g*us[1]; grad[2] = dv.b*us[2]; }
     if constexpr (NL > 0)
     {
@@ -132,7 +134,12 @@ BBMCU_D LobeJac<M> lobe_jacobian(const typename GeomOf<M>::type& geom, const flo
   constexpr bool SCALED = (M::SCALE >= 0);
   static_assert(!SCALED || M::SCALE == 0, "leading scale expected at offset 0");
   LobeJac<M> J;
-  if constexpr (NL == 0)
+  if constexpr (NFIT == 0)
+  {
+    J.v = GeomOf<M>::template eval_unscaled<float>(geom, in, out, a, component);
+    J.us[0] = J.us[1] = J.us[2] = 0.0f;
+  }
+  else if constexpr (NL == 0)
   {
     Spec<float> u = GeomOf<M>::template eval_unscaled<float>(geom, in, out, a, component);
     J.us[0] = u.r; J.us[1] = u.g; J.us[2] = u.b;

@@ -5,6 +5,7 @@
 #include "bbmcu_lobes.cuh"
 #include "bbmcu_epd.cuh"
 #include "bbmcu_he.cuh"
+#include "bbmcu_merl.cuh"
 
 namespace bbmcu {
 
@@ -15,6 +16,7 @@ enum ModelId : int {
   M_CookTorrance, M_LowCookTorrance, M_NganCookTorrance, M_CookTorranceWalter, M_CookTorranceHeitz,
   M_GGX, M_GGXHeitz, M_PhongWalter, M_LowMicrofacet, M_LowMicrofacetFit, M_LowSmooth,
   M_Ribardiere, M_RibardiereAnisotropic, M_Bagher, M_EPD, M_He, M_HeWestin, M_HeHolzschuch, M_NganHe,
+  M_Merl,                       // the measured-data model (include/staticmodel/merl.h), listed after the 34 analytic ones
   M_COUNT
 };
 
@@ -54,15 +56,17 @@ BBMCU_MODEL(M_He, HeModel<HE_VARIANT_HE>)
 BBMCU_MODEL(M_HeWestin, HeModel<HE_VARIANT_WESTIN>)
 BBMCU_MODEL(M_HeHolzschuch, HeModel<HE_VARIANT_HOLZSCHUCH>)
 BBMCU_MODEL(M_NganHe, HeModel<HE_VARIANT_NGAN>)
+BBMCU_MODEL(M_Merl, MerlModel)
 
 // floats of device-side tables appended to a lobe's attribute block (the He family's 90-bin sampling CDF)
 template<class M> struct TableFloats { static constexpr int N = 0; };
 template<int V> struct TableFloats<HeModel<V>> { static constexpr int N = HeModel<V>::NT; };
-BBMCU_HD constexpr int table_floats_of(int model) { return (model >= M_He && model <= M_NganHe) ? kHeCdfBins : 0; }
+template<> struct TableFloats<MerlModel> { static constexpr int N = MerlModel::NT; };
+BBMCU_HD constexpr int table_floats_of(int model) { return (model >= M_He && model <= M_Merl) ? kHeCdfBins : 0; }
 
 // uniform (per-launch) dispatch on a model id: calls f((ModelOf<id>::type*)nullptr)
 #define BBMCU_CASES_EPD BBMCU_CASE(M_EPD)
-#define BBMCU_CASES_HE BBMCU_CASE(M_He) BBMCU_CASE(M_HeWestin) BBMCU_CASE(M_HeHolzschuch) BBMCU_CASE(M_NganHe)
+#define BBMCU_CASES_HE BBMCU_CASE(M_He) BBMCU_CASE(M_HeWestin) BBMCU_CASE(M_HeHolzschuch) BBMCU_CASE(M_NganHe) BBMCU_CASE(M_Merl)
 #define BBMCU_ALL_CASES \
     BBMCU_CASE(M_Lambertian) BBMCU_CASE(M_OrenNayar) BBMCU_CASE(M_Phong) BBMCU_CASE(M_NganBlinnPhong) \
     BBMCU_CASE(M_Lafortune) BBMCU_CASE(M_NganLafortune) BBMCU_CASE(M_Ward) BBMCU_CASE(M_WardDuer) \

@@ -70,7 +70,7 @@ typedef struct {
   int flag;              /* one BBMCU_ATTR_* bit                                                       */
   int offset;            /* first float of the attribute in the model's attribute block               */
 } bbmcu_attr;
-BBMCU_API int  bbmcu_model_count(void);                          /* 34 */
+BBMCU_API int  bbmcu_model_count(void);                          /* 35: the 34 analytic models + Merl (staticmodel/merl.h) */
 BBMCU_API const char* bbmcu_model_name(int model_id);
 BBMCU_API int  bbmcu_model_lookup(const char* name, int* model_id);
 BBMCU_API int  bbmcu_model_layout(int model_id, bbmcu_attr* attrs, int* n_attrs);   /* reflection order (util/reflection.h:141-148) */

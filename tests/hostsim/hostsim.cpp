@@ -27,6 +27,9 @@ template<class Op> static void run(const Op& op, size_t n)
   else for(size_t i=0; i < n; i += kVec) op.group(i);
 }
 
+// host-compiled tests: the "device" table of a measured model is its host table
+namespace bbmcu { const float* merl_device_table(const bbmcu_host::MerlData& m, int) { return m.rgb.data(); } }
+
 extern "C" {
 const char* hostsim_last_error() { return g_err.c_str(); }
 // the EPD G1 table (bbm_b200/data/epd_g1.f32), owned by the caller
@@ -34,16 +37,16 @@ void hostsim_set_epd_table(const float* table) { g_epd_g1_host = table; }
 float hostsim_gamma_q_inv(float a, float q) { return epd_gamma_q_inv(a, q); }
 
 int hostsim_eval(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
-{ GUARD( EvalOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
+{ GUARD( EvalOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
 
 int hostsim_pdf(const char* bsdf, int component, const float* in, const float* out, size_t n, float* pdf)
-{ GUARD( PdfOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.in = in; op.out = out; op.pdf = pdf; op.n = n; op.aligned = false; run(op, n); ) }
+{ GUARD( PdfOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.in = in; op.out = out; op.pdf = pdf; op.n = n; op.aligned = false; run(op, n); ) }
 
 int hostsim_reflectance(const char* bsdf, int component, const float* out, size_t n, float* rgb)
-{ GUARD( ReflectanceOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
+{ GUARD( ReflectanceOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
 
 int hostsim_sample(const char* bsdf, int component, const float* out, const float* xi, size_t n, float* dir, float* pdf, int32_t* flag)
-{ GUARD( SampleOp<BsdfGeneric> op; op.bsdf = make_desc(bbmcu_host::parse_bsdf(bsdf)); op.component = component; op.out = out; op.xi = xi; op.dir = dir; op.pdf = pdf; op.flag = flag; op.n = n; op.aligned = false; run(op, n); ) }
+{ GUARD( SampleOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.out = out; op.xi = xi; op.dir = dir; op.pdf = pdf; op.flag = flag; op.n = n; op.aligned = false; run(op, n); ) }
 
 int hostsim_merl_index(const float* in, const float* out, size_t n, uint32_t* index)
 { GUARD( MerlIndexOp op; op.in = in; op.out = out; op.index = index; op.n = n; op.aligned = false; run(op, n); ) }

@@ -38,7 +38,8 @@ def test_no_device_fails_loudly():
 def test_model_table_matches_reference_reflection():
     import bbm_b200 as bb
     layout = json.load(open(os.path.join(ROOT, "tests", "golden", "model_layout.json")))
-    assert bb.model_names() == list(layout.keys()) and len(layout) == 34
+    # the 34 analytic models in bbm_info order, then the measured model Merl (include/staticmodel/merl.h)
+    assert bb.model_names() == list(layout.keys()) + ["Merl"] and len(layout) == 34
     for name, rec in layout.items():
         b = bb.Bsdf(name + "()")
         assert b.to_string() == rec["string"]

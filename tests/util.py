@@ -9,7 +9,7 @@ def implemented_models():
     global IMPLEMENTED
     if IMPLEMENTED is None:
         import bbm_b200 as bb
-        IMPLEMENTED = bb.model_names()          # all 34 since the EPD and He families landed
+        IMPLEMENTED = bb.model_names()          # all 34 analytic models + Merl
     return IMPLEMENTED
 
 
