@@ -211,12 +211,33 @@ def test_loss_against_measured_table(ctx, ref, tmp_path):
     assert_parity(L.terms(bb.Bsdf(fitted), 31*16*9), terms, 1e-5, floor=1e-12, what="standardLog vs merl<> reference")
 
 
+def test_grid_census_against_reference(ctx, ref):
+    """whole-grid properties of the reference that a restatement has to reproduce exactly:
+    which bins do NOT round-trip through index -> directions -> index, and where Ward / He evaluate to NaN / Inf"""
+    import bbm_b200 as bb
+    N = bb.MERL_BINS
+    i, o = ctx.merl_dirs(0, N)
+    back = ctx.merl_index(i, o)
+    no_round_trip = int((back != np.arange(N, dtype=np.uint32)).sum())
+    ri, ro = ref.merl_dirs(0, N, threads=8)
+    want = int((ref.merl_index(ri, ro, threads=8) != np.arange(N)).sum())
+    assert no_round_trip == want == 378883                       # samples sit on bin lower edges (merl_linearizer.h:72-73)
+    assert int((i[2] == 0).sum()) == 174592 and int((o[2] == 0).sum()) == 171978
+    for name, nan_inf in (("Ward", (133744, 212826)), ("WardDuer", (133744, 212826)), ("NganWard", (133744, 212826)), ("He", (1, 1)), ("CookTorrance", (0, 0))):
+        s = name + "()"
+        got = ctx.eval(bb.Bsdf(s), i, o).T
+        assert_parity(got, ref.eval(s, ri, ro, threads=8), 1e-5, what=f"grid eval {s}")      # NaN == NaN, Inf == Inf with sign
+        bad = ~np.isfinite(got).all(1)
+        nan = int(np.isnan(got).any(1).sum())
+        assert (nan, int(bad.sum()) - nan) == nan_inf, (name, nan, int(bad.sum()) - nan)
+
+
 def test_full_size_properties(ctx):
-    """2^22 pairs (the BASELINE config-2 workload shape, reduced 16x to keep the test short):
-    sample.pdf == pdf(sample.direction), flags consistent, reciprocity of eval"""
+    """2^26 pairs (the BASELINE config-2 workload at full size): sample.pdf == pdf(sample.direction), flags consistent,
+    unit sampled directions, reciprocity of eval"""
     import torch
     import bbm_b200 as bb
-    n = 1 << 22
+    n = 1 << 26
     g = torch.Generator(device="cuda").manual_seed(1)
     z = torch.rand(n, device="cuda", generator=g)
     ph = torch.rand(n, device="cuda", generator=g) * (2*np.pi)
