@@ -285,6 +285,12 @@ class Context:
             raise BbmInvalidArgument("expected a (3, 1458000) table")
         _check(lib().bbmcu_merl_write(self._h, filename.encode(), _ptr(rgb)), self._h)
 
+    def hp_precompute_g1(self):
+        """the (100, 1000) Holzschuch-Pacanowski G1 table, recomputed on the GPU (precompute/HolzschuchPacanowski/G1.cpp)"""
+        t = np.empty((100, 1000), np.float32)
+        _check(lib().bbmcu_hp_precompute_g1(self._h, _ptr(t)), self._h)
+        return t
+
     # ---- losses ------------------------------------------------------------------------------------
     def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0):
         return Loss(self, metric, reference, grid, component, unit, first, count)

@@ -36,6 +36,20 @@ BBMCU_D double m_sqrt(double a) { return sqrt(a); }
 BBMCU_D double m_safe_sqrt(double a) { return safe_sqrt_d(a); }
 BBMCU_D double val(double a) { return a; }
 
+// exp of a double argument to float accuracy (the terms of Eq. 78 are rounded to float anyway): expf of the float part
+// times (1 + remainder); ~2 ulp of a float, i.e. 1e-7 relative against the reference's double exp - the quick tier.
+// On the host this is the plain double exp.
+BBMCU_D double he_exp(double x)
+{
+#ifdef __CUDA_ARCH__
+  const float hi = (float)x;
+  const float lo = (float)(x - (double)hi);
+  return (double)(expf(hi) * (1.0f + lo));
+#else
+  return exp(x);
+#endif
+}
+
 template<int V> struct HeTraits;
 template<> struct HeTraits<HE_VARIANT_HE>         { static constexpr bool ERRATA = false, WESTIN = false, ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
 template<> struct HeTraits<HE_VARIANT_WESTIN>     { static constexpr bool ERRATA = true,  WESTIN = true,  ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
@@ -148,11 +162,14 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
     for(int m=1; m <= Tr::TERMS && !converged; ++m)
     {
       float tmin = 3.402823466e+38f;
+      // one double reciprocal per term instead of two double divisions per channel: g/m and (.)/m become products with
+      // 1/m, equal to the reference's quotients to 1 ulp of a double - invisible after the rounding to float
+      const double inv_m = 1.0 / (double)m;
 #pragma unroll
       for(int c=0; c < 3; ++c)
       {
-        gm[c] = (float)((double)gm[c] * (g[c] / (double)m));
-        term[c] = (float)(exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] / (double)m);
+        gm[c] = (float)((double)gm[c] * (g[c] * inv_m));
+        term[c] = (float)(he_exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] * inv_m);
         sum[c] += term[c];
       }
       tmin = term[0]; if(term[1] < tmin) tmin = term[1]; if(term[2] < tmin) tmin = term[2];      // std::min_element order

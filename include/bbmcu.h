@@ -119,6 +119,11 @@ BBMCU_API int  bbmcu_spherical_dirs(bbmcu_ctx* ctx, const bbmcu_spherical_grid* 
 BBMCU_API int  bbmcu_merl_read(bbmcu_ctx* ctx, const char* filename, float* rgb);
 BBMCU_API int  bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb);     /* inverse of the above */
 
+/* ---- Holzschuch-Pacanowski precompute (precompute/HolzschuchPacanowski/G1.cpp) --------------------------------------- */
+/* regenerates the 100 x 1000 G1 table of include/precomputed/holzschuchpacanowski/G1.h (row = 5/p - 1, column = the
+ * table's tan(theta) map) into `table` (HOST memory, 100000 floats): ~1e9 quadrature terms on the GPU */
+BBMCU_API int  bbmcu_hp_precompute_g1(bbmcu_ctx* ctx, float* table);
+
 /* ---- losses (include/loss/{cosine_weighted_l2,cosine_weighted_log}.h, include/bbm/sampledlossfunction.h:62-87) ---------------------------------- */
 /* The reference evaluates  loss = (1/N) sum_i e(in_i, out_i, fitted.eval(in_i,out_i), reference.eval(in_i,out_i))
  * over a linearizer.  A bbmcu_loss fixes metric, linearizer, component and the reference operand; the

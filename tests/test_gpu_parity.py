@@ -3,8 +3,12 @@
 (oracle/_ref, when present) on seeded inputs.  Tolerances are SURVEY.md section 8(c)'s:
 1e-5 relative for eval / pdf / reflectance / sampled directions, exact flags and bin indices,
 1e-4 for loss and gradient."""
+import os
+
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from tests.test_models_hostsim import COMPONENTS, _cases, defined_samples
 from tests.util import assert_parity, pdf_floor, soa, uses_only_implemented
@@ -316,3 +320,14 @@ def test_merl_model_on_gpu(ctx, ref, tmp_path):
     la = ctx.loss("nganL2", b, None)(fitted)
     lb = ctx.loss("nganL2", ctx.merl_read(path), None)(fitted)
     assert la[0] == lb[0]
+
+
+def test_hp_g1_table_regenerated_on_gpu(ctx):
+    """the reference's G1 generator (hours on one core) as one kernel; the result is the shipped
+    table (printed with 6 significant digits by the generator) to 5e-6 relative / 1e-6 absolute, every one of 100 000 entries"""
+    shipped = np.fromfile(os.path.join(ROOT, "bbm_b200", "data", "epd_g1.f32"), np.float32).reshape(100, 1000)
+    got = ctx.hp_precompute_g1()
+    err = np.abs(got.astype(np.float64) - shipped)
+    tol = 5e-6 * np.abs(shipped) + 1e-6
+    assert np.isfinite(got).all()
+    assert int((err > tol).sum()) == 0, (int((err > tol).sum()), float(err.max()), np.argwhere(err > tol)[:5])
