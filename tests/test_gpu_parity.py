@@ -331,3 +331,29 @@ def test_hp_g1_table_regenerated_on_gpu(ctx):
     tol = 5e-6 * np.abs(shipped) + 1e-6
     assert np.isfinite(got).all()
     assert int((err > tol).sum()) == 0, (int((err > tol).sum()), float(err.max()), np.argwhere(err > tol)[:5])
+
+
+@pytest.mark.parametrize("metric", ["nganL2", "bieronLog"])
+def test_loss_and_gradient_kernels_of_every_model(ctx, hostsim, metric):
+    """every compile-time loss kernel (one per model) on the device against the same device headers compiled for the host
+    (tests/hostsim), whose values and gradients are pinned against the reference in tests/test_gradients_hostsim.py"""
+    import bbm_b200 as bb
+    from tests.test_gradients_hostsim import CASES
+    hp = float(np.float32(2) * np.float32(np.pi))
+    tp, t0 = 1.4, 0.05
+    grid = bb.spherical_grid((11, 6), (4, 5), start_in=(0, t0), start_out=(0, t0), end_in=(hp, tp), end_out=(hp, tp))
+    N = 11 * 6 * 4 * 5
+    i, o = hostsim.spherical_dirs([11, 6, 4, 5], [0, t0, hp, tp, 0, t0, hp, tp], 0, N)
+    m = bb.METRICS.index(metric)
+    for fitted, truth in CASES:
+        fb = bb.Bsdf(fitted)
+        P = len(fb.parameter_values())
+        L = ctx.loss(metric, bb.Bsdf(truth), grid)
+        loss, grad = L(fb, grad=True)
+        plain = L(fb)
+        tv = hostsim.eval(truth, i, o)
+        want_l, want_g, _ = hostsim.loss(fitted, m, i, o, tv, nparams=P)
+        assert abs(loss[0] - want_l) <= 1e-4 * abs(want_l), (fitted, loss[0], want_l)
+        assert abs(plain[0] - want_l) <= 1e-4 * abs(want_l), (fitted, plain[0], want_l)
+        tol = 2e-4 * np.abs(want_g) + 2e-4 * np.abs(want_g).max()
+        assert np.all(np.abs(grad[0] - want_g) <= tol), (fitted, metric, grad[0], want_g)
