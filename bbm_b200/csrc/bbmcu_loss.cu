@@ -24,7 +24,9 @@ struct bbmcu_loss
   float* d_ref = nullptr;
   // scratch, grown on demand
   float* d_attrs = nullptr;   size_t attrs_cap = 0;
-  float* h_attrs = nullptr;   size_t h_attrs_cap = 0;   // pinned
+  float* h_attrs[2] = {nullptr, nullptr}; size_t h_attrs_cap[2] = {0, 0};   // pinned, double buffered
+  cudaEvent_t h_attrs_free[2] = {nullptr, nullptr};                          // recorded after the upload from each
+  int h_flip = 0;
   double* d_partial = nullptr; size_t partial_cap = 0;
   double* d_result = nullptr;  size_t result_cap = 0;
   double* h_result = nullptr;  size_t h_result_cap = 0;  // pinned
@@ -32,7 +34,7 @@ struct bbmcu_loss
   ~bbmcu_loss()
   {
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
-    if(h_attrs) cudaFreeHost(h_attrs);
+    for(int i=0; i < 2; ++i) { if(h_attrs[i]) cudaFreeHost(h_attrs[i]); if(h_attrs_free[i]) cudaEventDestroy(h_attrs_free[i]); }
     if(h_result) cudaFreeHost(h_result);
   }
 };
@@ -207,13 +209,18 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     const int cols = 1 + P;
     // attribute blocks for the K parameter sets
     grow(L->d_attrs, L->attrs_cap, K*(size_t)A);
-    if(K*(size_t)A > L->h_attrs_cap)
+    // two pinned staging buffers: packing the next batch never waits for the kernels of the previous one, only (and in
+    // practice never) for the upload that last read the buffer it is about to overwrite
+    const int hb = L->h_flip; L->h_flip ^= 1;
+    if(!L->h_attrs_free[hb]) BBMCU_CUDA(cudaEventCreateWithFlags(&L->h_attrs_free[hb], cudaEventDisableTiming));
+    else BBMCU_CUDA(cudaEventSynchronize(L->h_attrs_free[hb]));
+    if(K*(size_t)A > L->h_attrs_cap[hb])
     {
-      if(L->h_attrs) { BBMCU_CUDA(cudaFreeHost(L->h_attrs)); L->h_attrs = nullptr; L->h_attrs_cap = 0; }
-      BBMCU_CUDA(cudaMallocHost(&L->h_attrs, K*(size_t)A*sizeof(float)));
-      L->h_attrs_cap = K*(size_t)A;
+      if(L->h_attrs[hb]) { BBMCU_CUDA(cudaFreeHost(L->h_attrs[hb])); L->h_attrs[hb] = nullptr; L->h_attrs_cap[hb] = 0; }
+      BBMCU_CUDA(cudaMallocHost(&L->h_attrs[hb], K*(size_t)A*sizeof(float)));
+      L->h_attrs_cap[hb] = K*(size_t)A;
     }
-    BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));      // the previous upload from this pinned buffer has been consumed
+    float* const h_attrs = L->h_attrs[hb];
     {
       bbmcu_host::Bsdf tmp = bsdf->b;
       for(size_t k=0; k < K; ++k)
@@ -222,11 +229,12 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
         for(size_t l=0; l < tmp.lobes.size(); ++l)
         {
           size_t off = (size_t)shape.offset[l];
-          for(double v : tmp.lobes[l].values) L->h_attrs[k*A + off++] = (float)v;
+          for(double v : tmp.lobes[l].values) h_attrs[k*A + off++] = (float)v;
         }
       }
     }
-    BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, L->h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    BBMCU_CUDA(cudaEventRecord(L->h_attrs_free[hb], ctx->stream));
     // launch shape: about 8 resident blocks per SM over all K
     const size_t n = L->count;
     const bool static_shape = (shape.n_lobes == 1 && !shape.aggregate) || (shape.n_lobes == 2 && shape.aggregate && shape.model[0] == M_Lambertian);
