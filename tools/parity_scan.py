@@ -52,7 +52,10 @@ def scan(ctx, ref, s, n, seed, threads):
     want_p = ref.pdf(s, d_aos, out, threads=threads)
     res["eval_at_gpu_dir_beyond_1e-5"] = int(mismatch(rgb.T[ok], want_e[ok], 1e-5, 1e-30).any(1).sum())
     res["pdf_at_gpu_dir_beyond_1e-5"] = int(mismatch(p[ok], want_p[ok], 1e-5, pdf_floor(s, want_p[ok])).sum())
+    # sample.pdf == pdf(sample.direction, out) for every model except AshikhminShirleyFull, whose sample() mixes the pdfs
+    # of two different directions (ashikhminshirleyfull.h:97-113): that one is judged against the reference's sample.pdf
     res["sample_pdf_vs_pdf_mismatch"] = int(mismatch(sp[ok], want_p[ok], 1e-5, pdf_floor(s, want_p[ok])).sum())
+    res["sample_pdf_vs_ref_sample_pdf_beyond_1e-3"] = int(mismatch(sp[ok], rsp[ok], 1e-3, pdf_floor(s, rsp[ok])).sum())
     with np.errstate(invalid="ignore", divide="ignore"):
         err = np.abs(d_aos.astype(np.float64) - rd).max(1)
     res["dir_max_abs_err"] = float(np.nanmax(err))
