@@ -153,4 +153,151 @@ BBMCU_D void glibc_sincosf_both(float y, float& sn, float& cs)
 BBMCU_D float glibc_sinf(float y) { return glibc_sincosf<false>(y); }
 BBMCU_D float glibc_cosf(float y) { return glibc_sincosf<true>(y); }
 
+
+BBMCU_D uint64_t d2u(double f) {
+#ifdef __CUDA_ARCH__
+  return (uint64_t)__double_as_longlong(f);
+#else
+  uint64_t u; memcpy(&u, &f, 8); return u;
+#endif
+}
+BBMCU_D double u2d(uint64_t u) {
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double f; memcpy(&f, &u, 8); return f;
+#endif
+}
+
+// ---- glibc 2.39 expf / logf (ARM optimized routines: sysdeps/ieee754/flt-32/e_expf.c, e_logf.c with their
+// exp2f_data / logf_data tables) and erff (fdlibm, sysdeps/ieee754/flt-32/s_erff.c), written from the published
+// algorithms; the erff coefficients were cross-checked against the constants the host library carries.  expf follows
+// the x86-64 multiarch FMA build that the dynamic loader selects on every FMA-capable host (one fused
+// multiply-subtract in the reduction, fused polynomial steps).  Each agrees with the host glibc on 2e8 random
+// arguments without a single differing bit (tests/test_linearizer_loss_hostsim.py repeats a sample).
+// The Beckmann visible-normal sampler ends in erfinv near +-1, which amplifies a last-bit difference of any of these
+// by up to 1e4: with them it reproduces the reference's sampled directions instead of 4e-5 of them being off.
+// (tables: one copy in device memory and one for the host-compiled tests; a function-local array would live in
+// local memory and be rebuilt on every call)
+#define BBMCU_EXP2F_T { \
+0x3ff0000000000000, 0x3fefd9b0d3158574, 0x3fefb5586cf9890f, 0x3fef9301d0125b51, 0x3fef72b83c7d517b, 0x3fef54873168b9aa, 0x3fef387a6e756238, 0x3fef1e9df51fdee1, \
+0x3fef06fe0a31b715, 0x3feef1a7373aa9cb, 0x3feedea64c123422, 0x3feece086061892d, 0x3feebfdad5362a27, 0x3feeb42b569d4f82, 0x3feeab07dd485429, 0x3feea47eb03a5585, \
+0x3feea09e667f3bcd, 0x3fee9f75e8ec5f74, 0x3feea11473eb0187, 0x3feea589994cce13, 0x3feeace5422aa0db, 0x3feeb737b0cdc5e5, 0x3feec49182a3f090, 0x3feed503b23e255d, \
+0x3feee89f995ad3ad, 0x3feeff76f2fb5e47, 0x3fef199bdd85529c, 0x3fef3720dcef9069, 0x3fef5818dcfba487, 0x3fef7c97337b9b5f, 0x3fefa4afa2a490da, 0x3fefd0765b6e4540 }
+#ifdef __CUDACC__
+static __device__ const uint64_t d_exp2f_T[32] = BBMCU_EXP2F_T;
+#endif
+static const uint64_t h_exp2f_T[32] = BBMCU_EXP2F_T;
+BBMCU_D uint64_t exp2f_T(int i)
+{
+#ifdef __CUDA_ARCH__
+  return d_exp2f_T[i];
+#else
+  return h_exp2f_T[i];
+#endif
+}
+BBMCU_D float glibc_expf(float x)
+{
+  const double InvLn2N = 0x1.71547652b82fep+0 * 32, SHIFT = 0x1.8p+52;
+  const double C0 = 0x1.c6af84b912394p-5/32/32/32, C1 = 0x1.ebfce50fac4f3p-3/32/32, C2 = 0x1.62e42ff0c52d6p-1/32;
+  double xd = (double)x;
+  uint32_t abstop = (f2u(x) >> 20) & 0x7ff;
+  if(abstop >= 0x42b) {                       /* |x| >= 88 or NaN/Inf */
+    if(f2u(x) == f2u(u2f(0xff800000u))) return 0.0f;
+    if(abstop >= 0x7f8) return x + x;
+    if(x > 0x1.62e42ep6f) return u2f(0x7f800000u);   /* overflow */
+    if(x < -0x1.9fe368p6f) return 0.0f;      /* underflow */
+  }
+  double z = InvLn2N * xd;
+  double kd = z + SHIFT;
+  uint64_t ki = d2u(kd);
+  kd -= SHIFT;
+  double r = fma(InvLn2N, xd, -kd);
+  uint64_t t = exp2f_T((int)(ki % 32));
+  t += ki << (52 - 5);
+  double s = u2d(t);
+  z = fma(C0, r, C1);
+  double r2 = r * r;
+  double y = fma(C2, r, 1.0);
+  y = fma(z, r2, y);
+  y = y * s;
+  return (float)y;
+}
+#define BBMCU_LOGF_T { \
+ {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2}, {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2}, {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3}, \
+ {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3}, {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4}, \
+ {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0}, {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5}, {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4}, \
+ {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3}, {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3}, {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2}, {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2} }
+#ifdef __CUDACC__
+static __device__ const double d_logf_T[16][2] = BBMCU_LOGF_T;
+#endif
+static const double h_logf_T[16][2] = BBMCU_LOGF_T;
+BBMCU_D void logf_T(int i, double& invc, double& logc)
+{
+#ifdef __CUDA_ARCH__
+  invc = d_logf_T[i][0]; logc = d_logf_T[i][1];
+#else
+  invc = h_logf_T[i][0]; logc = h_logf_T[i][1];
+#endif
+}
+BBMCU_D float glibc_logf(float x)
+{
+  const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2, Ln2 = 0x1.62e42fefa39efp-1;
+  uint32_t ix = f2u(x);
+  if(ix == 0x3f800000) return 0.0f;
+  if(ix - 0x00800000 >= 0x7f800000 - 0x00800000) {
+    if(ix * 2 == 0) return u2f(0xff800000u);
+    if(ix == 0x7f800000) return x;
+    if((ix & 0x80000000) || ix * 2 >= 0xff000000) return (x - x) / 0.0f;
+    ix = f2u(x * 0x1p23f); ix -= 23 << 23;
+  }
+  uint32_t tmp = ix - 0x3f330000;
+  int i = (tmp >> (23 - 4)) % 16;
+  int k = (int32_t)tmp >> 23;
+  uint32_t iz = ix - (tmp & 0xff800000);
+  double invc, logc; logf_T(i, invc, logc);
+  double z = (double)u2f(iz);
+  double r = z * invc - 1;
+  double y0 = logc + (double)k * Ln2;
+  double r2 = r * r;
+  double y = A1 * r + A2;
+  y = A0 * r2 + y;
+  y = y * r2 + (y0 + r);
+  return (float)y;
+}
+BBMCU_D float glibc_erff(float x)
+{
+  const float erx = 8.4506291151e-01f, efx = 1.2837916613e-01f, efx8 = 1.0270333290e+00f;
+  uint32_t hx = f2u(x), ix = hx & 0x7fffffff;
+  if(ix >= 0x7f800000) { int i = ((uint32_t)hx >> 31) << 1; return (float)(1 - i) + 1.0f / x; }
+  if(ix < 0x3f580000) {
+    if(ix < 0x31800000) { if(ix < 0x04000000) return 0.0625f * (16.0f * x + u2f(0x400375d4) * x); return x + u2f(0x3e0375d4) * x; }
+    float z = x * x;
+    float r = u2f(0x3e0375d4) + z * (-u2f(0x3ea66beb) + z * (-u2f(0x3ce9528f) + z * (-u2f(0x3bbd1489) + z * u2f(0xb7c756b1))));
+    float s = 1.0f + z * (u2f(0x3ecbbbce) + z * (u2f(0x3d852a63) + z * (u2f(0x3ba68116) + z * (u2f(0x390aee49) + z * u2f(0xb684e21a)))));
+    float y = r / s;
+    return x + x * y;
+  }
+  if(ix < 0x3fa00000) {
+    float s = fabsf(x) - 1.0f;
+    float P = -u2f(0x3b1acdc6) + s * (u2f(0x3ed46805) + s * (-u2f(0x3ebe9208) + s * (u2f(0x3ea2fe54) + s * (-u2f(0x3de31cc2) + s * (u2f(0x3d1151b3) + s * u2f(0xbb0df9c0))))));
+    float Q = 1.0f + s * (u2f(0x3dd9f331) + s * (u2f(0x3f0a5785) + s * (u2f(0x3d931ae7) + s * (u2f(0x3e013307) + s * (u2f(0x3c5f6e13) + s * u2f(0x3c445aa3))))));
+    return ((int32_t)hx >= 0) ? erx + P / Q : -erx - P / Q;
+  }
+  if(ix >= 0x40c00000) return ((int32_t)hx >= 0) ? 1.0f - 1e-30f : 1e-30f - 1.0f;
+  float ax = fabsf(x);
+  float s = 1.0f / (ax * ax);
+  float R, S;
+  if(ix < 0x4036DB6E) {
+    R = -u2f(0x3c21a093) + s * (-u2f(0x3f31a0b7) + s * (-u2f(0x4128f022) + s * (-u2f(0x42798057) + s * (-u2f(0x4322658c) + s * (-u2f(0x43389ae7) + s * (-u2f(0x42a2932b) + s * u2f(0xc11d077e)))))));
+    S = 1.0f + s * (u2f(0x419d35ce) + s * (u2f(0x4309a863) + s * (u2f(0x43d9486f) + s * (u2f(0x442158c9) + s * (u2f(0x43d6810b) + s * (u2f(0x42d9451f) + s * (u2f(0x40d23f7c) + s * u2f(0xbd777f97))))))));
+  } else {
+    R = -u2f(0x3c21a092) + s * (-u2f(0x3f4c9dd4) + s * (-u2f(0x418e104b) + s * (-u2f(0x4320a2ea) + s * (-u2f(0x441f6441) + s * (-u2f(0x4480230b) + s * u2f(0xc3f1c275))))));
+    S = 1.0f + s * (u2f(0x41f2b459) + s * (u2f(0x43a2e571) + s * (u2f(0x44c01759) + s * (u2f(0x4547fdbb) + s * (u2f(0x451f90ce) + s * (u2f(0x43ed43a7) + s * u2f(0xc1b38712)))))));
+  }
+  float z = u2f(f2u(ax) & 0xfffff000);
+  float r = glibc_expf(-z * z - 0.5625f) * glibc_expf((z - ax) * (z + ax) + R / S);
+  return ((int32_t)hx >= 0) ? 1.0f - r / ax : r / ax - 1.0f;
+}
+
 } // namespace bbmcu

@@ -155,20 +155,22 @@ struct NdfBeckmann
     float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     if(SAMPLE_VISIBLE)
     {
-      // Jakob 2014 (beckmann.h:87-115); the double/float mix follows the reference's promotions.
+      // Jakob 2014 (beckmann.h:87-115); the double/float mix follows the reference's promotions.  erff / expf / logf
+      // are the host libm's (bbmcu_libm.cuh): the Newton iteration ends in erfinv near +-1, where one differing bit of
+      // any of them moves the sampled slope by up to 1e4 ulp.
       f3 vs = normalize(make_f3(view.x*ax, view.y*ay, view.z));
       float tanT = tanTheta(vs);
-      float maxval = erff(1.0f / tanT);
+      float maxval = glibc_erff(1.0f / tanT);
       float x0 = clampf(xi.x, 1e-5f, (float)(1.0 - 10e-6));
       float x1 = clampf(xi.y, 1e-5f, (float)(1.0 - 10e-6));
-      float x = maxval - (maxval + 1.0f) * erff(sqrtf(-logf(x0)));
-      float gauss = kInvSqrtPi * tanT * expf(-(vs.z*vs.z));
+      float x = maxval - (maxval + 1.0f) * glibc_erff(sqrtf(-glibc_logf(x0)));
+      float gauss = kInvSqrtPi * tanT * glibc_expf(-(vs.z*vs.z));
       x0 = (float)((double)x0 * (1.0 + (double)maxval + (double)gauss));
 #pragma unroll
       for(int i=0; i < 3; ++i)
       {
         float slope = (float)erfinv_ref(x);
-        float g = kInvSqrtPi * tanT * expf(-slope*slope);
+        float g = kInvSqrtPi * tanT * glibc_expf(-slope*slope);
         float value = (float)(1.0 + (double)x + (double)g - (double)x0);
         float deriv = (float)(1.0 - (double)(slope*tanT));
         x -= value / deriv;

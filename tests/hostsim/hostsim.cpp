@@ -75,8 +75,11 @@ size_t hostsim_libm_mismatches(int which, const float* a, const float* b, size_t
   for(size_t i=0; i < n; ++i)
   {
     float both_s, both_c; glibc_sincosf_both(a[i], both_s, both_c);     // which 3 / 4: the shared-reduction variant
-    float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : which == 2 ? glibc_cosf(a[i]) : which == 3 ? both_s : both_c;
-    float ref = which == 0 ? atan2f(a[i], b[i]) : (which == 1 || which == 3) ? sinf(a[i]) : cosf(a[i]);
+    float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : which == 2 ? glibc_cosf(a[i]) : which == 3 ? both_s : which == 4 ? both_c
+               : which == 5 ? glibc_expf(a[i]) : which == 6 ? glibc_logf(a[i]) : glibc_erff(a[i]);
+    float ref = which == 0 ? atan2f(a[i], b[i]) : (which == 1 || which == 3) ? sinf(a[i]) : (which == 2 || which == 4) ? cosf(a[i])
+              : which == 5 ? expf(a[i]) : which == 6 ? logf(a[i]) : erff(a[i]);
+    if(mine != mine && ref != ref) continue;
     uint32_t u, v; std::memcpy(&u, &mine, 4); std::memcpy(&v, &ref, 4);
     bad += (u != v);
   }

@@ -18,6 +18,13 @@ def test_glibc_trig_ports_match_host_libm(hostsim):
     assert hostsim.libm_mismatches(2, a) == 0
     assert hostsim.libm_mismatches(3, a) == 0          # glibc_sincosf_both (shared reduction, signs applied last)
     assert hostsim.libm_mismatches(4, a) == 0
+    e = (rng.random(n, dtype=np.float32) * 2 - 1) * np.float32(100.0)
+    e[::2] *= rng.random(n // 2, dtype=np.float32)
+    assert hostsim.libm_mismatches(5, e) == 0                          # glibc_expf (the host's FMA multiarch variant)
+    l = rng.random(n, dtype=np.float32) * np.float32(10.0)
+    l[::3] = np.float32(1.0) + (rng.random(len(l[::3]), dtype=np.float32) - np.float32(0.5)) * np.float32(1e-3)
+    assert hostsim.libm_mismatches(6, l) == 0                          # glibc_logf
+    assert hostsim.libm_mismatches(7, a) == 0                          # glibc_erff (a spans [-7, 7])
     z = np.float32(2 * np.pi) * rng.random(n, dtype=np.float32)       # the sampler's phi range
     assert hostsim.libm_mismatches(3, z) == 0 and hostsim.libm_mismatches(4, z) == 0
 

@@ -12,7 +12,10 @@ using namespace bbmcu;
 #ifndef MINB
 #define MINB 1
 #endif
-using GGXM = ModelOf<M_GGX>::type;
+#ifndef MODEL
+#define MODEL M_GGX
+#endif
+using GGXM = ModelOf<MODEL>::type;
 using Op = SampleEvalPdfOp<BsdfSingle<GGXM>>;
 __global__ void __launch_bounds__(BLOCK, MINB) k_var(const Op op, size_t groups)
 {
@@ -35,7 +38,7 @@ int main(int argc, char** argv)
   cudaMalloc(&out, 3*n*4); cudaMalloc(&xi, 2*n*4); cudaMalloc(&dir, 3*n*4); cudaMalloc(&sp, n*4); cudaMalloc(&rgb, 3*n*4); cudaMalloc(&pdf, n*4); cudaMalloc(&flag, n*4);
   k_init<<<1184, 256>>>(out, xi, n);
   Op op; memset(&op.bsdf, 0, sizeof(op.bsdf));
-  op.bsdf.n_lobes = 1; op.bsdf.model[0] = M_GGX; float a[5] = {0.5f, 0.5f, 0.5f, 0.1f, 1.3f}; memcpy(op.bsdf.attrs, a, sizeof(a)); op.bsdf.n_floats = 5;
+  op.bsdf.n_lobes = 1; op.bsdf.model[0] = MODEL; float a[5] = {0.5f, 0.5f, 0.5f, 0.1f, 1.3f}; memcpy(op.bsdf.attrs, a, sizeof(a)); op.bsdf.n_floats = 5;
   op.component = 3; op.out = out; op.xi = xi; op.dir = dir; op.spdf = sp; op.flag = flag; op.rgb = rgb; op.pdf = pdf; op.n = n; op.aligned = true;
   size_t groups = n / kVec;
   unsigned grid = (unsigned)std::min<size_t>((groups + BLOCK - 1) / BLOCK, (size_t)148 * blocks_per_sm);
