@@ -340,6 +340,48 @@ class Loss:
         _check(lib().bbmcu_loss_eval(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(params.shape[0]), None, None,
                                      _ptr(device_out)), self.ctx._h)
 
+    # ---- multi-GPU combine over NVLink peer memory (bbmcu_loss_peer_*): after connect_peers every call of this loss is a
+    # collective over the shards and returns the sum over them - no NCCL call, bit-identical on every rank
+    def peer_init(self, rank, world, max_values):
+        """allocate this shard's exchange window for batches of up to max_values = K*(1+P) doubles;
+        returns (64-byte cudaIpc handle for other processes, device address for contexts of this process)"""
+        h = (C.c_ubyte * 64)()
+        w = C.c_void_p()
+        _check(lib().bbmcu_loss_peer_init(self._h, C.c_int(rank), C.c_int(world), C.c_size_t(max_values), h, C.byref(w)), self.ctx._h)
+        return bytes(h), int(w.value)
+
+    def peer_connect(self, handles):
+        """handles: the `world` 64-byte handles in rank order (other processes' shards)"""
+        blob = b"".join(handles)
+        _check(lib().bbmcu_loss_peer_connect(self._h, C.c_char_p(blob)), self.ctx._h)
+
+    def peer_connect_ptrs(self, windows):
+        """windows: the `world` device addresses in rank order (shards living in this process)"""
+        arr = (C.c_void_p * len(windows))(*[C.c_void_p(int(w)) for w in windows])
+        _check(lib().bbmcu_loss_peer_connect_ptrs(self._h, arr), self.ctx._h)
+
+    def connect_peers(self, max_values, group=None):
+        """one process per GPU under torch.distributed: exchange the window handles and connect.  Collective: every rank
+        runs the same sequence of gathers whatever fails locally, and all ranks raise if any of them could not connect."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        err, h = None, b""
+        try:
+            h, _ = self.peer_init(rank, world, max_values)
+        except BbmError as e:
+            err = e
+        handles = [None] * world
+        dist.all_gather_object(handles, h, group=group)
+        if err is None and all(len(x) == 64 for x in handles):
+            try:
+                self.peer_connect(handles)
+            except BbmError as e:
+                err = e
+        oks = [None] * world
+        dist.all_gather_object(oks, err is None, group=group)
+        if not all(oks):
+            raise err if err is not None else BbmError("a peer rank could not map the exchange windows")
+
     def terms(self, bsdf, count):
         t = np.empty(count, np.float32)
         _check(lib().bbmcu_loss_terms(self._h, bsdf._h, _ptr(t)), self.ctx._h)

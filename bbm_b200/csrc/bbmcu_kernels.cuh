@@ -67,6 +67,7 @@ template<class B> struct EvalOp
 
 template<class B> struct PdfOp
 {
+  static constexpr bool kOneWaveWithTables = true;            // cheap body: pay the CDF prologue once per SM slot (bbmcu_launch.cuh)
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned;
@@ -95,6 +96,7 @@ template<class B> struct ReflectanceOp
 
 template<class B> struct SampleOp
 {
+  static constexpr bool kOneWaveWithTables = true;
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned;
@@ -110,6 +112,7 @@ template<class B> struct SampleOp
 // s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)   (20 B in, 36 B out per element)
 template<class B> struct SampleEvalPdfOp
 {
+  static constexpr bool kOneWaveWithTables = false;           // dominated by the model's eval, whose cost varies per element: keep many blocks for balance
   static constexpr int kBlock = B::kHandFused ? 512 : 256, kMinBlocks = B::kHandFused ? 2 : 1;     // launch shape (see Microfacet::kHandFusedEvalPdf)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned;

@@ -15,7 +15,27 @@ template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stre
   if(n == 0) return;
   size_t groups = (n + kVec - 1) / kVec;
   bind_device_tables();
-  k_foreach4<Op><<<grid_for(ctx, groups, Op::kBlock, 8*256/Op::kBlock), Op::kBlock, 0, stream>>>(op, groups);
+  unsigned grid = grid_for(ctx, groups, Op::kBlock, 8*256/Op::kBlock);
+  if constexpr (Op::kHasBsdf)
+  {
+    if constexpr (Op::kTables)
+    {
+      if(Op::kOneWaveWithTables && op.bsdf.n_tables)
+      {
+        // every block rebuilds the 90-bin sampling CDF in its prologue (90 back-scatter evaluations of the model): launch
+        // one resident wave and let it stride over the batch, so the prologue is paid once per SM slot
+        static int per_sm = 0;                                     // per operator instantiation
+        if(per_sm == 0)
+        {
+          BBMCU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_foreach4<Op>, Op::kBlock, 0));
+          if(per_sm < 1) per_sm = 1;
+        }
+        const unsigned wave = (unsigned)ctx->sm_count * (unsigned)per_sm;
+        if(grid > wave) grid = wave;
+      }
+    }
+  }
+  k_foreach4<Op><<<grid, Op::kBlock, 0, stream>>>(op, groups);
   BBMCU_CUDA(cudaGetLastError());
   ++ctx->launches;
 }

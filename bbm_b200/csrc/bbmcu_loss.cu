@@ -1,12 +1,31 @@
 // Loss objects of the C ABI (include/bbmcu.h): the six metrics over the MERL or spherical linearizer,
 // batched over K parameter sets, with the analytic parameter gradient.
 // Mirrors include/bbm/sampledlossfunction.h:26-95 and the thin metric classes of include/loss/*.h.
+#include <cstring>
 #include <memory>
 
 #include "bbmcu_launch.cuh"
 #include "bbmcu_losskernel.cuh"
 
 using namespace bbmcu;
+
+// ---- exchange window of one shard (device memory, cudaIpc-exported) ------------------------------------------------------
+//   [0, 256)   uint64 flags[2][kMaxPeers]: flags[parity][r] = sequence number of the last batch rank r has delivered
+//   [256, ...) double rows[2][world][cap]: rows[parity][r] = rank r's K x (1+P) totals of the batch with that parity
+// Two parities are enough: rank r can only deliver batch s+2 after it has seen everybody's flag of batch s+1, which a
+// peer raises after its own exchange kernel of batch s has finished reading (kernels of one shard run in stream order).
+constexpr int kMaxPeers = 16;
+constexpr size_t kPeerFlagBytes = 2 * kMaxPeers * sizeof(unsigned long long);
+struct PeerArgs
+{
+  int rank, world;
+  unsigned long long seq;
+  size_t cap;
+  unsigned char* win[kMaxPeers];
+  double* local;
+  unsigned int* counter;
+  unsigned int* status;
+};
 
 namespace bbmcu { SphericalGrid to_device_grid(const bbmcu_spherical_grid& g); }
 
@@ -31,8 +50,22 @@ struct bbmcu_loss
   double* d_result = nullptr;  size_t result_cap = 0;
   double* h_result = nullptr;  size_t h_result_cap = 0;  // pinned
   uint32_t* d_bad = nullptr;
+  // exchange over peer memory (bbmcu_loss_peer_*): this shard's window, the peers' windows mapped into this process
+  int peer_rank = 0, peer_world = 1;
+  bool peer_connected = false;
+  size_t peer_cap = 0;                                   // doubles per (parity, rank) row
+  unsigned char* peer_win[kMaxPeers] = {};               // [rank] = that shard's window; own entry = own allocation
+  bool peer_ipc[kMaxPeers] = {};                         // opened with cudaIpcOpenMemHandle (to be closed)
+  double* d_local = nullptr; size_t local_cap = 0;       // this shard's totals before the exchange
+  unsigned int* d_counter = nullptr;
+  unsigned int* h_peer_status = nullptr;                 // pinned, mapped: 1 = a peer did not arrive
+  unsigned long long peer_seq = 0;
   ~bbmcu_loss()
   {
+    for(int r=0; r < kMaxPeers; ++r) if(peer_ipc[r] && peer_win[r]) cudaIpcCloseMemHandle(peer_win[r]);
+    if(peer_win[peer_rank]) cudaFree(peer_win[peer_rank]);
+    cudaFree(d_local); cudaFree(d_counter);
+    if(h_peer_status) cudaFreeHost(h_peer_status);
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
     for(int i=0; i < 2; ++i) { if(h_attrs[i]) cudaFreeHost(h_attrs[i]); if(h_attrs_free[i]) cudaEventDestroy(h_attrs_free[i]); }
     if(h_result) cudaFreeHost(h_result);
@@ -97,6 +130,75 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_finish(const double* pa
     __syncthreads();
   }
   if(threadIdx.x == 0) result[(size_t)k*cols + j] = s[0] * inv_n;
+}
+
+// ---- the same finish, fused with the exchange over peer memory ----------------------------------------------------------
+__device__ __forceinline__ unsigned long long* peer_flags(unsigned char* win, int parity) { return reinterpret_cast<unsigned long long*>(win) + parity*kMaxPeers; }
+__device__ __forceinline__ double* peer_row(unsigned char* win, int parity, int world, size_t cap, int r) { return reinterpret_cast<double*>(win + kPeerFlagBytes) + ((size_t)parity*world + r)*cap; }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+
+// Every block finishes one (k, column) total of this shard as k_loss_finish does; the block that finishes last then
+//   1. stores the shard's rows into the window of every peer (remote stores over NVLink; its own window included),
+//   2. raises flag[parity][rank] = seq in every window (release, system scope),
+//   3. waits until the `world` flags of its own window carry seq (acquire; bounded: ~10 s, then status = 1 and NaN results),
+//   4. adds the rows in rank order - the same order on every shard, so all of them return identical bits.
+__global__ void __launch_bounds__(kFinishThreads) k_loss_finish_exchange(const double* partial, int blocks_x, int cols, double inv_n, double* result, const PeerArgs pa)
+{
+  __shared__ double s[kFinishThreads];
+  __shared__ int s_last, s_timeout;
+  const int k = blockIdx.x, j = blockIdx.y, tid = threadIdx.x;
+  const double* p = partial + ((size_t)k*cols + j)*blocks_x;
+  double v = 0.0;
+  for(int b = tid; b < blocks_x; b += kFinishThreads) v += p[b];
+  s[tid] = v;
+  __syncthreads();
+  for(int o = kFinishThreads/2; o > 0; o >>= 1)
+  {
+    if(tid < o) s[tid] += s[tid + o];
+    __syncthreads();
+  }
+  const unsigned int nvals = gridDim.x * gridDim.y;
+  if(tid == 0)
+  {
+    pa.local[(size_t)k*cols + j] = s[0] * inv_n;
+    __threadfence();
+    s_last = (atomicAdd(pa.counter, 1u) == nvals - 1u) ? 1 : 0;
+    s_timeout = 0;
+  }
+  __syncthreads();
+  if(!s_last) return;
+  __threadfence();
+  const int parity = (int)(pa.seq & 1ull);
+  for(int q = 0; q < pa.world; ++q)
+  {
+    double* dst = peer_row(pa.win[q], parity, pa.world, pa.cap, pa.rank);
+    for(unsigned int i = tid; i < nvals; i += kFinishThreads) dst[i] = __ldcg(pa.local + i);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if(tid < pa.world)
+  {
+    st_release_sys(peer_flags(pa.win[tid], parity) + pa.rank, pa.seq);
+    const unsigned long long* mine = peer_flags(pa.win[pa.rank], parity) + tid;
+    const unsigned long long t0 = global_ns();
+    while(ld_acquire_sys(mine) < pa.seq)
+    {
+      __nanosleep(200);
+      if(global_ns() - t0 > 10000000000ull) { s_timeout = 1; break; }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const bool bad = s_timeout != 0;
+  for(unsigned int i = tid; i < nvals; i += kFinishThreads)
+  {
+    double sum = 0.0;
+    for(int r = 0; r < pa.world; ++r) sum += __ldcv(peer_row(pa.win[pa.rank], parity, pa.world, pa.cap, r) + i);
+    result[i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+  }
+  if(tid == 0) { *pa.counter = 0u; if(bad) *pa.status = 1u; }
 }
 
 // per-sample terms l(idx) (sampledlossfunction::operator()(idx))
@@ -200,6 +302,7 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     if(!L || !bsdf) throw std::invalid_argument("BBM: null argument");
     if(K == 0) return;
     if(!params && K != 1) throw std::invalid_argument("BBM: params == NULL requires K == 1");
+    if(L->h_peer_status && *(volatile unsigned int*)L->h_peer_status) throw std::runtime_error("BBM: a peer shard did not arrive at an earlier loss exchange within 10 s");
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     const int P = bsdf->b.param_count(BBMCU_ATTR_ALL);
     if(P > kMaxParams) throw std::invalid_argument("BBM: more than " + std::to_string(kMaxParams) + " fit parameters");
@@ -267,7 +370,19 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     }
     else BBMCU_CUDA(cudaMemsetAsync(L->d_partial, 0, K*(size_t)bx*cols*sizeof(double), ctx->stream));
     double* result = device_out ? device_out : L->d_result;
-    k_loss_finish<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
+    if(L->peer_connected && L->peer_world > 1)
+    {
+      if(K*(size_t)cols > L->peer_cap) throw std::invalid_argument("BBM: K*(1+P) = " + std::to_string(K*(size_t)cols) + " exceeds the peer window (" + std::to_string(L->peer_cap) + " values)");
+      grow(L->d_local, L->local_cap, K*(size_t)cols);
+      PeerArgs pa{};
+      pa.rank = L->peer_rank; pa.world = L->peer_world; pa.seq = ++L->peer_seq; pa.cap = L->peer_cap;
+      for(int r=0; r < L->peer_world; ++r) pa.win[r] = L->peer_win[r];
+      pa.local = L->d_local; pa.counter = L->d_counter;
+      BBMCU_CUDA(cudaHostGetDevicePointer((void**)&pa.status, L->h_peer_status, 0));
+      k_loss_finish_exchange<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result, pa);
+    }
+    else
+      k_loss_finish<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
     BBMCU_CUDA(cudaGetLastError());
     ++ctx->launches;
     if(device_out) return;                       // caller all-reduces / reads it on the stream
@@ -279,11 +394,88 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     }
     BBMCU_CUDA(cudaMemcpyAsync(L->h_result, L->d_result, K*(size_t)cols*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if(L->h_peer_status && *(volatile unsigned int*)L->h_peer_status) throw std::runtime_error("BBM: a peer shard did not arrive at the loss exchange within 10 s");
     for(size_t k=0; k < K; ++k)
     {
       if(loss_out) loss_out[k] = L->h_result[k*cols];
       if(grad_out) for(int j=0; j < P; ++j) grad_out[k*P + j] = L->h_result[k*cols + 1 + j];
     }
+  });
+}
+
+int bbmcu_loss_peer_init(bbmcu_loss* L, int rank, int world, size_t max_values, unsigned char handle_out[64], void** window_out)
+{
+  bbmcu_ctx* ctx = L ? L->ctx : nullptr;
+  return guarded(ctx, [&] {
+    if(!L) throw std::invalid_argument("BBM: null argument");
+    if(world < 1 || world > kMaxPeers || rank < 0 || rank >= world) throw std::invalid_argument("BBM: peer rank/world out of range (at most " + std::to_string(kMaxPeers) + " shards)");
+    if(max_values == 0) throw std::invalid_argument("BBM: max_values == 0");
+    if(L->peer_win[L->peer_rank]) throw std::invalid_argument("BBM: the loss already has a peer window");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = kPeerFlagBytes + 2*(size_t)world*max_values*sizeof(double);
+    unsigned char* win = nullptr;
+    BBMCU_CUDA(cudaMalloc(&win, bytes));
+    BBMCU_CUDA(cudaMemset(win, 0, bytes));
+    BBMCU_CUDA(cudaMalloc(&L->d_counter, sizeof(unsigned int)));
+    BBMCU_CUDA(cudaMemset(L->d_counter, 0, sizeof(unsigned int)));
+    BBMCU_CUDA(cudaHostAlloc((void**)&L->h_peer_status, sizeof(unsigned int), cudaHostAllocMapped));
+    *L->h_peer_status = 0u;
+    BBMCU_CUDA(cudaDeviceSynchronize());
+    L->peer_rank = rank; L->peer_world = world; L->peer_cap = max_values; L->peer_win[rank] = win; L->peer_seq = 0;
+    if(handle_out)
+    {
+      cudaIpcMemHandle_t h;
+      BBMCU_CUDA(cudaIpcGetMemHandle(&h, win));
+      std::memcpy(handle_out, &h, 64);
+    }
+    if(window_out) *window_out = win;
+  });
+}
+
+int bbmcu_loss_peer_connect(bbmcu_loss* L, const unsigned char* handles)
+{
+  bbmcu_ctx* ctx = L ? L->ctx : nullptr;
+  return guarded(ctx, [&] {
+    if(!L || !handles) throw std::invalid_argument("BBM: null argument");
+    if(!L->peer_win[L->peer_rank]) throw std::invalid_argument("BBM: bbmcu_loss_peer_init first");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    for(int r=0; r < L->peer_world; ++r)
+    {
+      if(r == L->peer_rank) continue;
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, handles + 64*(size_t)r, 64);
+      void* p = nullptr;
+      BBMCU_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      L->peer_win[r] = static_cast<unsigned char*>(p); L->peer_ipc[r] = true;
+    }
+    L->peer_connected = true;
+  });
+}
+
+int bbmcu_loss_peer_connect_ptrs(bbmcu_loss* L, void* const* windows)
+{
+  bbmcu_ctx* ctx = L ? L->ctx : nullptr;
+  return guarded(ctx, [&] {
+    if(!L || !windows) throw std::invalid_argument("BBM: null argument");
+    if(!L->peer_win[L->peer_rank]) throw std::invalid_argument("BBM: bbmcu_loss_peer_init first");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    for(int r=0; r < L->peer_world; ++r)
+    {
+      if(r == L->peer_rank) continue;
+      if(!windows[r]) throw std::invalid_argument("BBM: null peer window");
+      cudaPointerAttributes at{};
+      BBMCU_CUDA(cudaPointerGetAttributes(&at, windows[r]));
+      if(at.type != cudaMemoryTypeDevice) throw std::invalid_argument("BBM: a peer window is not device memory");
+      if(at.device != ctx->device)
+      {
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if(e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else BBMCU_CUDA(e);
+      }
+      L->peer_win[r] = static_cast<unsigned char*>(windows[r]);
+    }
+    L->peer_connected = true;
   });
 }
 

@@ -9,6 +9,7 @@
 // deterministic and independent of scheduling (totals are judged against a double accumulation
 // of the per-sample terms).
 #pragma once
+#include <cstdlib>
 #include "bbmcu_ctx.hpp"
 #include "bbmcu_lossop.cuh"
 #include "bbmcu_tables.cuh"
@@ -166,7 +167,8 @@ inline void loss_tile_shape(size_t n, size_t K, int n_attrs, int sm_count, unsig
   if(tiles < 1) tiles = 1;
   const size_t smem_k = (size_t)(40*1024) / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the static shared-memory budget
   size_t split_fit = (K + smem_k - 1) / (smem_k ? smem_k : 1);
-  size_t split_fill = ((size_t)sm_count*16 + tiles - 1) / tiles;                        // ~16 blocks per SM over the launch
+  static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 16; }();
+  size_t split_fill = ((size_t)sm_count*fill + tiles - 1) / tiles;                      // ~16 blocks per SM over the launch (tuning override: BBMCU_LOSS_BLOCKS_PER_SM)
   size_t sp = split_fit > split_fill ? split_fit : split_fill;
   if(sp > K) sp = K;
   if(sp < 1) sp = 1;

@@ -260,42 +260,50 @@ struct NdfGGX
     // (*_nr / *_raw: IEEE results through the math library's own fast path, see bbmcu_math.cuh.  Ranges: the stretched
     // view is range-tested once in normalize_nr; vs.x^2 + vs.y^2 is in (1.19e-7, 1] inside the branch; hi is in [1, 2],
     // a in [0.5, 1]; xi0 in [0, 1] needs the lower test only)
+    // Branch-free: both cases of the reference's two select() calls run through ONE float-pair evaluation (a warp holds
+    // both cases almost always, so a branch would execute both sides anyway), and the unguarded *_raw results of
+    // out-of-range operands are selected away.
     f3 vs = normalize_nr(make_f3(view.x*ax, view.y*ay, view.z));
-    f3 T1 = make_f3(1, 0, 0);
-    if(vs.z < 0.99999988079071044921875f) { float rr = ieee_rcp_raw(ieee_sqrt_raw(vs.y*vs.y + vs.x*vs.x)); T1 = make_f3(vs.y*rr, (-vs.x)*rr, 0.0f); }
-    f3 T2 = make_f3(T1.y*vs.z, -(T1.x*vs.z), T1.x*vs.y - T1.y*vs.x);
-    float hi = 1.0f + vs.z, lo = vs.z - (hi - 1.0f);
-    float r0 = ieee_rcp_raw(hi);
-    float aa = fmaf(r0, fmaf(-lo, r0, fmaf(-hi, r0, 1.0f)), r0);
-    float r = (xi.x > 1e-30f) ? ieee_sqrt_raw(xi.x) : sqrtf(xi.x);
-    bool lower = xi.y < aa;
-    float phi;
-    if(lower) phi = ieee_div_raw(xi.y, aa) * kPi;
-    else
-    {
-      // (float)((1.0 + (double)(xi1 - a) / (1.0 - (double)a)) * pi) in float-float arithmetic: numerator and
-      // denominator are exact floats, the quotient, 1 + q and the product are carried as hi + lo pairs (~2^-46) and
-      // rounded once.  Differs from the double evaluation only where the double path itself rounds twice across a float
-      // tie (1.6e-5 of a grazing-biased test set, ~1e-7 of uniform inputs; one ulp of phi each).
-      float num = xi.y - aa, den = 1.0f - aa;
-      float qh = ieee_div_raw(num, den);
-      float ql = q_div(fmaf(-qh, den, num), den);
-      float sh = 1.0f + qh, sl = ((1.0f - sh) + qh) + ql;
-      float ph = sh * kPi;
-      phi = ph + fmaf(sl, kPi, fmaf(sh, kPi, -ph));
-    }
+    const bool tilted = vs.z < 0.99999988079071044921875f;
+    const float rr = ieee_rcp_raw(ieee_sqrt_raw(vs.y*vs.y + vs.x*vs.x));          // garbage for vs = +z: not selected
+    const f3 T1 = make_f3(tilted ? vs.y*rr : 1.0f, tilted ? (-vs.x)*rr : 0.0f, 0.0f);
+    const f3 T2 = make_f3(T1.y*vs.z, -(T1.x*vs.z), T1.x*vs.y - T1.y*vs.x);
+    const float hi = 1.0f + vs.z, lo = vs.z - (hi - 1.0f);
+    const float r0 = ieee_rcp_raw(hi);
+    const float aa = fmaf(r0, fmaf(-lo, r0, fmaf(-hi, r0, 1.0f)), r0);
+    // sqrt(xi0); below 1e-30 the root (< 1e-15) is taken as 0: it moves the normal by less than 1e-15
+    const float r = sel_gt(xi.x, 1e-30f, ieee_sqrt_raw(xi.x));
+    const bool lower = xi.y < aa;
+    // phi = (float)((double)(xi1 / a) * pi)  or  (float)((1.0 + (double)(xi1 - a) / (1.0 - (double)a)) * pi):
+    // quotient, 1 + q and the product are carried as hi + lo pairs (~2^-46) and rounded once.  In the first case the pair
+    // is (xi1 / a, 0) and the last line returns the correctly rounded float product, i.e. the reference's value exactly.
+    // The second differs from the double evaluation only where the double path itself rounds twice across a float tie
+    // (1.6e-5 of a grazing-biased test set, ~1e-7 of uniform inputs; one ulp of phi each).
+    const float num = lower ? xi.y : xi.y - aa, den = lower ? aa : 1.0f - aa, base = lower ? 0.0f : 1.0f;
+    const float qh = ieee_div_raw(num, den);
+    const float ql = lower ? 0.0f : q_div(fmaf(-qh, den, num), den);
+    const float sh = base + qh, sl = ((base - sh) + qh) + ql;
+    const float ph = sh * kPi;
+    const float phi = ph + fmaf(sl, kPi, fmaf(sh, kPi, -ph));
     float cp, sp; glibc_sincosf_both(phi, sp, cp);
-    float P1 = r*cp;
-    float P2;
-    if(lower) P2 = r*sp;
-    else
-    {
-      // (float)((double)vs.z * r * sp): the same product as hi + lo pairs, rounded once (2e-8 tie cases)
-      float hi2 = vs.z * r, lo2 = fmaf(vs.z, r, -hi2);
-      float t = hi2 * sp;
-      P2 = t + fmaf(lo2, sp, fmaf(hi2, sp, -t));
-    }
-    float w = (float)safe_sqrt_d(1.0 - (double)(P1*P1) - (double)(P2*P2));
+    const float P1 = r*cp;
+    // P2 = (float)(1.0 * r * sp)  or  (float)((double)vs.z * r * sp): the same product as a pair, rounded once
+    const float zz = lower ? 1.0f : vs.z;
+    const float hi2 = zz * r, lo2 = fmaf(zz, r, -hi2);
+    const float t2 = hi2 * sp;
+    const float P2 = t2 + fmaf(lo2, sp, fmaf(hi2, sp, -t2));
+    // (float)sqrt(max(1.0 - (double)(P1*P1) - (double)(P2*P2), 0)): both squares are float products, the differences are
+    // exact in double; here 1 - p1 - p2 is carried as a float pair (Fast2Sum twice: 1 >= p1, and 1 - p1 >= p2/2), the root
+    // is the IEEE float root of the high part plus one Newton correction with the exact residual, rounded once (differs
+    // from the double evaluation only within 2^-22 ulp of a rounding tie: ~1e-7 of samples, by one ulp of w).  Below
+    // 1e-30 the root is taken as 0.
+    const float p1 = P1*P1, p2 = P2*P2;
+    const float t = 1.0f - p1, e1 = (1.0f - t) - p1;
+    const float u = t - p2, e2 = (t - u) - p2;
+    const float lo_s = e1 + e2;
+    const float s_hi = u + lo_s, s_lo = lo_s - (s_hi - u);
+    const float q = ieee_sqrt_raw(s_hi);
+    const float w = sel_gt(s_hi, 1e-30f, fmaf(fmaf(-q, q, s_hi) + s_lo, 0.5f * q_rcp(q), q));
     f3 n = (T1*P1 + T2*P2) + vs*w;
     return q_normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
   }
@@ -645,11 +653,11 @@ struct Microfacet
       f3 h = q_normalize(in + out);
       const float inh = q_dot(in, h), outh = q_dot(out, h);
       const float den = fmaf(al2, h.z*h.z, fmaf(h.x, h.x, h.y*h.y));
-      const float Dv = (h.z > 0.0f) ? al2 * q_rcp(kPi * den * den) : 0.0f;
-      const float gi = (inh > 0.0f) ? 2.0f*in.z * q_rcp(in.z + q_sqrt(fmaf(al2, sinTheta2(in), in.z*in.z))) : 0.0f;
-      const float go = (outh > 0.0f) ? 2.0f*out.z * q_rcp(out.z + q_sqrt(fmaf(al2, sinTheta2(out), out.z*out.z))) : 0.0f;
+      const float Dv = sel_gt(h.z, 0.0f, al2 * q_rcp(kPi * den * den));
+      const float gi = sel_gt(inh, 0.0f, 2.0f*in.z * q_rcp(in.z + q_sqrt(fmaf(al2, sinTheta2(in), in.z*in.z))));
+      const float go = sel_gt(outh, 0.0f, 2.0f*out.z * q_rcp(out.z + q_sqrt(fmaf(al2, sinTheta2(out), out.z*out.z))));
       const float c = 0.5f*(inh + outh);
-      const float g = m_safe_sqrt(eta*eta + c*c - 1.0f);
+      const float g = q_sqrt(max0(eta*eta + c*c - 1.0f));
       const float A = g - c, B = g + c, n2 = fmaf(c, B, -1.0f), d2 = fmaf(c, A, 1.0f);
       const float R = q_rcp(B * d2);
       const float fa = A*d2*R, fb = n2*B*R;

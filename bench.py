@@ -267,7 +267,7 @@ def main():
         res = torch.zeros((LOSS_K, 1 + P), device=dev, dtype=torch.float64)
         ev, ev_back = torch.cuda.Event(), torch.cuda.Event()
 
-        def loss_step():
+        def step_nccl():
             L.eval_device(fitted, params, res)                       # on the library's stream
             if world > 1:
                 ev.record(stream)
@@ -276,23 +276,50 @@ def main():
                 ev_back.record(torch.cuda.current_stream())
                 stream.wait_event(ev_back)                           # ... and the next step's kernels after the all-reduce
 
-        for _ in range(3):
-            loss_step()
-        barrier()
-        l0 = ctx.launches
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        t0 = time.perf_counter()
+        # N > 1: the finish kernel fused with the exchange over NVLink peer memory (bbmcu_loss_peer_*) is the product path;
+        # the NCCL all-reduce of the same rows is timed beside it.  Falls back to NCCL if the windows cannot be mapped.
+        L_peer, peer_error = None, None
+        if world > 1:
+            try:
+                L_peer = ctx.loss("nganL2", truth, None, first=first, count=count)
+                L_peer.connect_peers(LOSS_K * (1 + P))
+            except Exception as e:                                   # noqa: BLE001 - reported in the JSON line
+                L_peer, peer_error = None, str(e)[:200]
+            ok = torch.tensor([1 if L_peer is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                L_peer, peer_error = None, peer_error or "a peer rank could not map the windows"
+
+        def step_peer():
+            L_peer.eval_device(fitted, params, res)                  # collective inside the library's own kernel
+
         nl = max(5, args.steps)
-        for _ in range(nl):
-            loss_step()
-        f1.record(stream)
-        ctx.synchronize()
-        torch.cuda.synchronize()
-        wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        kern_ms = max_over_ranks(f0.elapsed_time(f1))
-        step_ms = max(wall_ms, kern_ms) / nl if world > 1 else kern_ms / nl
+
+        def time_loss(step):
+            for _ in range(3):
+                step()
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            t0 = time.perf_counter()
+            for _ in range(nl):
+                step()
+            f1.record(stream)
+            ctx.synchronize()
+            torch.cuda.synchronize()
+            wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            kern_ms = max_over_ranks(f0.elapsed_time(f1))
+            return (max(wall_ms, kern_ms) if world > 1 else kern_ms) / nl
+
+        nccl_ms = time_loss(step_nccl) if world > 1 else None
+        loss0_nccl = float(res[0, 0].item()) if world > 1 else None
+        l0 = ctx.launches
+        step_ms = time_loss(step_peer if L_peer is not None else step_nccl)
+        launches_loss = (ctx.launches - l0) * nl // (nl + 3)
         passes = LOSS_K / (step_ms * 1e-3)
+        loss0 = float(res[0, 0].item())
+        if world > 1 and L_peer is not None:
+            assert abs(loss0 - loss0_nccl) <= 1e-12 * abs(loss0_nccl), (loss0, loss0_nccl)
         by_k = {}
         for kk in (1, 16):
             pk = params[:kk]
@@ -307,10 +334,17 @@ def main():
             h1.record(stream)
             ctx.synchronize()
             by_k[str(kk)] = kk / (max_over_ranks(h0.elapsed_time(h1)) / 20 * 1e-3)       # this rank's shard only, no collective
+        if world == 1:
+            collective = None
+        elif L_peer is not None:
+            collective = "rows exchanged over NVLink peer memory inside the finish kernel (no NCCL call); K x (1+P) doubles per rank"
+        else:
+            collective = "nccl all_reduce of K x (1+P) doubles (peer windows unavailable: %s)" % peer_error
         loss_info = {"value": passes, "passes_per_s_by_K_no_collective": by_k, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
-                     "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": "nccl all_reduce of K x (1+P) doubles" if world > 1 else None,
+                     "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": collective,
+                     "passes_per_s_with_nccl_all_reduce": (LOSS_K / (nccl_ms * 1e-3)) if nccl_ms else None,
                      "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / peak,
-                     "gpu_launches": ctx.launches - l0, "loss0": float(res[0, 0].item())}
+                     "gpu_launches": launches_loss, "loss0": loss0}
 
     # ---- extra (BASELINE configs[0], GPU side): Cook-Torrance eval over the MERL-grid directions ---------------------
     # materialised SoA directions, 24 B in + 12 B out = 36 B/eval; the 1 458 000 grid directions are tiled 32x so the

@@ -144,11 +144,31 @@ BBMCU_API uint64_t bbmcu_loss_samples(const bbmcu_loss* loss);      /* N of the 
  * params: K x P row-major, P = bbmcu_bsdf_param_count(bsdf, BBMCU_ATTR_ALL), forward enumeration order;
  * params == NULL with K == 1 evaluates the bsdf's current parameters.  loss: K doubles; grad: K x P doubles.
  * Host pointers.  device_out (may be NULL): if given, a DEVICE buffer of K*(1+P) doubles that receives
- * [loss_k, grad_k...] rows and no host copy/synchronisation is done (for the NCCL all-reduce). */
+ * [loss_k, grad_k...] rows and no host copy/synchronisation is done (for an NCCL all-reduce by the caller, or - after
+ * bbmcu_loss_peer_connect - already combined over the shards). */
 BBMCU_API int  bbmcu_loss_eval(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
                      double* loss_out, double* grad_out, double* device_out);
 /* per-sample terms l(idx) of the shard (sampledlossfunction::operator()(idx)); `terms` = count floats */
 BBMCU_API int  bbmcu_loss_terms(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, float* terms);
+
+/* ---- multi-GPU combine of the sample-axis shards over NVLink peer memory -------------------------------------------------
+ * (no reference counterpart: bbm is single-threaded; this is the exchange step of SURVEY.md section 8e.)
+ * One process (or context) per GPU of ONE node owns one shard of the same loss.  After the calls below every
+ * bbmcu_loss_eval of that loss is a COLLECTIVE over the `world` shards - all of them must call it with the same bsdf shape
+ * and K, in the same order - and returns the sum over the shards (= the reference's mean): the kernel that finishes a
+ * shard's K x (1+P) totals stores them into every peer's exchange window (plain remote stores), raises a per-peer sequence
+ * flag, waits for the `world` flags of its own window and adds the rows in rank order.  No NCCL call, no host round trip;
+ * every rank gets bit-identical results.  A peer that does not arrive within ~10 s makes the call fail (BBMCU_RUNTIME_ERROR
+ * at the next synchronising call) instead of hanging the device.
+ *   peer_init:     allocates this shard's window for batches of up to max_values = K*(1+P) doubles and returns its
+ *                  cudaIpcMemHandle (64 bytes) for the other PROCESSES, and its device address for contexts of the same
+ *                  process;
+ *   peer_connect:  handles = world x 64 bytes in rank order (own entry ignored), as exchanged by the host's launcher
+ *                  (torch.distributed all_gather, MPI, a pipe ...);
+ *   peer_connect_ptrs: the same for shards living in one process (windows[r] = peer r's device address). */
+BBMCU_API int  bbmcu_loss_peer_init(bbmcu_loss* loss, int rank, int world, size_t max_values, unsigned char handle_out[64], void** window_out);
+BBMCU_API int  bbmcu_loss_peer_connect(bbmcu_loss* loss, const unsigned char* handles);
+BBMCU_API int  bbmcu_loss_peer_connect_ptrs(bbmcu_loss* loss, void* const* windows);
 
 /* ---- .fit files (include/io/fit.h:34-77) -------------------------------------------------------------- */
 typedef struct bbmcu_fit bbmcu_fit;

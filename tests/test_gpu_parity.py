@@ -197,6 +197,43 @@ def test_loss_batched_and_sharded(ctx):
     assert np.allclose(la + lb, lk, rtol=2e-6) and np.allclose(ga + gb, gk, rtol=2e-5, atol=1e-7*np.abs(gk).max())
 
 
+def test_loss_peer_exchange_two_shards_one_device(ctx):
+    """the finish kernel fused with the exchange over peer memory (bbmcu_loss_peer_*): two shards of one loss, each on its
+    own context (stream) of this device, combine through each other's windows; both get the same bits, equal to the
+    unsharded loss, over three batches (both window parities and the first one reused)"""
+    import torch
+    import bbm_b200 as bb
+    ctx_b = bb.Context(0)
+    fitted = bb.Bsdf("Aggregate(Lambertian(), CookTorrance())")
+    truth = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), CookTorrance([0.3,0.3,0.3], 0.2, 1.5))")
+    whole = ctx.loss("nganL2", truth, None)
+    A = ctx.loss("nganL2", truth, None, first=0, count=700001)
+    B = ctx_b.loss("nganL2", truth, None, first=700001, count=1458000 - 700001)
+    rng = np.random.default_rng(9)
+    p0 = fitted.parameter_values()
+    K, cols = 5, 1 + len(p0)
+    params = p0[None] * (1 + 0.2*rng.random((K, len(p0))))
+    params[:, 7] = 1.2 + rng.random(K)
+    _, wa = A.peer_init(0, 2, 8*cols)
+    _, wb = B.peer_init(1, 2, 8*cols)
+    A.peer_connect_ptrs([wa, wb])
+    B.peer_connect_ptrs([wa, wb])
+    dev = torch.device("cuda", 0)
+    for batch in range(3):
+        p = params * (1 + 0.01*batch)
+        ra = torch.zeros((K, cols), dtype=torch.float64, device=dev)
+        rb = torch.zeros((K, cols), dtype=torch.float64, device=dev)
+        A.eval_device(fitted, p, ra)            # asynchronous: A's exchange block waits on the device for B's rows
+        B.eval_device(fitted, p, rb)
+        ctx.synchronize(); ctx_b.synchronize()
+        assert torch.equal(ra, rb)
+        lw, gw = whole(fitted, p, grad=True)
+        got = ra.cpu().numpy()
+        assert np.allclose(got[:, 0], lw, rtol=2e-6) and np.allclose(got[:, 1:], gw, rtol=2e-5, atol=1e-7*np.abs(gw).max())
+    with pytest.raises(bb.BbmInvalidArgument):
+        A.eval_device(fitted, np.repeat(params, 2, 0), torch.zeros((2*K, cols), dtype=torch.float64, device=dev))     # 10 rows > the 8-row window
+
+
 def test_loss_against_measured_table(ctx, ref, tmp_path):
     """reference operand = a MERL binary written by us and read by the unmodified reference's merl<> loader"""
     import bbm_b200 as bb

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--log2", type=int, default=24)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--once", action="store_true", help="one launch per (model, op), no warm-up: the form tools/pipe_scan.py profiles")
     a = ap.parse_args()
     import torch
     import bbm_b200 as bb
@@ -43,6 +44,10 @@ def main():
     torch.cuda.synchronize()
 
     def timed(fn):
+        if a.once:
+            fn()
+            ctx.synchronize()
+            return 1.0
         fn(); fn()
         ctx.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
