@@ -49,6 +49,7 @@ BBMCU_D void lobe_sample(int model, const float* a, f3 out, f2 xi, int component
 // ---- run-time lobe list -----------------------------------------------------------------------
 struct BsdfGeneric
 {
+  static constexpr int kMinBlocks = 1;                     // every model's code behind one switch: let it have its registers
   static constexpr bool kTables = true;
   static constexpr bool kFusedSample = false;
   static constexpr bool kHandFused = false;
@@ -134,9 +135,17 @@ template<class M, class = void> struct SamplePdfIsPdf { static constexpr bool va
 template<class M> struct SamplePdfIsPdf<M, typename std::enable_if<M::kSamplePdfIsPdf>::type> { static constexpr bool value = true; };
 
 // ---- compile-time single model (no dispatch, smallest register footprint) ------------------------
+// Resident 256-thread blocks per SM the single-model kernels are compiled for.  3 (<= 80 registers) measured best or
+// within 2 % of best for every model whose kernels were swept (tools/microbench: Bagher eval 5.8 -> 9.7 G/s, Low
+// microfacet sample 21 -> 38, Phong / Lafortune / Ribardiere sample + fused +10..40 %); models whose series evaluation
+// loses more to spills than it gains in occupancy say so with kLaunchMinBlocks (He's Taylor series: 3.8 -> 3.2 G/s at 3).
+template<class M, class = void> struct LaunchMinBlocks { static constexpr int value = 3; };
+template<class M> struct LaunchMinBlocks<M, typename std::enable_if<(M::kLaunchMinBlocks > 0)>::type> { static constexpr int value = M::kLaunchMinBlocks; };
+
 template<class M>
 struct BsdfSingle
 {
+  static constexpr int kMinBlocks = LaunchMinBlocks<M>::value;
   static constexpr bool kTables = TableFloats<M>::N > 0;
   static constexpr bool kFusedSample = SamplePdfIsPdf<M>::value;
   static constexpr bool kHandFused = HandFused<M>::value;

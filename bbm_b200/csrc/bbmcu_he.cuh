@@ -61,6 +61,7 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
 {
   using Tr = HeTraits<V>;
   using F = typename Tr::F;
+  static constexpr int kLaunchMinBlocks = (V == HE_VARIANT_HOLZSCHUCH) ? 3 : 1;      // see LaunchMinBlocks (bbmcu_bsdf.cuh)
   static constexpr int SCALE = Tr::SCALED ? 0 : -1;
   static constexpr int OFF_R = Tr::SCALED ? 3 : 0;       // roughness (sigma0), then autocorrelation (tau)
   static constexpr int OFF_F = OFF_R + 2;

@@ -53,7 +53,7 @@ BBMCU_D void store4x3(float* p, size_t i, size_t n, bool aligned, const Lanes3& 
 // ---- operators --------------------------------------------------------------------------------------
 template<class B> struct EvalOp
 {
-  static constexpr int kBlock = 256, kMinBlocks = 1;
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;     // eval never reads the sampling tables
   BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -68,7 +68,7 @@ template<class B> struct EvalOp
 template<class B> struct PdfOp
 {
   static constexpr bool kOneWaveWithTables = true;            // cheap body: pay the CDF prologue once per SM slot (bbmcu_launch.cuh)
-  static constexpr int kBlock = 256, kMinBlocks = 1;
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -82,7 +82,7 @@ template<class B> struct PdfOp
 
 template<class B> struct ReflectanceOp
 {
-  static constexpr int kBlock = 256, kMinBlocks = 1;
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;
   BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -97,7 +97,7 @@ template<class B> struct ReflectanceOp
 template<class B> struct SampleOp
 {
   static constexpr bool kOneWaveWithTables = true;
-  static constexpr int kBlock = 256, kMinBlocks = 1;
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
@@ -113,7 +113,7 @@ template<class B> struct SampleOp
 template<class B> struct SampleEvalPdfOp
 {
   static constexpr bool kOneWaveWithTables = false;           // dominated by the model's eval, whose cost varies per element: keep many blocks for balance
-  static constexpr int kBlock = B::kHandFused ? 512 : 256, kMinBlocks = B::kHandFused ? 2 : 1;     // launch shape (see Microfacet::kHandFusedEvalPdf)
+  static constexpr int kBlock = B::kHandFused ? 512 : 256, kMinBlocks = B::kHandFused ? 2 : B::kMinBlocks;     // launch shape (see Microfacet::kHandFusedEvalPdf)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned;
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const

@@ -251,7 +251,7 @@ BBMCU_D float glibc_logf(float x)
   if(ix - 0x00800000 >= 0x7f800000 - 0x00800000) {
     if(ix * 2 == 0) return u2f(0xff800000u);
     if(ix == 0x7f800000) return x;
-    if((ix & 0x80000000) || ix * 2 >= 0xff000000) return (x - x) / 0.0f;
+    if((ix & 0x80000000) || ix * 2 >= 0xff000000) return u2f(0x7fc00000u);          // __math_invalidf: NaN
     ix = f2u(x * 0x1p23f); ix -= 23 << 23;
   }
   uint32_t tmp = ix - 0x3f330000;
