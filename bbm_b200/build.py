@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libbbmcu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-DEFINES = []
+DEFINES = [d for d in os.environ.get("BBMCU_DEFINES", "").split() if d]        # e.g. BBMCU_DEFINES="-DBBMCU_LOSS_MINB_EXPERIMENT" for tuning builds
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
               "-diag-suppress", "20012,20011,20014,177,550"] + DEFINES

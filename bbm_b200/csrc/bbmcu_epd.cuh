@@ -264,6 +264,7 @@ BBMCU_D float epd_gamma_q_inv(float a, float q)
 struct NdfEPD
 {
   static constexpr int NA = 2;         // beta, p
+  static constexpr int kFusedMinBlocks = 1;      // the fused sample + eval + pdf kernel spills at 80 registers (4.1 -> 2.6 G/s)
   template<class T> BBMCU_D static T normalization(const T& beta, const T& p)
   {
     if(!(val(p) > kEps)) return T(0.0f) / (beta*beta);

@@ -121,14 +121,27 @@ struct NdfBeckmann
     if(!(h.z > 0.0f)) return T(0.0f);
     T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     float c2 = h.z*h.z;
-    T sx = h.x/ax, sy = h.y/ay;
     T d;
     if constexpr (std::is_same<T, float>::value)
+    {
       // the exponent keeps the reference's IEEE operations (exp amplifies its relative error by |exponent|, 10^2..10^4
-      // for fitted roughness 0.003-0.02); the quotient outside is a final value
-      d = q_div(m_exp(-(sx*sx + sy*sy) / c2), ax*ay*c2*c2);
+      // for fitted roughness 0.003-0.02); the quotient outside is a final value.  The three IEEE divisions go through
+      // the unguarded fast path when roughness (uniform) and cos^2 (almost always) are in range: same bits, no slow-path
+      // regions.  |h.x|, |h.y| <= 1 over alpha > 1e-14 stay below 1e14, their squares below 2e28, the exponent below 2e35.
+      float e;
+      if((ax > 1e-14f) && (ax < 1e30f) && (ay > 1e-14f) && (ay < 1e30f) && (c2 > 1e-7f))
+      {
+        const float sx = ieee_div_raw(h.x, ax), sy = ieee_div_raw(h.y, ay);
+        e = ieee_div_raw(-(sx*sx + sy*sy), c2);
+      }
+      else { const float sx = h.x/ax, sy = h.y/ay; e = -(sx*sx + sy*sy) / c2; }
+      d = q_div(m_exp(e), ax*ay*c2*c2);
+    }
     else
+    {
+      T sx = h.x/ax, sy = h.y/ay;
       d = m_exp(-(sx*sx + sy*sy) / c2) / (ax*ay*c2*c2);
+    }
     if(NORMALIZE) d = d * kInvPi;
     return d;
   }
@@ -562,9 +575,13 @@ template<class NDF, class = void> struct HasSampleUnchecked { static constexpr b
 template<class NDF> struct HasSampleUnchecked<NDF, typename std::enable_if<NDF::kHasSampleUnchecked>::type> { static constexpr bool value = true; };
 template<class NDF> BBMCU_D f3 quick_halfway(f3 a, f3 b) { if constexpr (QuickHalfway<NDF>::value) return q_normalize(a + b); else return halfway(a, b); }
 
+template<class NDF, class = void> struct NdfFusedMinBlocks { static constexpr int value = 0; };
+template<class NDF> struct NdfFusedMinBlocks<NDF, typename std::enable_if<(NDF::kFusedMinBlocks > 0)>::type> { static constexpr int value = NDF::kFusedMinBlocks; };
+
 template<class NDF, class G, class F, int NORM, bool SCALED>
 struct Microfacet
 {
+  static constexpr int kLaunchMinBlocksFused = NdfFusedMinBlocks<NDF>::value;      // 0: the default of bbmcu_bsdf.cuh
   static constexpr int SCALE = SCALED ? 0 : -1;
   static constexpr int OFF_NDF = SCALED ? 3 : 0;
   static constexpr int OFF_F = OFF_NDF + NDF::NA;
