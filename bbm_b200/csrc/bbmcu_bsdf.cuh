@@ -157,6 +157,8 @@ struct BsdfSingle
   { if constexpr (kFusedSample) M::sample_dir(out, xi, b.attrs, component, dir, flag); }
   BBMCU_D static void eval_pdf(const BsdfDesc& b, f3 in, f3 out, int component, Spec<float>& e, float& p)
   { if constexpr (kFusedSample) M::eval_pdf(in, out, b.attrs, component, e, p); }
+  BBMCU_D static void sample_eval_pdf_merged(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag, Spec<float>& e, float& p)
+  { if constexpr (kHandFused) M::sample_eval_pdf_merged(out, xi, b.attrs, component, dir, flag, e, p); }
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component) { return M::template eval<float>(in, out, b.attrs, component); }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component) { return M::reflectance(out, b.attrs, component); }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component) { return M::pdf(in, out, b.attrs, component); }

@@ -124,7 +124,12 @@ template<class B> struct SampleEvalPdfOp
     {
       f3 o = b.get(k), dd;
       Spec<float> s;
-      if constexpr (B::kFusedSample)
+      if constexpr (B::kHandFused)
+      {
+        B::sample_eval_pdf_merged(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, f[k], s, p.v[k]);
+        sp.v[k] = p.v[k];                                     // p is already 0 when the sample is invalid
+      }
+      else if constexpr (B::kFusedSample)
       {
         B::sample_dir(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, f[k]);
         B::eval_pdf(bsdf, dd, o, component, s, p.v[k]);

@@ -93,10 +93,10 @@ template<int C> __device__ __forceinline__ void warp_reduce_multi(const float (&
   writer = (lane & ~used & 31) == 0;
 }
 
-// (launch bounds: 256 x 2, i.e. <= 128 registers, measured best: one resident block (255 registers allowed) runs K = 256 in
-// 3.81 ms, two in 2.71 ms, three (80 registers, spills) in 2.80 ms)
+// (launch bounds: block size only, which lets the compiler settle at 128 registers = 2 resident blocks: 2.65 ms for K = 256;
+// measured alternatives: (256, 1) -> 255 registers allowed, 3.81 ms; (256, 2) 2.71 ms; (256, 3) -> 80 registers, spills, 2.80 ms)
 template<class LossT, bool WG>
-__global__ void __launch_bounds__(kLossThreads, 2) k_loss_tile(const LossArgs a, int K, int k_per_block)
+__global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, int K, int k_per_block)
 {
   constexpr int P = LossT::P;
   constexpr int C = WG ? 1 + P : 1;

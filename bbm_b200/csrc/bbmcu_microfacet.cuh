@@ -317,7 +317,8 @@ struct NdfGGX
     const float s_hi = u + lo_s, s_lo = lo_s - (s_hi - u);
     const float q = ieee_sqrt_raw(s_hi);
     const float w = sel_gt(s_hi, 1e-30f, fmaf(fmaf(-q, q, s_hi) + s_lo, 0.5f * q_rcp(q), q));
-    f3 n = (T1*P1 + T2*P2) + vs*w;
+    // n = P1 T1 + P2 T2 + w vs feeds only the final normalisation: fused multiply-adds (1e-7 of |n| = 1, nothing cancels after)
+    const f3 n = make_f3(fmaf(T1.x, P1, fmaf(T2.x, P2, vs.x*w)), fmaf(T1.y, P1, fmaf(T2.y, P2, vs.y*w)), fmaf(T2.z, P2, vs.z*w));
     return q_normalize(make_f3(n.x*ax, n.y*ay, fmaxf(0.0f, n.z)));
   }
 };
@@ -708,6 +709,38 @@ struct Microfacet
     e = divide_out(to_spec(D) * to_spec(Gv) * to_spec(Fv), in.z*out.z);
     if(SCALED) e = e * load_spec(a);
     p = q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(outh));
+  }
+  // The whole fused element - sample, eval, pdf - of the hand-merged model without a branch: every validity test of
+  // sample (microfacet.h:118-127) and eval / pdf (:74-81, :154-160) becomes a predicate that selects zeros at the end; the
+  // arithmetic runs on whatever the element holds (the *_raw operations neither trap nor loop on garbage).
+  BBMCU_D static void sample_eval_pdf_merged(f3 out, f2 xi, const float* a, int component, f3& dir, int& flag, Spec<float>& e, float& p)
+  {
+    static_assert(kHandFusedEvalPdf, "only the hand-merged model has this path");
+    const bool ok_s = (component & FLAG_SPECULAR) && xi_valid(xi) && (out.z > 0.0f);
+    const f3 m = NDF::sample_unchecked(out, xi, a + OFF_NDF);
+    const float d2m = 2.0f * q_dot(m, out);                       // reflect(out, m) = m (2 m.out) - out, a final value: fused
+    const f3 in = make_f3(fmaf(m.x, d2m, -out.x), fmaf(m.y, d2m, -out.y), fmaf(m.z, d2m, -out.z));
+    const bool ok_e = ok_s && (in.z > 0.0f);
+    const float al = a[OFF_NDF], al2 = al*al, eta = a[OFF_F];
+    const f3 h = q_normalize(in + out);
+    const float inh = q_dot(in, h), outh = q_dot(out, h);
+    const float den = fmaf(al2, h.z*h.z, fmaf(h.x, h.x, h.y*h.y));
+    const float Dv = sel_gt(h.z, 0.0f, al2 * q_rcp(kPi * den * den));
+    const float gi = sel_gt(inh, 0.0f, 2.0f*in.z * q_rcp(in.z + q_sqrt(fmaf(al2, sinTheta2(in), in.z*in.z))));
+    const float go = sel_gt(outh, 0.0f, 2.0f*out.z * q_rcp(out.z + q_sqrt(fmaf(al2, sinTheta2(out), out.z*out.z))));
+    const float c = 0.5f*(inh + outh);
+    const float g = q_sqrt(max0(eta*eta + c*c - 1.0f));
+    const float A = g - c, B = g + c, n2 = fmaf(c, B, -1.0f), d2 = fmaf(c, A, 1.0f);
+    const float R = q_rcp(B * d2);
+    const float fa = A*d2*R, fb = n2*B*R;
+    const float Fv = fmaxf(0.5f * (fa*fa) * fmaf(fb, fb, 1.0f), 0.0f);
+    const float R4 = q_rcp(4.0f * in.z * out.z);
+    const float u = ok_e ? Dv * (gi*go) * Fv * R4 : 0.0f;
+    const float pv = Dv * go * in.z * R4;
+    dir = make_f3(ok_s ? in.x : 0.0f, ok_s ? in.y : 0.0f, ok_s ? in.z : 0.0f);
+    flag = ok_s ? FLAG_SPECULAR : FLAG_NONE;
+    e = Spec<float>(u*a[0], u*a[1], u*a[2]);
+    p = (ok_e && (pv > 0.0f)) ? pv : 0.0f;
   }
   // sample.pdf is pdf(sample.direction, out) (microfacet.h:138): fused sample -> eval -> pdf passes evaluate it once
   static constexpr bool kSamplePdfIsPdf = true;
