@@ -10,20 +10,21 @@
 using namespace bbmcu;
 
 // ---- exchange window of one shard (device memory, cudaIpc-exported) ------------------------------------------------------
-//   [0, 256)   uint64 flags[2][kMaxPeers]: flags[parity][r] = sequence number of the last batch rank r has delivered
-//   [256, ...) double rows[2][world][cap]: rows[parity][r] = rank r's K x (1+P) totals of the batch with that parity
-// Two parities are enough: rank r can only deliver batch s+2 after it has seen everybody's flag of batch s+1, which a
-// peer raises after its own exchange kernel of batch s has finished reading (kernels of one shard run in stream order).
+//   PeerWord rows[2][world][cap]: rows[parity][r][i] = value i of rank r's K x (1+P) totals of the batch with that parity,
+//   as two 8-byte words {low 32 bits of the double | seq << 32, high 32 bits | seq << 32} (seq = batch number mod 2^32).
+// Every word carries its own arrival flag (aligned 8-byte stores are single-copy atomic), so there is no separate flag,
+// fence or counter on the path: a value has arrived when both of its words show the batch's seq.
+// Two parities are enough: rank r can only deliver batch s+2 after it has gathered batch s+1, which needs every peer's
+// rows of s+1, and a peer sends those only after its own gather of batch s has finished (kernels of one shard run in
+// stream order).
 constexpr int kMaxPeers = 16;
-constexpr size_t kPeerFlagBytes = 2 * kMaxPeers * sizeof(unsigned long long);
+struct PeerWord { unsigned long long lo, hi; };
 struct PeerArgs
 {
   int rank, world;
-  unsigned long long seq;
+  unsigned int seq;
   size_t cap;
   unsigned char* win[kMaxPeers];
-  double* local;
-  unsigned int* counter;
   unsigned int* status;
 };
 
@@ -56,15 +57,12 @@ struct bbmcu_loss
   size_t peer_cap = 0;                                   // doubles per (parity, rank) row
   unsigned char* peer_win[kMaxPeers] = {};               // [rank] = that shard's window; own entry = own allocation
   bool peer_ipc[kMaxPeers] = {};                         // opened with cudaIpcOpenMemHandle (to be closed)
-  double* d_local = nullptr; size_t local_cap = 0;       // this shard's totals before the exchange
-  unsigned int* d_counter = nullptr;
   unsigned int* h_peer_status = nullptr;                 // pinned, mapped: 1 = a peer did not arrive
-  unsigned long long peer_seq = 0;
+  unsigned int peer_seq = 0;
   ~bbmcu_loss()
   {
     for(int r=0; r < kMaxPeers; ++r) if(peer_ipc[r] && peer_win[r]) cudaIpcCloseMemHandle(peer_win[r]);
     if(peer_win[peer_rank]) cudaFree(peer_win[peer_rank]);
-    cudaFree(d_local); cudaFree(d_counter);
     if(h_peer_status) cudaFreeHost(h_peer_status);
     cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
     for(int i=0; i < 2; ++i) { if(h_attrs[i]) cudaFreeHost(h_attrs[i]); if(h_attrs_free[i]) cudaEventDestroy(h_attrs_free[i]); }
@@ -133,21 +131,16 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_finish(const double* pa
 }
 
 // ---- the same finish, fused with the exchange over peer memory ----------------------------------------------------------
-__device__ __forceinline__ unsigned long long* peer_flags(unsigned char* win, int parity) { return reinterpret_cast<unsigned long long*>(win) + parity*kMaxPeers; }
-__device__ __forceinline__ double* peer_row(unsigned char* win, int parity, int world, size_t cap, int r) { return reinterpret_cast<double*>(win + kPeerFlagBytes) + ((size_t)parity*world + r)*cap; }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ PeerWord* peer_row(unsigned char* win, int parity, int world, size_t cap, int r) { return reinterpret_cast<PeerWord*>(win) + ((size_t)parity*world + r)*cap; }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
-// Every block finishes one (k, column) total of this shard as k_loss_finish does; the block that finishes last then
-//   1. stores the shard's rows into the window of every peer (remote stores over NVLink; its own window included),
-//   2. raises flag[parity][rank] = seq in every window (release, system scope),
-//   3. waits until the `world` flags of its own window carry seq (acquire; bounded: ~10 s, then status = 1 and NaN results),
-//   4. adds the rows in rank order - the same order on every shard, so all of them return identical bits.
-__global__ void __launch_bounds__(kFinishThreads) k_loss_finish_exchange(const double* partial, int blocks_x, int cols, double inv_n, double* result, const PeerArgs pa)
+// send: every block finishes one (k, column) total of this shard as k_loss_finish does and stores it - two flagged words -
+// into the window of every peer (remote stores over NVLink; its own window included).  Nothing waits here.
+__global__ void __launch_bounds__(kFinishThreads) k_loss_finish_send(const double* partial, int blocks_x, int cols, double inv_n, const PeerArgs pa)
 {
   __shared__ double s[kFinishThreads];
-  __shared__ int s_last, s_timeout;
   const int k = blockIdx.x, j = blockIdx.y, tid = threadIdx.x;
   const double* p = partial + ((size_t)k*cols + j)*blocks_x;
   double v = 0.0;
@@ -159,46 +152,48 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_finish_exchange(const d
     if(tid < o) s[tid] += s[tid + o];
     __syncthreads();
   }
-  const unsigned int nvals = gridDim.x * gridDim.y;
-  if(tid == 0)
-  {
-    pa.local[(size_t)k*cols + j] = s[0] * inv_n;
-    __threadfence();
-    s_last = (atomicAdd(pa.counter, 1u) == nvals - 1u) ? 1 : 0;
-    s_timeout = 0;
-  }
-  __syncthreads();
-  if(!s_last) return;
-  __threadfence();
-  const int parity = (int)(pa.seq & 1ull);
-  for(int q = 0; q < pa.world; ++q)
-  {
-    double* dst = peer_row(pa.win[q], parity, pa.world, pa.cap, pa.rank);
-    for(unsigned int i = tid; i < nvals; i += kFinishThreads) dst[i] = __ldcg(pa.local + i);
-  }
-  __threadfence_system();
-  __syncthreads();
   if(tid < pa.world)
   {
-    st_release_sys(peer_flags(pa.win[tid], parity) + pa.rank, pa.seq);
-    const unsigned long long* mine = peer_flags(pa.win[pa.rank], parity) + tid;
-    const unsigned long long t0 = global_ns();
-    while(ld_acquire_sys(mine) < pa.seq)
-    {
-      __nanosleep(200);
-      if(global_ns() - t0 > 10000000000ull) { s_timeout = 1; break; }
-    }
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(s[0] * inv_n), flag = (unsigned long long)pa.seq << 32;
+    PeerWord* dst = peer_row(pa.win[tid], (int)(pa.seq & 1u), pa.world, pa.cap, pa.rank) + ((size_t)k*cols + j);
+    st_relaxed_sys(&dst->lo, (bits & 0xffffffffull) | flag);
+    st_relaxed_sys(&dst->hi, (bits >> 32) | flag);
   }
-  __syncthreads();
-  __threadfence_system();
-  const bool bad = s_timeout != 0;
-  for(unsigned int i = tid; i < nvals; i += kFinishThreads)
+}
+
+// gather: thread i polls value i of every rank's row in its own window until both words carry this batch's seq, and adds
+// them in rank order - the same order on every shard, so all of them return identical bits.  Bounded: a value that has not
+// arrived after ~10 s sets status = 1 and yields NaN instead of hanging the device.
+__global__ void __launch_bounds__(kFinishThreads) k_loss_gather(unsigned int nvals, double* result, const PeerArgs pa)
+{
+  const unsigned int i = blockIdx.x * kFinishThreads + threadIdx.x;
+  if(i >= nvals) return;
+  const PeerWord* rows = peer_row(pa.win[pa.rank], (int)(pa.seq & 1u), pa.world, pa.cap, 0) + i;
+  double vals[kMaxPeers];
+  unsigned int pending = (pa.world >= 32) ? 0xffffffffu : ((1u << pa.world) - 1u);
+  const unsigned long long t0 = global_ns();
+  bool bad = false;
+  while(pending)
   {
-    double sum = 0.0;
-    for(int r = 0; r < pa.world; ++r) sum += __ldcv(peer_row(pa.win[pa.rank], parity, pa.world, pa.cap, r) + i);
-    result[i] = bad ? __longlong_as_double(0x7ff8000000000000ll) : sum;
+#pragma unroll
+    for(int r = 0; r < kMaxPeers; ++r)
+    {
+      if(!(pending & (1u << r))) continue;
+      const PeerWord* w = rows + (size_t)r*pa.cap;
+      const unsigned long long lo = ld_relaxed_sys(&w->lo), hi = ld_relaxed_sys(&w->hi);
+      if((unsigned int)(lo >> 32) == pa.seq && (unsigned int)(hi >> 32) == pa.seq)
+      {
+        vals[r] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
+        pending &= ~(1u << r);
+      }
+    }
+    if(pending && (global_ns() - t0 > 10000000000ull)) { bad = true; break; }
   }
-  if(tid == 0) { *pa.counter = 0u; if(bad) *pa.status = 1u; }
+  double sum = 0.0;
+#pragma unroll
+  for(int r = 0; r < kMaxPeers; ++r) if(r < pa.world) sum += vals[r];
+  if(bad) { *pa.status = 1u; sum = __longlong_as_double(0x7ff8000000000000ll); }
+  result[i] = sum;
 }
 
 // per-sample terms l(idx) (sampledlossfunction::operator()(idx))
@@ -373,13 +368,16 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     if(L->peer_connected && L->peer_world > 1)
     {
       if(K*(size_t)cols > L->peer_cap) throw std::invalid_argument("BBM: K*(1+P) = " + std::to_string(K*(size_t)cols) + " exceeds the peer window (" + std::to_string(L->peer_cap) + " values)");
-      grow(L->d_local, L->local_cap, K*(size_t)cols);
       PeerArgs pa{};
-      pa.rank = L->peer_rank; pa.world = L->peer_world; pa.seq = ++L->peer_seq; pa.cap = L->peer_cap;
+      pa.rank = L->peer_rank; pa.world = L->peer_world; pa.cap = L->peer_cap;
+      if(++L->peer_seq == 0u) L->peer_seq = 2u;                     // 0 marks a fresh window; 2 keeps the parities alternating across the wrap
+      pa.seq = L->peer_seq;
       for(int r=0; r < L->peer_world; ++r) pa.win[r] = L->peer_win[r];
-      pa.local = L->d_local; pa.counter = L->d_counter;
       BBMCU_CUDA(cudaHostGetDevicePointer((void**)&pa.status, L->h_peer_status, 0));
-      k_loss_finish_exchange<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result, pa);
+      k_loss_finish_send<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, pa);
+      const unsigned nvals = (unsigned)(K*(size_t)cols);
+      k_loss_gather<<<(nvals + kFinishThreads - 1) / kFinishThreads, kFinishThreads, 0, ctx->stream>>>(nvals, result, pa);
+      ++ctx->launches;
     }
     else
       k_loss_finish<<<dim3((unsigned)K, (unsigned)cols), kFinishThreads, 0, ctx->stream>>>(L->d_partial, (int)bx, cols, 1.0 / (double)L->N, result);
@@ -413,12 +411,10 @@ int bbmcu_loss_peer_init(bbmcu_loss* L, int rank, int world, size_t max_values, 
     if(L->peer_win[L->peer_rank]) throw std::invalid_argument("BBM: the loss already has a peer window");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     BBMCU_CUDA(cudaSetDevice(ctx->device));
-    const size_t bytes = kPeerFlagBytes + 2*(size_t)world*max_values*sizeof(double);
+    const size_t bytes = 2*(size_t)world*max_values*sizeof(PeerWord);
     unsigned char* win = nullptr;
     BBMCU_CUDA(cudaMalloc(&win, bytes));
     BBMCU_CUDA(cudaMemset(win, 0, bytes));
-    BBMCU_CUDA(cudaMalloc(&L->d_counter, sizeof(unsigned int)));
-    BBMCU_CUDA(cudaMemset(L->d_counter, 0, sizeof(unsigned int)));
     BBMCU_CUDA(cudaHostAlloc((void**)&L->h_peer_status, sizeof(unsigned int), cudaHostAllocMapped));
     *L->h_peer_status = 0u;
     BBMCU_CUDA(cudaDeviceSynchronize());

@@ -156,10 +156,11 @@ BBMCU_API int  bbmcu_loss_terms(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, float*
  * One process (or context) per GPU of ONE node owns one shard of the same loss.  After the calls below every
  * bbmcu_loss_eval of that loss is a COLLECTIVE over the `world` shards - all of them must call it with the same bsdf shape
  * and K, in the same order - and returns the sum over the shards (= the reference's mean): the kernel that finishes a
- * shard's K x (1+P) totals stores them into every peer's exchange window (plain remote stores), raises a per-peer sequence
- * flag, waits for the `world` flags of its own window and adds the rows in rank order.  No NCCL call, no host round trip;
- * every rank gets bit-identical results.  A peer that does not arrive within ~10 s makes the call fail (BBMCU_RUNTIME_ERROR
- * at the next synchronising call) instead of hanging the device.
+ * shard's K x (1+P) totals stores each of them into every peer's exchange window as two 8-byte words that carry the batch
+ * number next to the payload (plain remote stores over NVLink, nothing waits), and a gather kernel polls the `world` rows
+ * of its own window until every word shows this batch and adds them in rank order.  No NCCL call, no fence, flag or host
+ * round trip; every rank gets bit-identical results.  A peer that does not arrive within ~10 s makes the call fail
+ * (BBMCU_RUNTIME_ERROR at the next synchronising call) instead of hanging the device.
  *   peer_init:     allocates this shard's window for batches of up to max_values = K*(1+P) doubles and returns its
  *                  cudaIpcMemHandle (64 bytes) for the other PROCESSES, and its device address for contexts of the same
  *                  process;
