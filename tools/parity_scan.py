@@ -75,9 +75,18 @@ def main():
     ctx = bb.Context(0)
     ref = refbind.Ref("float")
     threads = len(os.sched_getaffinity(0))
-    rows = [scan(ctx, ref, s, 1 << a.log2, a.seed, threads) for s in a.bsdfs]
-    for r in rows:
-        print(json.dumps(r))
+    strings = []
+    for s in a.bsdfs:
+        if s == "@defaults":                                   # every analytic model at its default parameters
+            strings += [m + "()" for m in bb.model_names() if m != "Merl"]
+        elif s.startswith("@"):                                # the configurations of an earlier scan (its JSON file)
+            strings += [r["bsdf"] for r in json.load(open(s[1:]))]
+        else:
+            strings.append(s)
+    rows = []
+    for s in strings:
+        rows.append(scan(ctx, ref, s, 1 << a.log2, a.seed, threads))
+        print(json.dumps(rows[-1]), flush=True)
     if a.out:
         json.dump(rows, open(a.out, "w"), indent=1)
 
