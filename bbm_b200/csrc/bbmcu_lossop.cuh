@@ -94,6 +94,15 @@ template<class M> struct GeomOf<M, typename VoidT<typename M::Geom>::type>
 template<class M, class = void> struct GrayUnscaled { static constexpr bool value = false; };
 template<class M> struct GrayUnscaled<M, typename std::enable_if<M::kGrayUnscaled>::type> { static constexpr bool value = true; };
 
+// microfacet lobes whose jacobian separates into an NDF block and a Fresnel block (Microfacet::unscaled_gray_jacobian):
+// scaled, gray before the scale, every NDF and Fresnel parameter a fit parameter in attribute order
+template<class M, class = void> struct SeparableJac { static constexpr bool value = false; };
+template<class M> struct SeparableJac<M, typename std::enable_if<(M::kNdfParams + M::kFresnelParams > 0)>::type>
+{
+  static constexpr bool value = GrayUnscaled<M>::value && (M::SCALE == 0) && FitMap<M>::NFIT == M::NA && FitMap<M>::attr_of(M::NA - 1) == M::NA - 1
+                             && NonLinear<M>::N == M::kNdfParams + M::kFresnelParams;
+};
+
 // value and parameter jacobian of one lobe.  Scale parameters (a leading RGB attribute) touch one channel each and are
 // kept as the three unscaled values `us`; the NL non-linear parameters carry a full RGB column.
 template<class M> struct LobeJac
@@ -144,6 +153,14 @@ BBMCU_D LobeJac<M> lobe_jacobian(const typename GeomOf<M>::type& geom, const flo
     Spec<float> u = GeomOf<M>::template eval_unscaled<float>(geom, in, out, a, component);
     J.us[0] = u.r; J.us[1] = u.g; J.us[2] = u.b;
     J.v = Spec<float>(a[0]*u.r, a[1]*u.g, a[2]*u.b);
+  }
+  else if constexpr (SeparableJac<M>::value)
+  {
+    const Dual<NL> u = M::template unscaled_gray_jacobian<NL>(geom, in, out, a, component);
+    J.us[0] = J.us[1] = J.us[2] = u.v;
+#pragma unroll
+    for(int j=0; j < NL; ++j) J.jr[j] = u.d[j];
+    J.v = Spec<float>(a[0]*u.v, a[1]*u.v, a[2]*u.v);
   }
   else
   {

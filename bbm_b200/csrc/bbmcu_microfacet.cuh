@@ -609,6 +609,35 @@ struct Microfacet
     Spec<T> dgf = to_spec(D) * to_spec(Gv) * to_spec(Fv);
     return divide_out(dgf, in.z*out.z);
   }
+  // Value and parameter jacobian of the gray unscaled lobe u = D G F / (N z_i z_o) for the batched loss kernels.  D and G
+  // depend on the NDF's parameters only, F on its own: their tangents never mix, so instead of pushing NA_ndf + NA_f
+  // tangents through every product (eval_unscaled_g<Dual<N>>), D G carries NA_ndf tangents, F carries NA_f, and
+  //   du/d(ndf) = (D G)' F k,   du/d(f) = D G F' k.
+  static constexpr int kNdfParams = NDF::NA, kFresnelParams = F::NA;
+  template<int N> BBMCU_D static Dual<N> unscaled_gray_jacobian(const Geom& g, f3 in, f3 out, const float* a, int component)
+  {
+    static_assert(kGrayUnscaled && N == NDF::NA + F::NA, "scalar D, G, F with every NDF and Fresnel parameter fitted");
+    Dual<N> r(0.0f);
+    if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return r;
+    using DN = Dual<NDF::NA>;
+    using DF = Dual<F::NA>;
+    DN an[NDF::NA];
+    DF af[F::NA];
+#pragma unroll
+    for(int i=0; i < NDF::NA; ++i) { an[i] = DN(a[OFF_NDF + i]); an[i].d[i] = 1.0f; }
+#pragma unroll
+    for(int i=0; i < F::NA; ++i) { af[i] = DF(a[OFF_F + i]); af[i].d[i] = 1.0f; }
+    const DN dg = NDF::template D<DN>(g.h, an) * G::template eval<NDF, DN>(in, out, g.h, an);
+    const DF fv = F::template evalq<DF>(af, 0.5f*(g.inh + g.outh));
+    const float k = q_rcp((float)norm() * (in.z*out.z));
+    const float dgk = dg.v * k, fk = fv.v * k;
+    r.v = dgk * fv.v;
+#pragma unroll
+    for(int i=0; i < NDF::NA; ++i) r.d[i] = dg.d[i] * fk;
+#pragma unroll
+    for(int i=0; i < F::NA; ++i) r.d[NDF::NA + i] = dgk * fv.d[i];
+    return r;
+  }
   // eval without the leading scale (microfacet.h:74-102)
   template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
   {
