@@ -9,6 +9,8 @@
 // The six metrics are the error functors of include/loss/cosine_weighted_l2.h:25-34,96-105,166-176 and
 // include/loss/cosine_weighted_log.h:32-43,101-112,170-181 (nganL2, lowL2, bieronL2, lowLog, bieronLog, standardLog).
 #pragma once
+#include <array>
+#include <algorithm>
 #include <optional>
 #include "bsdf.hpp"
 
@@ -73,6 +75,23 @@ public:
     const size_t P = parameters(), K = P ? params_KxP.size() / P : 0;
     if(K) check(bbmcu_loss_eval(_loss.get(), _fitted.get(), params_KxP.data(), K, nullptr, nullptr, device_out), _fitted.ctx().get());
   }
+  // ---- shards of one loss on the GPUs of a node: combine inside the library's kernels over NVLink peer memory ------------
+  // (bbmcu_loss_peer_*; after connecting, every evaluation is a collective over the shards and returns their sum)
+  // allocate this shard's exchange window for batches of up to max_values = K*(1+P) doubles: the 64-byte handle goes to
+  // the other processes (MPI_Allgather, a pipe, ...), *window to contexts of this process
+  std::array<unsigned char, 64> peer_init(int rank, int world, size_t max_values, void** window = nullptr)
+  {
+    std::array<unsigned char, 64> h{};
+    check(bbmcu_loss_peer_init(_loss.get(), rank, world, max_values, h.data(), window), _fitted.ctx().get());
+    return h;
+  }
+  void peer_connect(const std::vector<std::array<unsigned char, 64>>& handles_by_rank)
+  {
+    std::vector<unsigned char> blob(64*handles_by_rank.size());
+    for(size_t r=0; r < handles_by_rank.size(); ++r) std::copy(handles_by_rank[r].begin(), handles_by_rank[r].end(), blob.begin() + 64*r);
+    check(bbmcu_loss_peer_connect(_loss.get(), blob.data()), _fitted.ctx().get());
+  }
+  void peer_connect(const std::vector<void*>& windows_by_rank) { check(bbmcu_loss_peer_connect_ptrs(_loss.get(), windows_by_rank.data()), _fitted.ctx().get()); }
   // write the live parameters back into the fitted BSDF (toString / export)
   void commit() { _fitted.set_parameter_values(*_params); }
   cuda_bsdf& fitted() const { return _fitted; }

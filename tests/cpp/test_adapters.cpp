@@ -8,6 +8,7 @@
 #include "bbmcu/loss.hpp"
 #include "bbmcu/optimizer.hpp"
 #include "bbmcu/fit.hpp"
+#include <cuda_runtime_api.h>
 
 using namespace bbmcu;
 
@@ -80,6 +81,37 @@ int main(int argc, char** argv)
     std::printf("\"gd_first\": %.9g, \"gd_last\": %.9g,\n", trace_g.front(), trace_g.back());
     loss_g.commit();
     std::printf("\"gd_fitted\": \"%s\",\n", fitted.toString().c_str());
+
+    // two shards of one loss on two contexts (streams) of this device, combined over each other's exchange windows
+    {
+      context ctx2(0);
+      cuda_bsdf fitted_b = bsdf_import(ctx2, fitted.toString());
+      std::vector<double> pa = fitted.parameter_values(), pb = pa;
+      const auto grid = spherical_grid({13, 8}, {5, 6});
+      cuda_loss whole(metric::nganL2, fitted, truth, pa, grid);
+      const uint64_t n = whole.samples(), cut = n / 2 + 7;
+      cuda_loss sa(metric::nganL2, fitted, truth, pa, grid, bsdf_flag::All, 0, cut);
+      cuda_loss sb(metric::nganL2, fitted_b, truth, pb, grid, bsdf_flag::All, cut, n - cut);
+      const size_t cols = 1 + pa.size();
+      void *wa = nullptr, *wb = nullptr;
+      sa.peer_init(0, 2, 4*cols, &wa);
+      sb.peer_init(1, 2, 4*cols, &wb);
+      sa.peer_connect(std::vector<void*>{wa, wb});
+      sb.peer_connect(std::vector<void*>{wa, wb});
+      double *da = nullptr, *db = nullptr;
+      if(cudaMalloc((void**)&da, cols*sizeof(double)) != cudaSuccess || cudaMalloc((void**)&db, cols*sizeof(double)) != cudaSuccess) throw std::runtime_error("cudaMalloc");
+      sa.eval_device(pa, da);                      // asynchronous: its gather kernel waits on the device for the other shard's rows
+      sb.eval_device(pb, db);
+      ctx.synchronize(); ctx2.synchronize();
+      std::vector<double> ha(cols), hb(cols);
+      cudaMemcpy(ha.data(), da, cols*sizeof(double), cudaMemcpyDeviceToHost);
+      cudaMemcpy(hb.data(), db, cols*sizeof(double), cudaMemcpyDeviceToHost);
+      cudaFree(da); cudaFree(db);
+      std::vector<double> g;
+      const double l = whole.gradient(g);
+      std::printf("\"peer_identical\": %s, \"peer_loss\": %.12g, \"whole_loss\": %.12g, \"peer_grad0\": %.12g, \"whole_grad0\": %.12g,\n",
+                  ha == hb ? "true" : "false", ha[0], l, ha[1], g[0]);
+    }
 
     // error behaviour: the reference throws std::invalid_argument from its parser
     bool threw = false;

@@ -17,8 +17,9 @@ def _build():
     import bbm_b200  # noqa: F401  (libbbmcu.so must exist)
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     libdir = os.path.join(ROOT, "bbm_b200")
-    cmd = ["g++", "-std=c++20", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), SRC, "-o", EXE,
-           "-L" + libdir, "-l:libbbmcu.so", "-Wl,-rpath," + libdir]
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")           # cudaMalloc for the device buffers of the peer-exchange block
+    cmd = ["g++", "-std=c++20", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"), SRC, "-o", EXE,
+           "-L" + libdir, "-l:libbbmcu.so", "-Wl,-rpath," + libdir, "-L" + os.path.join(cuda, "lib64"), "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
 
@@ -41,6 +42,10 @@ def test_adapter_program_against_reference(golden_loss, ref):
     assert abs(out["loss0"] - m["double_total"]) <= 1e-4 * abs(m["double_total"])
     fd = np.array(m["fd_gradient"])
     assert np.all(np.abs(np.array(out["gradient"]) - fd) <= 1e-4 * np.abs(fd) + 1e-9)
+    # two shards on two streams, combined over peer memory inside the library's kernels: identical on both, equal to the whole
+    assert out["peer_identical"] is True
+    assert abs(out["peer_loss"] - out["whole_loss"]) <= 1e-5 * abs(out["whole_loss"])
+    assert abs(out["peer_grad0"] - out["whole_grad0"]) <= 1e-5 * abs(out["whole_grad0"]) + 1e-12
     # scalar concept calls against the compiled reference
     truth = meta["truth"]
     i = np.array([[0.3, 0.2, 0.9327379]], np.float32)
