@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_generic(const LossArgs a,
   const int k = blockIdx.y, P = a.P;
   if(threadIdx.x == 0) { b = shape; }
   __syncthreads();
-  for(int i = threadIdx.x; i < a.n_attrs; i += blockDim.x) b.attrs[i] = a.attrs[(size_t)k*a.attr_stride + i];
+  for(int i = threadIdx.x; i < a.n_attrs; i += blockDim.x) b.attrs[i] = loss_attr(a, (size_t)k*a.attr_stride + i);
   __syncthreads();
   double acc[1 + kMaxParams];
   for(int j=0; j <= P; ++j) acc[j] = 0.0;
@@ -305,25 +305,34 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     const int A = shape.n_floats;                 // device floats per parameter set (He lobes carry an unused table gap)
     const bool want_grad = (grad_out != nullptr) || (device_out != nullptr);
     const int cols = 1 + P;
-    // attribute blocks for the K parameter sets
-    grow(L->d_attrs, L->attrs_cap, K*(size_t)A);
-    // two pinned staging buffers: packing the next batch never waits for the kernels of the previous one, only (and in
-    // practice never) for the upload that last read the buffer it is about to overwrite
-    const int hb = L->h_flip; L->h_flip ^= 1;
-    if(!L->h_attrs_free[hb]) BBMCU_CUDA(cudaEventCreateWithFlags(&L->h_attrs_free[hb], cudaEventDisableTiming));
-    else BBMCU_CUDA(cudaEventSynchronize(L->h_attrs_free[hb]));
-    if(K*(size_t)A > L->h_attrs_cap[hb])
+    // attribute blocks for the K parameter sets: inside the kernel arguments when they fit (one compass step), else
+    // through two pinned staging buffers - packing the next batch never waits for the kernels of the previous one, only
+    // (and in practice never) for the upload that last read the buffer it is about to overwrite
+    LossArgs a;
+    const bool inline_attrs = K*(size_t)A <= (size_t)kInlineAttrFloats;
+    a.inline_count = inline_attrs ? (int)(K*(size_t)A) : 0;
+    float* h_attrs = a.inline_attrs;
+    int hb = 0;
+    if(!inline_attrs)
     {
-      if(L->h_attrs[hb]) { BBMCU_CUDA(cudaFreeHost(L->h_attrs[hb])); L->h_attrs[hb] = nullptr; L->h_attrs_cap[hb] = 0; }
-      BBMCU_CUDA(cudaMallocHost(&L->h_attrs[hb], K*(size_t)A*sizeof(float)));
-      L->h_attrs_cap[hb] = K*(size_t)A;
+      grow(L->d_attrs, L->attrs_cap, K*(size_t)A);
+      hb = L->h_flip; L->h_flip ^= 1;
+      if(!L->h_attrs_free[hb]) BBMCU_CUDA(cudaEventCreateWithFlags(&L->h_attrs_free[hb], cudaEventDisableTiming));
+      else BBMCU_CUDA(cudaEventSynchronize(L->h_attrs_free[hb]));
+      if(K*(size_t)A > L->h_attrs_cap[hb])
+      {
+        if(L->h_attrs[hb]) { BBMCU_CUDA(cudaFreeHost(L->h_attrs[hb])); L->h_attrs[hb] = nullptr; L->h_attrs_cap[hb] = 0; }
+        BBMCU_CUDA(cudaMallocHost(&L->h_attrs[hb], K*(size_t)A*sizeof(float)));
+        L->h_attrs_cap[hb] = K*(size_t)A;
+      }
+      h_attrs = L->h_attrs[hb];
     }
-    float* const h_attrs = L->h_attrs[hb];
     {
       bbmcu_host::Bsdf tmp = bsdf->b;
       for(size_t k=0; k < K; ++k)
       {
         if(params) tmp.set_params(BBMCU_ATTR_ALL, params + k*P, P);
+        for(int i=0; i < A; ++i) h_attrs[k*A + i] = 0.0f;               // table gaps of He lobes are never read; keep them defined
         for(size_t l=0; l < tmp.lobes.size(); ++l)
         {
           size_t off = (size_t)shape.offset[l];
@@ -331,8 +340,11 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
         }
       }
     }
-    BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    BBMCU_CUDA(cudaEventRecord(L->h_attrs_free[hb], ctx->stream));
+    if(!inline_attrs)
+    {
+      BBMCU_CUDA(cudaMemcpyAsync(L->d_attrs, h_attrs, K*(size_t)A*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      BBMCU_CUDA(cudaEventRecord(L->h_attrs_free[hb], ctx->stream));
+    }
     // launch shape: about 8 resident blocks per SM over all K
     const size_t n = L->count;
     const bool static_shape = (shape.n_lobes == 1 && !shape.aggregate) || (shape.n_lobes == 2 && shape.aggregate && shape.model[0] == M_Lambertian);
@@ -342,7 +354,6 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     if(static_shape) bx = (unsigned)std::max<size_t>(1, (n + kTileSamples - 1) / kTileSamples);     // one partial row per sample tile
     grow(L->d_partial, L->partial_cap, K*(size_t)bx*cols);
     grow(L->d_result, L->result_cap, K*(size_t)cols);
-    LossArgs a;
     a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = n; a.attrs = L->d_attrs; a.attr_stride = A; a.n_attrs = A;
     a.metric = L->metric; a.component = L->component; a.want_grad = want_grad ? 1 : 0; a.partial = L->d_partial; a.P = P; a.sm_count = ctx->sm_count;
     bool done = false;

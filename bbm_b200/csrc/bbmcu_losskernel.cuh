@@ -30,7 +30,13 @@ struct LossArgs
   double* partial;        // K x (1 + P) x blocks_x
   int P;
   int sm_count;
+  // small batches (one compass step: K = 2P parameter sets) travel inside the kernel arguments: no staging buffer, no
+  // host-to-device copy, no event on the path.  inline_count = K * n_attrs floats (0: read `attrs`)
+  int inline_count;
+  float inline_attrs[256];
 };
+constexpr int kInlineAttrFloats = 256;
+BBMCU_D float loss_attr(const LossArgs& a, size_t idx) { return a.inline_count ? a.inline_attrs[idx] : a.attrs[idx]; }
 
 constexpr int kLossThreads = 256;
 
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
   const int tile = blockIdx.x;
   const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
   for(int i = threadIdx.x; i < (k1 - k0)*a.n_attrs; i += blockDim.x)
-    s_attr_tile[i] = a.attrs[(size_t)(k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs)];
+    s_attr_tile[i] = loss_attr(a, (size_t)(k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs));
   f3 in[kTileSPT], out[kTileSPT]; Spec<float> ref[kTileSPT]; bool valid[kTileSPT];
 #pragma unroll
   for(int s=0; s < kTileSPT; ++s)
