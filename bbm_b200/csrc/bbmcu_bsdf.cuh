@@ -46,63 +46,118 @@ BBMCU_D void lobe_sample(int model, const float* a, f3 out, f2 xi, int component
   dispatch_model(model, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; M::sample(out, xi, a, component, dir, pdfv, flag); });
 }
 
-// ---- run-time lobe list -----------------------------------------------------------------------
-struct BsdfGeneric
+// ---- lobe lists ---------------------------------------------------------------------------------
+// How lobe l of a descriptor reaches its model's code: through the switch over every model id (any BSDF string), or - for
+// the shape of every entry of the reference's fits/*.fit, Aggregate(M0, M1) - through a two-way branch between two models
+// known at compile time (the kernel then holds two models instead of thirty-five: 5-10 x faster, 80 instead of 255 registers).
+struct DispatchAll
 {
-  static constexpr int kMinBlocks = 1, kMinBlocksFused = 1;   // every model's code behind one switch: let it have its registers
+  static constexpr int kMinBlocks = 1;                     // every model's code behind one switch: let it have its registers
+  static constexpr int kLobes = 0;                         // taken from the descriptor
   static constexpr bool kTables = true;
+  template<class F> BBMCU_D static void apply(const BsdfDesc& b, int l, F&& f) { dispatch_model(b.model[l], f); }
+};
+template<class M0, class M1>
+struct DispatchPair
+{
+  static constexpr int kMinBlocks = 2;
+  static constexpr int kLobes = 2;
+  static constexpr bool kTables = false;                   // pairs with a He-family or measured lobe stay on the run-time path
+  template<class F> BBMCU_D static void apply(const BsdfDesc&, int l, F&& f) { if(l == 0) f((M0*)nullptr); else f((M1*)nullptr); }
+};
+
+// the reference's aggregate semantics over a lobe list (aggregatebsdf.h:77-211)
+template<class Dsp>
+struct BsdfLobes
+{
+  static constexpr int kMinBlocks = Dsp::kMinBlocks, kMinBlocksFused = Dsp::kMinBlocks;
+  static constexpr bool kTables = Dsp::kTables;
+  BBMCU_D static Spec<float> lobe_eval(const BsdfDesc& b, int l, f3 in, f3 out, int component)
+  {
+    Spec<float> r(0.0f); const float* a = b.attrs + b.offset[l];
+    Dsp::apply(b, l, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::template eval<float>(in, out, a, component); });
+    return r;
+  }
+  BBMCU_D static float lobe_pdf(const BsdfDesc& b, int l, f3 in, f3 out, int component)
+  {
+    float r = 0.0f; const float* a = b.attrs + b.offset[l];
+    Dsp::apply(b, l, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::pdf(in, out, a, component); });
+    return r;
+  }
+  BBMCU_D static Spec<float> lobe_reflectance(const BsdfDesc& b, int l, f3 out, int component)
+  {
+    Spec<float> r(0.0f); const float* a = b.attrs + b.offset[l];
+    Dsp::apply(b, l, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::reflectance(out, a, component); });
+    return r;
+  }
+  BBMCU_D static void lobe_sample(const BsdfDesc& b, int l, f3 out, f2 xi, int component, f3& dir, float& pdfv, int& flag)
+  {
+    dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE; const float* a = b.attrs + b.offset[l];
+    Dsp::apply(b, l, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; M::sample(out, xi, a, component, dir, pdfv, flag); });
+  }
   static constexpr bool kFusedSample = false;
   static constexpr bool kHandFused = false;
   BBMCU_D static void sample_dir(const BsdfDesc&, f3, f2, int, f3&, int&) {}
   BBMCU_D static void eval_pdf(const BsdfDesc&, f3, f3, int, Spec<float>&, float&) {}
+  // f(l) for every lobe: unrolled over a compile-time count (the weights then live in registers and DispatchPair's branch
+  // folds away), a plain loop over the descriptor's count otherwise
+  template<class F> BBMCU_D static void for_lobes(const BsdfDesc& b, F&& f)
+  {
+    if constexpr (Dsp::kLobes > 0) {
+#pragma unroll
+      for(int l=0; l < Dsp::kLobes; ++l) f(l);
+    }
+    else for(int l=0; l < b.n_lobes; ++l) f(l);
+  }
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component)
   {
-    if(!b.aggregate) return lobe_eval(b.model[0], b.attrs + b.offset[0], in, out, component);
+    if(!b.aggregate) return lobe_eval(b, 0, in, out, component);
     Spec<float> r(0.0f);                                   // std::accumulate from Spectrum(0) (aggregatebsdf.h:96-100)
-    for(int l=0; l < b.n_lobes; ++l) r = r + lobe_eval(b.model[l], b.attrs + b.offset[l], in, out, component);
+    for_lobes(b, [&](int l) { r = r + lobe_eval(b, l, in, out, component); });
     return r;
   }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component)
   {
-    if(!b.aggregate) return lobe_reflectance(b.model[0], b.attrs + b.offset[0], out, component);
+    if(!b.aggregate) return lobe_reflectance(b, 0, out, component);
     Spec<float> r(0.0f);
-    for(int l=0; l < b.n_lobes; ++l) r = r + lobe_reflectance(b.model[l], b.attrs + b.offset[l], out, component);
+    for_lobes(b, [&](int l) { r = r + lobe_reflectance(b, l, out, component); });
     return r;
   }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component)
   {
-    if(!b.aggregate) return lobe_pdf(b.model[0], b.attrs + b.offset[0], in, out, component);
+    if(!b.aggregate) return lobe_pdf(b, 0, in, out, component);
     float w[kMaxLobes], sum = 0.0f;
-    for(int l=0; l < b.n_lobes; ++l) { w[l] = hsum(lobe_reflectance(b.model[l], b.attrs + b.offset[l], out, component)); sum += w[l]; }
+    for_lobes(b, [&](int l) { w[l] = hsum(lobe_reflectance(b, l, out, component)); sum += w[l]; });
     if(!(sum > kEps)) return 0.0f;
     float p = 0.0f;                                        // pdf += w * pdf_l / sum, term by term (aggregatebsdf.h:183)
-    for(int l=0; l < b.n_lobes; ++l) p += w[l] * lobe_pdf(b.model[l], b.attrs + b.offset[l], in, out, component) / sum;
+    for_lobes(b, [&](int l) { p += w[l] * lobe_pdf(b, l, in, out, component) / sum; });
     return p;
   }
   BBMCU_D static void sample(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, float& pdfv, int& flag)
   {
-    if(!b.aggregate) { lobe_sample(b.model[0], b.attrs + b.offset[0], out, xi, component, dir, pdfv, flag); return; }
+    if(!b.aggregate) { lobe_sample(b, 0, out, xi, component, dir, pdfv, flag); return; }
     // the reference returns an uninitialised sample when the weight sum is <= eps
     // (aggregatebsdf.h:104,116-117); we return {0, 0, None} there (documented deviation).
     dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
     float w[kMaxLobes], sum = 0.0f;
-    for(int l=0; l < b.n_lobes; ++l) { w[l] = hsum(lobe_reflectance(b.model[l], b.attrs + b.offset[l], out, component)); sum += w[l]; }
+    for_lobes(b, [&](int l) { w[l] = hsum(lobe_reflectance(b, l, out, component)); sum += w[l]; });
     if(!(sum > kEps)) return;
     float residual = xi.x * sum;
-    for(int l=0; l < b.n_lobes; ++l)
-    {
+    for_lobes(b, [&](int l) {
       if((residual >= 0.0f) && (residual <= w[l]))
       {
         float nr = (w[l] > kEps) ? residual / w[l] : 0.0f;
-        lobe_sample(b.model[l], b.attrs + b.offset[l], out, make_f2(nr, xi.y), component, dir, pdfv, flag);
+        lobe_sample(b, l, out, make_f2(nr, xi.y), component, dir, pdfv, flag);
       }
       residual -= w[l];
-    }
+    });
     float p = 0.0f;
-    for(int l=0; l < b.n_lobes; ++l) p += w[l] * lobe_pdf(b.model[l], b.attrs + b.offset[l], dir, out, component) / sum;
+    for_lobes(b, [&](int l) { p += w[l] * lobe_pdf(b, l, dir, out, component) / sum; });
     pdfv = p;
   }
 };
+using BsdfGeneric = BsdfLobes<DispatchAll>;
+template<class M0, class M1> using BsdfPair = BsdfLobes<DispatchPair<M0, M1>>;
 
 // ---- device-side tables: the sampling CDF of He-family lobes (ndf/sampler.h:143-181) ------------------------
 // phase 1: thread `tid` of `nthreads` fills the un-normalised samples; phase 2 (after a barrier): one thread per

@@ -57,6 +57,29 @@ static void launch_bsdf_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& 
   else go((BsdfGeneric*)nullptr);
 }
 
+// Aggregate(Lambertian, M), M without device tables: the two-model kernels (BsdfPair).  Returns false for any other shape.
+template<template<class> class OpT, class Fill>
+static bool launch_pair_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& d, size_t n, Fill&& fill)
+{
+  if(!(d.aggregate && d.n_lobes == 2 && d.model[0] == M_Lambertian && d.n_tables == 0)) return false;
+  bool launched = false;
+  dispatch_model_host(d.model[1], [&](auto* m) {
+    using M = typename std::remove_pointer<decltype(m)>::type;
+    if constexpr (TableFloats<M>::N == 0)
+    {
+      OpT<BsdfPair<Lambertian, M>> op; op.bsdf = d; fill(op);
+      launch_foreach4(ctx, stream, op, n);
+      launched = true;
+    }
+  });
+  return launched;
+}
+bool launch_pair_eval(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* rgb, size_t n, bool aligned);
+bool launch_pair_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* pdf, size_t n, bool aligned);
+bool launch_pair_sample(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi, float* dir, float* pdf, int32_t* flag, size_t n, bool aligned);
+bool launch_pair_sample_eval_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
+                                 float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n, bool aligned);
+
 // entry points implemented one per translation unit so the model instantiations compile in parallel
 void launch_eval(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* rgb, size_t n);
 void launch_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* pdf, size_t n);
