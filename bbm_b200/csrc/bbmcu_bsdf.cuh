@@ -72,6 +72,7 @@ struct BsdfLobes
 {
   static constexpr int kMinBlocks = Dsp::kMinBlocks, kMinBlocksFused = Dsp::kMinBlocks;
   static constexpr bool kTables = Dsp::kTables;
+  static constexpr bool kAggregatePdfFromSample = true;
   BBMCU_D static Spec<float> lobe_eval(const BsdfDesc& b, int l, f3 in, f3 out, int component)
   {
     Spec<float> r(0.0f); const float* a = b.attrs + b.offset[l];
@@ -205,6 +206,7 @@ template<class M>
 struct BsdfSingle
 {
   static constexpr int kMinBlocks = LaunchMinBlocks<M>::value, kMinBlocksFused = LaunchMinBlocksFused<M>::value;
+  static constexpr bool kAggregatePdfFromSample = false;
   static constexpr bool kTables = TableFloats<M>::N > 0;
   static constexpr bool kFusedSample = SamplePdfIsPdf<M>::value;
   static constexpr bool kHandFused = HandFused<M>::value;

@@ -138,7 +138,10 @@ template<class B> struct SampleEvalPdfOp
       else
       {
         B::sample(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, sp.v[k], f[k]);
-        p.v[k] = B::pdf(bsdf, dd, o, component);
+        // an aggregate's sample.pdf IS pdf(sample.direction, out) - the same weights and lobe pdfs in the same order
+        // (aggregatebsdf.h:119-126 and :183) - so the fused pass does not evaluate it twice
+        if(B::kAggregatePdfFromSample && bsdf.aggregate) p.v[k] = sp.v[k];
+        else p.v[k] = B::pdf(bsdf, dd, o, component);
         s = B::eval(bsdf, dd, o, component);
       }
       d.set(k, dd); c.set(k, make_f3(s.r, s.g, s.b));
