@@ -1,6 +1,7 @@
 // Host-side launch helper: pick the compile-time single-model kernel when the BSDF is one model,
 // the run-time lobe-list kernel otherwise.
 #pragma once
+#include <cstdlib>
 #include "bbmcu_ctx.hpp"
 #include "bbmcu_kernels.cuh"
 #include "bbmcu_tables.cuh"
@@ -62,6 +63,9 @@ template<template<class> class OpT, class Fill>
 static bool launch_pair_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& d, size_t n, Fill&& fill)
 {
   if(!(d.aggregate && d.n_lobes == 2 && d.model[0] == M_Lambertian && d.n_tables == 0)) return false;
+  // BBMCU_DISABLE_PAIR_KERNELS=1 keeps such aggregates on the run-time lobe list (tests compare the two paths bit for bit)
+  static const bool disabled = [] { const char* e = std::getenv("BBMCU_DISABLE_PAIR_KERNELS"); return e && e[0] == '1'; }();
+  if(disabled) return false;
   bool launched = false;
   dispatch_model_host(d.model[1], [&](auto* m) {
     using M = typename std::remove_pointer<decltype(m)>::type;

@@ -234,6 +234,38 @@ def test_loss_peer_exchange_two_shards_one_device(ctx):
         A.eval_device(fitted, np.repeat(params, 2, 0), torch.zeros((2*K, cols), dtype=torch.float64, device=dev))     # 10 rows > the 8-row window
 
 
+def test_pair_kernels_equal_runtime_lobe_list():
+    """Aggregate(Lambertian, M) runs on the compile-time pair kernels; the run-time lobe list (BBMCU_DISABLE_PAIR_KERNELS=1,
+    read once per process, hence a subprocess) does the same arithmetic in the same order: every output bit-identical"""
+    import subprocess
+    import sys
+    code = r'''
+import sys, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+import bbm_b200 as bb
+ctx = bb.Context(0)
+rng = np.random.default_rng(21)
+n = 1 << 16
+def hemi():
+    z = rng.random(n); ph = rng.random(n) * 2 * np.pi; s = np.sqrt(1 - z * z)
+    return np.ascontiguousarray(np.stack([s * np.cos(ph), s * np.sin(ph), z]).astype(np.float32))
+i, o, xi = hemi(), hemi(), np.ascontiguousarray(rng.random((2, n)).astype(np.float32))
+h = hashlib.sha256()
+for m in ("CookTorrance([0.3,0.3,0.3], 0.2, 1.5)", "GGX([0.5,0.4,0.3], 0.15, 1.7)", "Ward()", "NganLafortune()", "LowMicrofacet()", "AshikhminShirley()"):
+    b = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), %%s)" %% m)
+    for a in (ctx.eval(b, i, o), ctx.pdf(b, i, o)) + tuple(ctx.sample(b, o, xi)) + tuple(ctx.sample_eval_pdf(b, o, xi)):
+        h.update(np.ascontiguousarray(a).tobytes())
+print(h.hexdigest())
+''' % ROOT
+    digests = []
+    for flag in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BBMCU_DISABLE_PAIR_KERNELS=flag), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(r.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1]
+
+
 def test_loss_against_measured_table(ctx, ref, tmp_path):
     """reference operand = a MERL binary written by us and read by the unmodified reference's merl<> loader"""
     import bbm_b200 as bb
