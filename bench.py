@@ -59,23 +59,58 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML through nvidia_ml_py (a
+    query takes ~0.1 ms, so a 15 ms timed region still gets tens of samples); the nvidia-smi command line of the recipe is
+    the fall-back (~50 ms per query)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.stop, self.index = [], False, index
+        self.sm, self.mx, self.reasons, self.stop, self.index, self.source = [], [], set(), False, index, "nvidia-smi"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES renumbers CUDA devices, not NVML's: map through the UUID-free common case (identity)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv, self.source = pynvml, "nvml"
+        except Exception:
+            self.nv = None
         self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _sample_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        r = int(get(self.h))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self.reasons |= {k for k, v in bits.items() if r & v}
+
+    def _sample_smi(self):
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                           capture_output=True, text=True, timeout=5).stdout.strip()
+        if o:
+            r = [x.strip() for x in o.split(",")]
+            if r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0]))
+            if r[1].replace(".", "").isdigit():
+                self.mx.append(float(r[1]))
+            self.reasons |= {self.NAMES[i] for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")}
 
     def _run(self):
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
-            time.sleep(0.1)
+                if self.nv is not None:
+                    self.nv, self.source = None, "nvidia-smi"
+            time.sleep(0.0005 if self.nv is not None else 0.1)
 
     def __enter__(self):
         self.t.start()
@@ -86,11 +121,8 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) >= 6 and r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def host_threads():
@@ -217,8 +249,15 @@ def main():
             step()
         e1.record(stream)
         ctx.synchronize()
+        launches = ctx.launches - l0
+        in_region = len(clocks.sm)
+        # a query takes milliseconds and K steps may take fewer: keep the same kernel running (untimed, after e1) until the
+        # sampler has seen the device under this load a few times
+        t_stop = time.perf_counter() + 0.5
+        while len(clocks.sm) < in_region + 5 and time.perf_counter() < t_stop:
+            step()
+            ctx.synchronize()
         barrier()
-    launches = ctx.launches - l0
     ms = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e9
@@ -226,6 +265,7 @@ def main():
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
     clk = clocks.summary()
+    clk["samples_in_timed_region"] = in_region
 
     # ---- e2e: host (pinned) buffers through the same public call -----------------------------------
     e2e = None
