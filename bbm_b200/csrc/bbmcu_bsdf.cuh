@@ -21,31 +21,6 @@ struct BsdfDesc
   float attrs[kMaxAttrs];
 };
 
-// ---- single lobe helpers ----------------------------------------------------------------------
-BBMCU_D Spec<float> lobe_eval(int model, const float* a, f3 in, f3 out, int component)
-{
-  Spec<float> r(0.0f);
-  dispatch_model(model, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::template eval<float>(in, out, a, component); });
-  return r;
-}
-BBMCU_D float lobe_pdf(int model, const float* a, f3 in, f3 out, int component)
-{
-  float r = 0.0f;
-  dispatch_model(model, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::pdf(in, out, a, component); });
-  return r;
-}
-BBMCU_D Spec<float> lobe_reflectance(int model, const float* a, f3 out, int component)
-{
-  Spec<float> r(0.0f);
-  dispatch_model(model, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; r = M::reflectance(out, a, component); });
-  return r;
-}
-BBMCU_D void lobe_sample(int model, const float* a, f3 out, f2 xi, int component, f3& dir, float& pdfv, int& flag)
-{
-  dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
-  dispatch_model(model, [&](auto* tag) { using M = typename std::remove_pointer<decltype(tag)>::type; M::sample(out, xi, a, component, dir, pdfv, flag); });
-}
-
 // ---- lobe lists ---------------------------------------------------------------------------------
 // How lobe l of a descriptor reaches its model's code: through the switch over every model id (any BSDF string), or - for
 // the shape of every entry of the reference's fits/*.fit, Aggregate(M0, M1) - through a two-way branch between two models
