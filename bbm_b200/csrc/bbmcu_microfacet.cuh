@@ -679,7 +679,7 @@ struct Microfacet
     if(h.z < 0.0f) h = -h;
     return q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(dot(out, h)));
   }
-  // Walter's GGX has a hand-merged eval + pdf below; its fused kernel is launched 512 x 2 (64 registers, measured best)
+  // Walter's GGX has a hand-merged eval + pdf below
   static constexpr bool kHandFusedEvalPdf = std::is_same<NDF, NdfGGX<false>>::value && std::is_same<G, GUncorrelated>::value && std::is_same<F, FresnelCookIor>::value && NORM == 1;
   // eval and pdf of ONE direction pair sharing the half vector, D and G1 (the fused sample -> eval -> pdf pass).
   // in.z > 0 and out.z > 0 imply h.z > 0, so pdf's flip of h (microfacet.h:163) never triggers here.
