@@ -232,6 +232,12 @@ def test_loss_peer_exchange_two_shards_one_device(ctx):
         assert np.allclose(got[:, 0], lw, rtol=2e-6) and np.allclose(got[:, 1:], gw, rtol=2e-5, atol=1e-7*np.abs(gw).max())
     with pytest.raises(bb.BbmInvalidArgument):
         A.eval_device(fitted, np.repeat(params, 2, 0), torch.zeros((2*K, cols), dtype=torch.float64, device=dev))     # 10 rows > the 8-row window
+    with pytest.raises(bb.BbmInvalidArgument):
+        A.peer_init(0, 2, 8*cols)                                       # one window per loss
+    with pytest.raises(bb.BbmInvalidArgument):
+        whole.peer_init(2, 2, 8*cols)                                   # rank outside [0, world)
+    with pytest.raises(bb.BbmInvalidArgument):
+        whole.peer_connect_ptrs([wa, wb])                               # connect before init
 
 
 def test_pair_kernels_equal_runtime_lobe_list():
