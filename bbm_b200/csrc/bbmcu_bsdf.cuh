@@ -35,7 +35,7 @@ struct DispatchAll
 template<class M0, class M1>
 struct DispatchPair
 {
-  static constexpr int kMinBlocks = 2;
+  static constexpr int kMinBlocks = 3;                     // swept like the single-model kernels: 3 >= 2 = 1 (+0..18 %), fused Ward -1 %
   static constexpr int kLobes = 2;
   static constexpr bool kTables = false;                   // pairs with a He-family or measured lobe stay on the run-time path
   template<class F> BBMCU_D static void apply(const BsdfDesc&, int l, F&& f) { if(l == 0) f((M0*)nullptr); else f((M1*)nullptr); }

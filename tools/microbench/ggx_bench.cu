@@ -19,12 +19,17 @@ using namespace bbmcu;
 #define OP 2          // 0 eval, 1 sample, 2 sample + eval + pdf
 #endif
 using GGXM = ModelOf<MODEL>::type;
-#if OP == 0
-using Op = EvalOp<BsdfSingle<GGXM>>;
-#elif OP == 1
-using Op = SampleOp<BsdfSingle<GGXM>>;
+#ifdef PAIR            // Aggregate(Lambertian, MODEL) on the compile-time pair kernels
+using BsdfT = BsdfPair<Lambertian, GGXM>;
 #else
-using Op = SampleEvalPdfOp<BsdfSingle<GGXM>>;
+using BsdfT = BsdfSingle<GGXM>;
+#endif
+#if OP == 0
+using Op = EvalOp<BsdfT>;
+#elif OP == 1
+using Op = SampleOp<BsdfT>;
+#else
+using Op = SampleEvalPdfOp<BsdfT>;
 #endif
 __global__ void __launch_bounds__(BLOCK, MINB) k_var(const Op op, size_t groups)
 {
@@ -51,7 +56,14 @@ int main(int argc, char** argv)
   // default parameters of the model come from a file written by the host library (tools/microbench/defaults.py): "n v0 v1 ..."
   { float a[64] = {0.5f, 0.5f, 0.5f, 0.1f, 1.3f}; int na = 5;
     if(argc > 3) { FILE* f = fopen(argv[3], "r"); if(f) { if(fscanf(f, "%d", &na) == 1) for(int i=0; i < na && i < 64; ++i) if(fscanf(f, "%f", &a[i]) != 1) break; fclose(f); } }
-    memcpy(op.bsdf.attrs, a, sizeof(float)*na); op.bsdf.n_floats = na; }
+#ifdef PAIR
+    const float lam[3] = {0.2f, 0.1f, 0.05f};
+    memcpy(op.bsdf.attrs, lam, sizeof(lam)); memcpy(op.bsdf.attrs + 3, a, sizeof(float)*na); op.bsdf.n_floats = 3 + na;
+    op.bsdf.n_lobes = 2; op.bsdf.aggregate = 1; op.bsdf.model[0] = M_Lambertian; op.bsdf.model[1] = MODEL; op.bsdf.offset[0] = 0; op.bsdf.offset[1] = 3;
+#else
+    memcpy(op.bsdf.attrs, a, sizeof(float)*na); op.bsdf.n_floats = na;
+#endif
+  }
   op.component = 3; op.out = out; op.n = n; op.aligned = true;
 #if OP == 0
   op.in = dir; op.rgb = rgb; k_init<<<1184, 256>>>(dir, xi, n, 0x9e3779b9u);            // independent incident directions
