@@ -66,6 +66,12 @@ def lib():
         L.bbmcu_launch_count.argtypes = [C.c_void_p]
         L.bbmcu_loss_samples.restype = C.c_uint64
         L.bbmcu_loss_samples.argtypes = [C.c_void_p]
+        L.bbmcu_loss_shard_count.restype = C.c_uint64
+        L.bbmcu_loss_shard_count.argtypes = [C.c_void_p]
+        L.bbmcu_loss_materials.argtypes = [C.c_void_p]
+        L.bbmcu_set_plane_stride.argtypes = [C.c_void_p, C.c_size_t]
+        L.bbmcu_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.bbmcu_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
         for name in ("bbmcu_destroy", "bbmcu_bsdf_free", "bbmcu_loss_free", "bbmcu_fit_free"):
             getattr(L, name).restype = None
             getattr(L, name).argtypes = [C.c_void_p]
@@ -110,6 +116,27 @@ def _n(a, rows):
     if str(a.dtype) not in ("float32", "torch.float32"):
         raise BbmInvalidArgument(f"expected float32, got {a.dtype}")
     return shape[1]
+
+
+def _ld(a):
+    """plane stride in elements of a (rows, n) buffer: n when contiguous, larger for a column slice x[:, :n] of a padded
+    buffer (planes then start 16-byte aligned for any n, see bbmcu_set_plane_stride)"""
+    if hasattr(a, "data_ptr"):
+        st = a.stride()
+    else:
+        st = tuple(x // a.itemsize for x in a.strides)
+    if len(st) != 2 or st[1] != 1:
+        raise BbmInvalidArgument("planes of a struct-of-arrays buffer must be contiguous rows")
+    return int(st[0]) if a.shape[0] > 1 else int(a.shape[1])
+
+
+def _sptr(a):
+    """address of a (rows, n) buffer whose rows may be strided (see _ld)"""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
 
 
 def model_names():
@@ -242,17 +269,66 @@ class Context:
         _check(lib().bbmcu_sample(self._h, bsdf._h, component, unit, _ptr(out_xyz), _ptr(xi_uv), C.c_size_t(n), _ptr(d), _ptr(p), _ptr(f)), self._h)
         return d, p, f
 
-    def sample_eval_pdf(self, bsdf, out_xyz, xi_uv, component=ALL, unit=RADIANCE, outputs=None):
-        """s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)"""
+    OUTPUT_NAMES = ("dir", "sample_pdf", "flag", "rgb", "pdf")
+
+    def _sep_outputs(self, proto, n, outputs, want):
+        if outputs is None:
+            want = self.OUTPUT_NAMES if want is None else want
+            mk = {"dir": lambda: _like(proto, (3, n)), "sample_pdf": lambda: _like(proto, (n,)), "flag": lambda: _like(proto, (n,), np.int32),
+                  "rgb": lambda: _like(proto, (3, n)), "pdf": lambda: _like(proto, (n,))}
+            outputs = tuple(mk[k]() if k in want else None for k in self.OUTPUT_NAMES)
+        if all(o is None for o in outputs):
+            raise BbmInvalidArgument("at least one output is needed")
+        return outputs
+
+    def sample_eval_pdf(self, bsdf, out_xyz, xi_uv, component=ALL, unit=RADIANCE, outputs=None, want=None):
+        """s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out).
+        Returns (dir, sample_pdf, flag, rgb, pdf); entries not named in `want` (or None in `outputs`) are neither stored
+        nor copied back.  A column slice x[:, :n] of a padded buffer keeps 16-byte accesses for any n."""
         n = _n(out_xyz, 3)
         if _n(xi_uv, 2) != n:
             raise BbmInvalidArgument("out/xi batch sizes differ")
-        if outputs is None:
-            outputs = (_like(out_xyz, (3, n)), _like(out_xyz, (n,)), _like(out_xyz, (n,), np.int32), _like(out_xyz, (3, n)), _like(out_xyz, (n,)))
+        outputs = self._sep_outputs(out_xyz, n, outputs, want)
         d, sp, f, rgb, p = outputs
-        _check(lib().bbmcu_sample_eval_pdf(self._h, bsdf._h, component, unit, _ptr(out_xyz), _ptr(xi_uv), C.c_size_t(n),
-                                           _ptr(d), _ptr(sp), _ptr(f), _ptr(rgb), _ptr(p)), self._h)
+        ld = _ld(out_xyz)
+        if any(_ld(a) != ld for a in (xi_uv, d, rgb) if a is not None):
+            raise BbmInvalidArgument("all struct-of-arrays arguments of one call must share one plane stride")
+        if ld != n:
+            _check(lib().bbmcu_set_plane_stride(self._h, ld), self._h)
+        try:
+            _check(lib().bbmcu_sample_eval_pdf(self._h, bsdf._h, component, unit, _sptr(out_xyz), _sptr(xi_uv), C.c_size_t(n),
+                                               _sptr(d), _ptr(sp), _ptr(f), _sptr(rgb), _ptr(p)), self._h)
+        finally:
+            if ld != n:
+                lib().bbmcu_set_plane_stride(self._h, 0)
         return outputs
+
+    def sample_eval_pdf_generated(self, bsdf, seed, first, n, component=ALL, unit=RADIANCE, like=None, outputs=None, want=None, inputs=False):
+        """the same pass over inputs drawn on the device from (seed, first + i) - 0 bytes in.  Returns
+        (dir, sample_pdf, flag, rgb, pdf) and, with inputs=True, also the generated (out_xyz, xi_uv)."""
+        proto = like if like is not None else np.empty(0, np.float32)
+        outputs = self._sep_outputs(proto, n, outputs, want)
+        d, sp, f, rgb, p = outputs
+        go, gx = (_like(proto, (3, n)), _like(proto, (2, n))) if inputs is True else (inputs if inputs else (None, None))
+        _check(lib().bbmcu_sample_eval_pdf_generated(self._h, bsdf._h, component, unit, C.c_uint64(seed), C.c_uint64(first), C.c_size_t(n),
+                                                     _ptr(go), _ptr(gx), _ptr(d), _ptr(sp), _ptr(f), _ptr(rgb), _ptr(p)), self._h)
+        return (outputs, (go, gx)) if inputs else outputs
+
+    def eval_merl_grid(self, bsdf, first=0, n=MERL_BINS, component=ALL, unit=RADIANCE, like=None, rgb=None, dirs=False):
+        """eval at (in, out) = merl_linearizer(idx), idx = first .. first+n-1, directions generated inside the kernel
+        (0 B in, 12 B out per eval).  dirs=True also returns the generated (in, out) - bit-identical to merl_dirs()."""
+        proto = like if like is not None else (rgb if rgb is not None else np.empty(0, np.float32))
+        rgb = _like(proto, (3, n)) if rgb is None else rgb
+        i, o = (_like(proto, (3, n)), _like(proto, (3, n))) if dirs is True else (dirs if dirs else (None, None))
+        _check(lib().bbmcu_eval_merl_grid(self._h, bsdf._h, component, unit, C.c_uint32(first), C.c_size_t(n), _ptr(rgb), _ptr(i), _ptr(o)), self._h)
+        return (rgb, i, o) if dirs else rgb
+
+    def host_register(self, array):
+        """page-lock a numpy array once so the host-pointer path DMAs it in place (bbmcu_host_register)"""
+        _check(lib().bbmcu_host_register(self._h, C.c_void_p(array.ctypes.data), C.c_size_t(array.nbytes)), self._h)
+
+    def host_unregister(self, array):
+        _check(lib().bbmcu_host_unregister(self._h, C.c_void_p(array.ctypes.data)), self._h)
 
     # ---- linearizers ---------------------------------------------------------------------------
     def merl_index(self, in_xyz, out_xyz, index=None):
@@ -292,23 +368,31 @@ class Context:
         return t
 
     # ---- losses ------------------------------------------------------------------------------------
-    def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0):
-        return Loss(self, metric, reference, grid, component, unit, first, count)
+    def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False):
+        return Loss(self, metric, reference, grid, component, unit, first, count, materialise)
 
 
 class Loss:
     """a bbm::sampledlossfunction (include/bbm/sampledlossfunction.h:26-95) with one of the six error
-    functors of include/loss/*.h.  `reference` is a Bsdf or a (3, 1458000) measured MERL table."""
+    functors of include/loss/*.h.  `reference` is a Bsdf, a (3, 1458000) measured MERL table, or a LIST of such tables
+    (a batch of materials evaluated in one launch, see eval_multi).  By default the kernels generate the linearizer's
+    directions from the sample index; materialise=True keeps them as planes in device memory instead (same bits)."""
 
-    def __init__(self, ctx, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0):
+    def __init__(self, ctx, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False):
         self.ctx = ctx
         self._h = C.c_void_p()
         m = METRICS.index(metric) if isinstance(metric, str) else int(metric)
-        ref_b = reference._h if isinstance(reference, Bsdf) else None
-        ref_t = None if isinstance(reference, Bsdf) else _ptr(reference)
         self._keep = reference
-        _check(lib().bbmcu_loss_create(ctx._h, m, C.byref(grid) if grid is not None else None, component, unit, ref_b, ref_t,
-                                       C.c_uint64(first), C.c_uint64(count), C.byref(self._h)), ctx._h)
+        flags = 1 if materialise else 0
+        if isinstance(reference, Bsdf):
+            ref_b, tabs, M = reference._h, None, 1
+        else:
+            tables = list(reference) if isinstance(reference, (list, tuple)) else [reference]
+            M = len(tables)
+            tabs = (C.c_void_p * M)(*[_ptr(t) for t in tables])
+            ref_b = None
+        _check(lib().bbmcu_loss_create_ex(ctx._h, m, C.byref(grid) if grid is not None else None, component, unit, ref_b, tabs, C.c_int(M),
+                                          C.c_uint64(first), C.c_uint64(count), C.c_uint(flags), C.byref(self._h)), ctx._h)
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -382,9 +466,41 @@ class Loss:
         if not all(oks):
             raise err if err is not None else BbmError("a peer rank could not map the exchange windows")
 
-    def terms(self, bsdf, count):
-        t = np.empty(count, np.float32)
-        _check(lib().bbmcu_loss_terms(self._h, bsdf._h, _ptr(t)), self.ctx._h)
+    def shard_count(self):
+        return int(lib().bbmcu_loss_shard_count(self._h))
+
+    def materials(self):
+        return int(lib().bbmcu_loss_materials(self._h))
+
+    def set_metric(self, metric):
+        """switch the per-sample functor (the tabulated reference is metric independent): free"""
+        m = METRICS.index(metric) if isinstance(metric, str) else int(metric)
+        _check(lib().bbmcu_loss_set_metric(self._h, m), self.ctx._h)
+
+    def eval_multi(self, bsdf, params, grad=False):
+        """params (M, K, P): K parameter vectors for each of the M materials, ONE launch -> loss (M, K) [, gradient (M, K, P)]"""
+        P = len(bsdf.parameter_values())
+        params = np.ascontiguousarray(params, np.float64)
+        M = self.materials()
+        if params.ndim != 3 or params.shape[0] != M or params.shape[2] != P:
+            raise BbmInvalidArgument(f"expected parameters of shape ({M}, K, {P}), got {params.shape}")
+        K = params.shape[1]
+        loss = np.empty((M, K), np.float64)
+        g = np.empty((M, K, P), np.float64) if grad else None
+        _check(lib().bbmcu_loss_eval_multi(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(K), loss.ctypes.data_as(C.c_void_p),
+                                           g.ctypes.data_as(C.c_void_p) if grad else None, None), self.ctx._h)
+        return (loss, g) if grad else loss
+
+    def eval_multi_device(self, bsdf, params, device_out):
+        params = np.ascontiguousarray(params, np.float64)
+        _check(lib().bbmcu_loss_eval_multi(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(params.shape[1]), None, None,
+                                           _ptr(device_out)), self.ctx._h)
+
+    def terms(self, bsdf, count=None, material=0):
+        """per-sample terms l(idx) of this shard (sampledlossfunction::operator()(idx)); `count` is ignored (kept for
+        callers of the first version: the buffer is always sized from the shard)"""
+        t = np.empty(self.shard_count(), np.float32)
+        _check(lib().bbmcu_loss_terms_at(self._h, bsdf._h, C.c_int(material), _ptr(t)), self.ctx._h)
         return t
 
 

@@ -5,6 +5,8 @@
 #include <fstream>
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 
 #include "bbmcu_launch.cuh"
 
@@ -47,6 +49,29 @@ const float* epd_table_device(int device)
   return table[device];
 }
 
+// the separable merl_linearizer table (bbmcu_linearizer.cuh): 360 rows filled by the very device functions merl_dirs() uses
+__global__ void k_merl_lin_tab(float* tab) { const int j = blockIdx.x * blockDim.x + threadIdx.x; if(j < 360) merl_lin_tab_fill(tab, j); }
+const float* merl_lin_table_device(int device)
+{
+  static std::mutex mtx;
+  static float* table[64] = {};
+  std::lock_guard<std::mutex> lock(mtx);
+  if(device < 0 || device >= 64) throw std::invalid_argument("BBM: device index out of range");
+  if(!table[device])
+  {
+    int cur = 0; BBMCU_CUDA(cudaGetDevice(&cur));
+    BBMCU_CUDA(cudaSetDevice(device));
+    float* p = nullptr;
+    BBMCU_CUDA(cudaMalloc(&p, kMerlLinTabFloats*sizeof(float)));
+    k_merl_lin_tab<<<3, 128>>>(p);
+    BBMCU_CUDA(cudaGetLastError());
+    BBMCU_CUDA(cudaDeviceSynchronize());
+    BBMCU_CUDA(cudaSetDevice(cur));
+    table[device] = p;
+  }
+  return table[device];
+}
+
 // device copies of MERL tables: created on first use per device, released with the MerlData (its `release` hook)
 static void merl_release(int device, void* ptr)
 {
@@ -73,56 +98,145 @@ const float* merl_device_table(const bbmcu_host::MerlData& m, int device)
 
 namespace {
 
-struct ArrayArg { const void* ptr; int planes; bool input; };    // 4-byte elements, SoA planes of n
+struct ArrayArg { const void* ptr; int planes; bool input; };    // 4-byte elements, SoA planes; an OUTPUT pointer may be null (not wanted)
+
+enum class Mem { Device, Pinned, Pageable };
+Mem classify(const void* p)
+{
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if(e != cudaSuccess) { cudaGetLastError(); return Mem::Pageable; }
+  if(a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return Mem::Device;
+  return a.type == cudaMemoryTypeHost ? Mem::Pinned : Mem::Pageable;       // Host = cudaMallocHost / cudaHostRegister'ed
+}
 
 // classify the buffers of one call: all device (true) or all host (false); mixing is an error
-bool all_device(const std::vector<ArrayArg>& args)
+bool all_device(const std::vector<ArrayArg>& args, std::vector<Mem>& kind)
 {
   int dev = 0, host = 0;
-  for(auto& a : args) { if(!a.ptr) throw std::invalid_argument("BBM: null data pointer"); (is_device_pointer(a.ptr) ? dev : host)++; }
+  kind.assign(args.size(), Mem::Device);
+  for(size_t a=0; a < args.size(); ++a)
+  {
+    if(!args[a].ptr) { if(args[a].input) throw std::invalid_argument("BBM: null input pointer"); continue; }
+    kind[a] = classify(args[a].ptr);
+    (kind[a] == Mem::Device ? dev : host)++;
+  }
   if(dev && host) throw std::invalid_argument("BBM: data pointers of one call must be all host or all device memory");
+  if(!dev && !host) throw std::invalid_argument("BBM: every output pointer of the call is null");
   return dev > 0;
 }
 
 constexpr size_t kChunk = size_t(1) << 21;       // elements per host-pointer chunk
 
-// Host-pointer path: chunks of the batch flow through kSlots device staging buffers, each chunk's
-// H2D copies, kernel and D2H copies on its own stream so copies of one chunk overlap the kernel
-// and copies of its neighbours.  `launch(stream, device_pointers, chunk_n)` issues the kernel.
+// rows x bytes strided copy on `threads` host threads (pageable memory <-> pinned staging)
+void host_copy_rows(char* dst, size_t dst_pitch, const char* src, size_t src_pitch, size_t bytes, int rows, int threads)
+{
+  if(bytes * (size_t)rows < (size_t(1) << 20) || threads <= 1) { for(int r=0; r < rows; ++r) std::memcpy(dst + r*dst_pitch, src + r*src_pitch, bytes); return; }
+  std::vector<std::thread> pool;
+  const size_t per = ((bytes + threads - 1) / threads + 63) & ~size_t(63);
+  for(int t=0; t < threads; ++t)
+  {
+    const size_t b0 = (size_t)t*per; if(b0 >= bytes) break;
+    const size_t bn = std::min(per, bytes - b0);
+    pool.emplace_back([=] { for(int r=0; r < rows; ++r) std::memcpy(dst + r*dst_pitch + b0, src + r*src_pitch + b0, bn); });
+  }
+  for(auto& th : pool) th.join();
+}
+
+// Host-pointer path: chunks of the batch flow through kSlots device staging buffers, each chunk's H2D copies, kernel and
+// D2H copies on its own stream so copies of one chunk overlap the kernel and the copies of its neighbours.  Pinned /
+// registered caller memory is DMA'd in place; PAGEABLE caller memory goes through a pinned staging ring filled and
+// drained by a few host threads (cudaMemcpyAsync from pageable memory would serialise the whole pipeline).  The staging
+// planes are padded to a multiple of 4 floats, so the kernels keep their 16-byte accesses for any n.
+// `launch(stream, device_pointers, chunk_n)` issues the kernel; device pointers of null outputs are null.
 template<class Launch>
-void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, Launch&& launch)
+void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, const std::vector<Mem>& kind, Launch&& launch)
 {
   if(n == 0) return;
   const size_t cap = std::min(n, kChunk);
+  const size_t ld = (cap + 3) & ~size_t(3);                    // staging plane stride
+  const size_t user_ld = ctx->user_ld ? ctx->user_ld : n;      // the caller's plane stride
+  if(user_ld < n) throw std::invalid_argument("BBM: plane stride smaller than the batch");
   size_t need = 0;
+  bool any_pageable = false;
   std::vector<size_t> off(args.size());
-  for(size_t a=0; a < args.size(); ++a) { off[a] = need; need += ((size_t)args[a].planes * cap * 4 + 255) & ~size_t(255); }
+  for(size_t a=0; a < args.size(); ++a)
+  {
+    off[a] = need;
+    if(!args[a].ptr) continue;
+    need += ((size_t)args[a].planes * ld * 4 + 255) & ~size_t(255);
+    any_pageable |= (kind[a] == Mem::Pageable);
+  }
   if(need > ctx->slot_bytes)
   {
+    ctx->slot_bytes = 0;                                   // stays 0 if an allocation below throws: the next call re-allocates
     for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) BBMCU_CUDA(cudaFree(ctx->slot_buf[s])); ctx->slot_buf[s] = nullptr; }
     for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaMalloc(&ctx->slot_buf[s], need));
     ctx->slot_bytes = need;
   }
-  BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));          // order after earlier device-pointer work
-  size_t chunk_id = 0;
-  for(size_t c0 = 0; c0 < n; c0 += cap, ++chunk_id)
+  if(any_pageable && need > ctx->pin_bytes)
   {
-    const size_t cn = std::min(cap, n - c0);
-    const int s = (int)(chunk_id % bbmcu_ctx::kSlots);
-    cudaStream_t st = ctx->slot_stream[s];                  // in-order reuse of the slot buffer
-    std::vector<void*> dptr(args.size());
-    for(size_t a=0; a < args.size(); ++a)
-    {
-      dptr[a] = (char*)ctx->slot_buf[s] + off[a];
-      if(args[a].input)
-        BBMCU_CUDA(cudaMemcpy2DAsync(dptr[a], cn*4, (const char*)args[a].ptr + c0*4, n*4, cn*4, args[a].planes, cudaMemcpyHostToDevice, st));
-    }
-    launch(st, dptr, cn);
-    for(size_t a=0; a < args.size(); ++a)
-      if(!args[a].input)
-        BBMCU_CUDA(cudaMemcpy2DAsync((char*)args[a].ptr + c0*4, n*4, dptr[a], cn*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
+    ctx->pin_bytes = 0;
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->pin_buf[s]) BBMCU_CUDA(cudaFreeHost(ctx->pin_buf[s])); ctx->pin_buf[s] = nullptr; }
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaMallocHost(&ctx->pin_buf[s], need));
+    ctx->pin_bytes = need;
   }
-  for(int s=0; s < bbmcu_ctx::kSlots; ++s) BBMCU_CUDA(cudaStreamSynchronize(ctx->slot_stream[s]));
+  const int threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));          // order after earlier device-pointer work
+  struct Pending { bool busy = false; size_t c0 = 0, cn = 0; } pending[bbmcu_ctx::kSlots];
+  // wait for the chunk that last used slot s and hand its pageable outputs to the caller
+  auto drain = [&](int s) {
+    if(!pending[s].busy) return;
+    BBMCU_CUDA(cudaStreamSynchronize(ctx->slot_stream[s]));
+    pending[s].busy = false;
+    for(size_t a=0; a < args.size(); ++a)
+      if(args[a].ptr && !args[a].input && kind[a] == Mem::Pageable)
+        host_copy_rows((char*)args[a].ptr + pending[s].c0*4, user_ld*4, (const char*)ctx->pin_buf[s] + off[a], ld*4, pending[s].cn*4, args[a].planes, threads);
+  };
+  const size_t saved_ld = ctx->ld;
+  ctx->ld = ld;
+  try
+  {
+    size_t chunk_id = 0;
+    for(size_t c0 = 0; c0 < n; c0 += cap, ++chunk_id)
+    {
+      const size_t cn = std::min(cap, n - c0);
+      const int s = (int)(chunk_id % bbmcu_ctx::kSlots);
+      cudaStream_t st = ctx->slot_stream[s];                  // in-order reuse of the slot buffer
+      if(any_pageable) drain(s);
+      std::vector<void*> dptr(args.size(), nullptr);
+      for(size_t a=0; a < args.size(); ++a)
+      {
+        if(!args[a].ptr) continue;
+        dptr[a] = (char*)ctx->slot_buf[s] + off[a];
+        if(!args[a].input) continue;
+        const char* src = (const char*)args[a].ptr + c0*4;
+        if(kind[a] == Mem::Pageable)
+        {
+          host_copy_rows((char*)ctx->pin_buf[s] + off[a], ld*4, src, user_ld*4, cn*4, args[a].planes, threads);
+          BBMCU_CUDA(cudaMemcpy2DAsync(dptr[a], ld*4, (const char*)ctx->pin_buf[s] + off[a], ld*4, cn*4, args[a].planes, cudaMemcpyHostToDevice, st));
+        }
+        else BBMCU_CUDA(cudaMemcpy2DAsync(dptr[a], ld*4, src, user_ld*4, cn*4, args[a].planes, cudaMemcpyHostToDevice, st));
+      }
+      launch(st, dptr, cn);
+      for(size_t a=0; a < args.size(); ++a)
+      {
+        if(!args[a].ptr || args[a].input) continue;
+        if(kind[a] == Mem::Pageable) BBMCU_CUDA(cudaMemcpy2DAsync((char*)ctx->pin_buf[s] + off[a], ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
+        else BBMCU_CUDA(cudaMemcpy2DAsync((char*)args[a].ptr + c0*4, user_ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
+      }
+      pending[s].busy = true; pending[s].c0 = c0; pending[s].cn = cn;
+    }
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(any_pageable) drain(s); else BBMCU_CUDA(cudaStreamSynchronize(ctx->slot_stream[s])); }
+  }
+  catch(...)
+  {
+    // copies into the caller's memory may still be in flight: do not return before they have landed
+    for(int s=0; s < bbmcu_ctx::kSlots; ++s) cudaStreamSynchronize(ctx->slot_stream[s]);
+    ctx->ld = saved_ld;
+    throw;
+  }
+  ctx->ld = saved_ld;
 }
 
 template<class Launch>
@@ -130,13 +244,18 @@ void run_any(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, Launch
 {
   if(!ctx) throw std::invalid_argument("BBM: null context");
   BBMCU_CUDA(cudaSetDevice(ctx->device));
-  if(all_device(args))
+  std::vector<Mem> kind;
+  if(all_device(args, kind))
   {
     std::vector<void*> p(args.size());
     for(size_t a=0; a < args.size(); ++a) p[a] = const_cast<void*>(args[a].ptr);
-    launch(ctx->stream, p, n);
+    if(ctx->user_ld && ctx->user_ld < n) throw std::invalid_argument("BBM: plane stride smaller than the batch");
+    const size_t saved_ld = ctx->ld;
+    ctx->ld = ctx->user_ld;
+    try { launch(ctx->stream, p, n); } catch(...) { ctx->ld = saved_ld; throw; }
+    ctx->ld = saved_ld;
   }
-  else run_hosted(ctx, n, args, launch);
+  else run_hosted(ctx, n, args, kind, launch);
 }
 
 void check_flags(int component, int unit)
@@ -176,7 +295,7 @@ void bbmcu_destroy(bbmcu_ctx* ctx)
   if(!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]); if(ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]); }
+  for(int s=0; s < bbmcu_ctx::kSlots; ++s) { if(ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]); if(ctx->pin_buf[s]) cudaFreeHost(ctx->pin_buf[s]); if(ctx->slot_stream[s]) cudaStreamDestroy(ctx->slot_stream[s]); }
   if(ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -185,6 +304,19 @@ const char* bbmcu_last_error(bbmcu_ctx* ctx) { return ctx ? ctx->error.c_str() :
 int bbmcu_synchronize(bbmcu_ctx* ctx) { return guarded(ctx, [&] { if(!ctx) throw std::invalid_argument("BBM: null context"); BBMCU_CUDA(cudaStreamSynchronize(ctx->stream)); }); }
 void* bbmcu_stream(bbmcu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t bbmcu_launch_count(bbmcu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int bbmcu_set_plane_stride(bbmcu_ctx* ctx, size_t ld) { return guarded(ctx, [&] { if(!ctx) throw std::invalid_argument("BBM: null context"); ctx->user_ld = ld; }); }
+int bbmcu_host_register(bbmcu_ctx* ctx, void* ptr, size_t bytes)
+{
+  return guarded(ctx, [&] {
+    if(!ctx || !ptr || !bytes) throw std::invalid_argument("BBM: null argument");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BBMCU_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+  });
+}
+int bbmcu_host_unregister(bbmcu_ctx* ctx, void* ptr)
+{
+  return guarded(ctx, [&] { if(!ctx || !ptr) throw std::invalid_argument("BBM: null argument"); BBMCU_CUDA(cudaSetDevice(ctx->device)); BBMCU_CUDA(cudaHostUnregister(ptr)); });
+}
 
 // ---- registry -----------------------------------------------------------------------------------------
 int bbmcu_model_count(void) { return (int)bbmcu_host::model_table().size(); }
@@ -329,6 +461,42 @@ int bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component,
   });
 }
 
+int bbmcu_sample_eval_pdf_generated(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, uint64_t seed, uint64_t first, size_t n,
+                                    float* gen_out, float* gen_xi, float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
+    size_t done = 0;                                     // chunks arrive in order: the running element offset
+    run_any(ctx, n, {{gen_out, 3, false}, {gen_xi, 2, false}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}},
+            [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      GenArgs g; g.gen = 1; g.seed = seed; g.first = first + done; g.out = (float*)p[0]; g.xi = (float*)p[1];
+      launch_sample_eval_pdf(ctx, s, d, component, nullptr, nullptr, (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn, g);
+      done += cn; });
+  });
+}
+
+int bbmcu_eval_merl_grid(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit, uint32_t first, size_t n, float* rgb, float* in, float* out)
+{
+  return guarded(ctx, [&] {
+    if(!bsdf) throw std::invalid_argument("BBM: null bsdf");
+    check_flags(component, unit);
+    if(n == 0) return;
+    if(!ctx) throw std::invalid_argument("BBM: null context");
+    if((uint64_t)first + n > kMerlBins) throw std::out_of_range("BBM: bins beyond the MERL grid");
+    if(!rgb) throw std::invalid_argument("BBM: null output pointer");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    BsdfDesc d = make_desc(bsdf->b, ctx->device);
+    size_t done = 0;
+    run_any(ctx, n, {{rgb, 3, false}, {in, 3, false}, {out, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      launch_eval_grid(ctx, s, d, component, first + (uint32_t)done, (float*)p[0], (float*)p[1], (float*)p[2], cn); done += cn; });
+  });
+}
+
 // ---- linearizers ----------------------------------------------------------------------------------------
 int bbmcu_merl_index(bbmcu_ctx* ctx, const float* in, const float* out, size_t n, uint32_t* index)
 {
@@ -336,7 +504,7 @@ int bbmcu_merl_index(bbmcu_ctx* ctx, const float* in, const float* out, size_t n
     if(n == 0) return;
     run_any(ctx, n, {{in, 3, true}, {out, 3, true}, {index, 1, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       MerlIndexOp op; op.in = (const float*)p[0]; op.out = (const float*)p[1]; op.index = (uint32_t*)p[2]; op.n = cn;
-      op.aligned = aligned16(p[0]) && aligned16(p[1]) && aligned16(p[2]) && (cn % 4 == 0);
+      op.aligned = aligned16(p[0]) && aligned16(p[1]) && aligned16(p[2]);
       launch_foreach4(ctx, s, op, cn); });
   });
 }
@@ -348,7 +516,7 @@ int bbmcu_merl_dirs(bbmcu_ctx* ctx, uint32_t first, size_t n, float* in, float* 
     size_t done = 0;     // run_any hands out consecutive chunks; track the running first index
     run_any(ctx, n, {{in, 3, false}, {out, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       MerlDirsOp op; op.first = first + (uint32_t)done; op.in = (float*)p[0]; op.out = (float*)p[1]; op.n = cn;
-      op.aligned = aligned16(p[0]) && aligned16(p[1]) && (cn % 4 == 0);
+      op.aligned = aligned16(p[0]) && aligned16(p[1]);
       launch_foreach4(ctx, s, op, cn); done += cn; });
   });
 }
@@ -387,7 +555,7 @@ int bbmcu_spherical_dirs(bbmcu_ctx* ctx, const bbmcu_spherical_grid* grid, uint6
     size_t done = 0;
     run_any(ctx, n, {{in, 3, false}, {out, 3, false}}, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       SphericalDirsOp op; op.grid = g; op.first = first + done; op.in = (float*)p[0]; op.out = (float*)p[1]; op.n = cn;
-      op.aligned = aligned16(p[0]) && aligned16(p[1]) && (cn % 4 == 0);
+      op.aligned = aligned16(p[0]) && aligned16(p[1]);
       launch_foreach4(ctx, s, op, cn); done += cn; });
   });
 }

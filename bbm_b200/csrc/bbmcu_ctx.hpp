@@ -19,6 +19,12 @@ struct bbmcu_ctx
   cudaStream_t slot_stream[kSlots] = {};           // host-pointer chunks round-robin here
   void* slot_buf[kSlots] = {};                     // device staging, one per slot
   size_t slot_bytes = 0;
+  // plane stride (floats) of SoA arguments: `ld` is what the kernels launched right now use (0 = n), `user_ld` what
+  // bbmcu_set_plane_stride asked for (device and host pointers of the caller)
+  size_t ld = 0, user_ld = 0;
+  void* pin_buf[kSlots] = {};                      // pinned staging for PAGEABLE host memory, one per slot
+  size_t pin_bytes = 0;
+  cudaEvent_t slot_done[kSlots] = {};              // recorded after the last D2H of the chunk in the slot
   std::string error;
   uint64_t launches = 0;
 };

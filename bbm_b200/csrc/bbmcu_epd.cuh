@@ -316,7 +316,7 @@ struct NdfEPD
   {
     if(!xi_valid(xi)) return make_f3(0, 0, 0);
     float ph = kTwoPi * xi.x;
-    float cp = cosf(ph), sp = sinf(ph);
+    float cp, sp; glibc_sincosf_both(ph, sp, cp);              // the host libm's sinf / cosf restated (bbmcu_libm.cuh)
     float inv_p = 1.0f / a[1];
     float tan2 = a[0]*a[0] * powf(epd_gamma_q_inv(inv_p, xi.y), inv_p);
     float cosT = (float)(1.0 / sqrt(1.0 + (double)tan2));

@@ -50,6 +50,14 @@ BBMCU_D double he_exp(double x)
 #endif
 }
 
+// erfc and the double exp of the series, by tier.  STRICT is the path of the sampling CDF (backscatter below): the
+// reference's CDF entries must come out bit for bit, or a xi within an ulp of an entry picks the neighbouring bin and the
+// sampled direction jumps by a bin width (5e-6 of all samples before).  There erfc is the host libm's erfcf restated
+// (bbmcu_libm.cuh), exp the true double exp, and the series keeps the reference's divisions.
+template<bool STRICT> BBMCU_D float he_erfc(float a) { return STRICT ? glibc_erfcf(a) : erfcf(a); }
+template<bool STRICT, int N> BBMCU_D Dual<N> he_erfc(const Dual<N>& a) { return m_erfc(a); }
+template<bool STRICT> BBMCU_D double he_exp_t(double x) { return STRICT ? exp(x) : he_exp(x); }
+
 template<int V> struct HeTraits;
 template<> struct HeTraits<HE_VARIANT_HE>         { static constexpr bool ERRATA = false, WESTIN = false, ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
 template<> struct HeTraits<HE_VARIANT_WESTIN>     { static constexpr bool ERRATA = true,  WESTIN = true,  ADAPTIVE = true,  ROUGH = true,  SCALED = false; static constexpr int TERMS = 64; using F = FresnelComplexRGB; };
@@ -69,13 +77,13 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
   static constexpr int NT = kHeCdfBins;                  // device-side CDF appended to the attribute block
 
   // ---- Eq. 24-25: mono-directional shadowing ---------------------------------------------------------
-  template<class T> BBMCU_D static T S1(f3 v, const T& rough, const T& tau)
+  template<class T, bool STRICT = false> BBMCU_D static T S1(f3 v, const T& rough, const T& tau)
   {
     using W = typename WideOf<T>::type;
     if(val(rough) < kEps) return T(1.0f);
     float cot = 1.0f / tanTheta(v);
     T scaledCot = he_narrow(he_wide(tau * cot) / (he_wide(rough) * 2.0f));
-    T erfcv = he_narrow(he_wide(m_erfc(scaledCot)) * 0.5f);
+    T erfcv = he_narrow(he_wide(he_erfc<STRICT>(scaledCot)) * 0.5f);
     T Lambda = he_narrow((W)(0.5f * he_wide(T(kInvSqrtPi))) / he_wide(scaledCot));
     if(Tr::ERRATA) { W s = he_wide(scaledCot); Lambda = he_narrow(he_wide(Lambda) * m_exp(-(s*s))); }
     Lambda = Lambda - erfcv;
@@ -99,13 +107,13 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
   }
 
   // ---- Eq. 80: apparent roughness, Newton-Raphson ------------------------------------------------------
-  template<class T> BBMCU_D static T sigma(f3 in, f3 out, const T& rough, const T& tau)
+  template<class T, bool STRICT = false> BBMCU_D static T sigma(f3 in, f3 out, const T& rough, const T& tau)
   {
     using W = typename WideOf<T>::type;
     if(!(val(rough) > kEps)) return T(0.0f);
     float ti = tanTheta(in), to = tanTheta(out);
-    T Ki = (ti > kEps) ? ti * m_erfc(tau / (2.0f * rough * ti)) : T(0.0f);
-    T Ko = (to > kEps) ? to * m_erfc(tau / (2.0f * rough * to)) : T(0.0f);
+    T Ki = (ti > kEps) ? ti * he_erfc<STRICT>(tau / (2.0f * rough * ti)) : T(0.0f);
+    T Ko = (to > kEps) ? to * he_erfc<STRICT>(tau / (2.0f * rough * to)) : T(0.0f);
     const float rs8pi = 1.0f / sqrtf((float)(8.0 * kPiD));
     T f0 = rs8pi * (Ki + Ko);
     T x = (val(f0) <= 1.0f) ? f0 : he_narrow(m_safe_sqrt(2.0f * he_wide(m_log(f0))));
@@ -129,13 +137,13 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
     float x = a + t*(b - a);
     return ((t > 1.0f) == (b > a)) ? (b < x ? x : b) : (b > x ? x : b);
   }
-  BBMCU_D static Spec<float> D(f3 in, f3 out, const float& rough, const float& tau)
+  template<bool STRICT = false> BBMCU_D static Spec<float> D(f3 in, f3 out, const float& rough, const float& tau)
   {
     const float wl[3] = {0.645f, 0.526f, 0.444f};            // floatRGB wavelengths (backbone/native/include/backbone.h:36)
     const float thr = Tr::ROUGH ? 18.0f : 3.402823466e+38f;
     float sx = in.x + out.x, sy = in.y + out.y;
     float v_xy2 = sx*sx + sy*sy;
-    float base = kTwoPi * sigma<float>(in, out, rough, tau) * (in.z + out.z);
+    float base = kTwoPi * sigma<float, STRICT>(in, out, rough, tau) * (in.z + out.z);
     float tau2 = (float)((double)tau * (double)tau);
     const float pi2q = (0.25f * kPi) * kPi, pi2x4 = (4.0f * kPi) * kPi;
     double g[3], nrm[3]; float eb[3];
@@ -169,8 +177,16 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
 #pragma unroll
       for(int c=0; c < 3; ++c)
       {
-        gm[c] = (float)((double)gm[c] * (g[c] * inv_m));
-        term[c] = (float)(he_exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] * inv_m);
+        if(STRICT)
+        {
+          gm[c] = (float)((double)gm[c] * (g[c] / (double)m));                                    // gm *= g / m   (he.h:450)
+          term[c] = (float)(exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] / (double)m);  // he.h:451
+        }
+        else
+        {
+          gm[c] = (float)((double)gm[c] * (g[c] * inv_m));
+          term[c] = (float)(he_exp(-g[c] - (double)(eb[c] / (float)m)) * (double)gm[c] * inv_m);
+        }
         sum[c] += term[c];
       }
       tmin = term[0]; if(term[1] < tmin) tmin = term[1]; if(term[2] < tmin) tmin = term[2];      // std::min_element order
@@ -181,7 +197,7 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
                        (float)(nrm[2] * (double)lerpf(sum[2], ra[2], weight)));
   }
   // derivative-carrying version (float arithmetic; same control flow, decided on the values)
-  template<int N> BBMCU_D static Spec<Dual<N>> D(f3 in, f3 out, const Dual<N>& rough, const Dual<N>& tau)
+  template<bool STRICT = false, int N> BBMCU_D static Spec<Dual<N>> D(f3 in, f3 out, const Dual<N>& rough, const Dual<N>& tau)
   {
     using T = Dual<N>;
     const float wl[3] = {0.645f, 0.526f, 0.444f};
@@ -235,13 +251,13 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
   }
 
   // ---- the BSDF concept ----------------------------------------------------------------------------------
-  template<class T> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
+  template<class T, bool STRICT = false> BBMCU_D static Spec<T> eval_unscaled(f3 in, f3 out, const T* a, int component)
   {
     if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<T>(T(0.0f));
     const T& rough = a[OFF_R]; const T& tau = a[OFF_R + 1];
-    T S = S1<T>(in, rough, tau) * S1<T>(out, rough, tau);
+    T S = S1<T, STRICT>(in, rough, tau) * S1<T, STRICT>(out, rough, tau);
     float Gt = G(in, out);
-    Spec<T> Dt = D(in, out, rough, tau);
+    Spec<T> Dt = D<STRICT>(in, out, rough, tau);
     float cosHalf = (float)safe_sqrt_d((double)(1.0f + dot(in, out)) / 2.0);
     Spec<T> Ft = to_spec(F::template eval<T>(a + OFF_F, cosHalf));
     float nrm = 1.0f / (kPi * in.z * out.z);
@@ -263,7 +279,7 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
   }
 
   // ---- data-driven sampling: ndf::sampler over the back-scatter of the UNSCALED model (bbmcu_ndfsampler.cuh) ----------
-  BBMCU_D static float backscatter(const float* a, int component, f3 h) { return hsum(eval_unscaled<float>(h, h, a, component)); }
+  BBMCU_D static float backscatter(const float* a, int component, f3 h) { return hsum(eval_unscaled<float, true>(h, h, a, component)); }
 };
 
 } // namespace bbmcu

@@ -47,21 +47,61 @@ BBMCU_D void store4i(int32_t* p, size_t i, size_t n, bool aligned, const int (&r
   for(int k=0; k < kVec; ++k) if(i + k < n) p[i + k] = r[k];
 }
 struct Lanes3 { Lanes x, y, z; BBMCU_D f3 get(int k) const { return make_f3(x.v[k], y.v[k], z.v[k]); } BBMCU_D void set(int k, f3 a) { x.v[k] = a.x; y.v[k] = a.y; z.v[k] = a.z; } };
-BBMCU_D Lanes3 load4x3(const float* p, size_t i, size_t n, bool aligned) { Lanes3 r; r.x = load4(p, i, n, aligned); r.y = load4(p + n, i, n, aligned); r.z = load4(p + 2*n, i, n, aligned); return r; }
-BBMCU_D void store4x3(float* p, size_t i, size_t n, bool aligned, const Lanes3& r) { store4(p, i, n, aligned, r.x); store4(p + n, i, n, aligned, r.y); store4(p + 2*n, i, n, aligned, r.z); }
+BBMCU_D Lanes3 load4x3(const float* p, size_t i, size_t n, size_t ld, bool aligned) { Lanes3 r; r.x = load4(p, i, n, aligned); r.y = load4(p + ld, i, n, aligned); r.z = load4(p + 2*ld, i, n, aligned); return r; }
+BBMCU_D void store4x3(float* p, size_t i, size_t n, size_t ld, bool aligned, const Lanes3& r) { store4(p, i, n, aligned, r.x); store4(p + ld, i, n, aligned, r.y); store4(p + 2*ld, i, n, aligned, r.z); }
+
+// ---- counter-based inputs: Philox4x32-10 (Salmon et al. 2011) ---------------------------------------------------------
+// One call per element index gives four 32-bit words: the outgoing direction (uniform on the upper hemisphere, as
+// bin/checkBsdf.cpp:38-45 sampleHemisphere draws it: cos theta = u0, phi = 2 pi u1) and the two random numbers xi of
+// sample().  Every kernel that takes "generated" inputs calls this one function, so a batch is a pure function of
+// (seed, first index): the oracle side of the parity tests asks the library to write the inputs out and reads those.
+struct GenInputs { f3 out; f2 xi; };
+BBMCU_D uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+BBMCU_D void philox4x32_10(uint64_t counter, uint64_t seed, uint32_t (&r)[4])
+{
+  uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = 0x9E3779B9u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for(int round=0; round < 10; ++round)
+  {
+    const uint32_t h0 = mulhi32(0xD2511F53u, c0), l0 = 0xD2511F53u * c0, h1 = mulhi32(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  r[0] = c0; r[1] = c1; r[2] = c2; r[3] = c3;
+}
+BBMCU_D float u01(uint32_t u) { return (float)(u >> 8) * 0x1p-24f; }          // [0, 1), exact in float
+BBMCU_D GenInputs generate_inputs(uint64_t seed, uint64_t index)
+{
+  uint32_t r[4];
+  philox4x32_10(index, seed, r);
+  GenInputs g;
+  const float z = u01(r[0]), ph = u01(r[1]) * kTwoPi;
+  const float st = sqrtf(fmaxf(1.0f - z*z, 0.0f));
+  float sp, cp; glibc_sincosf_both(ph, sp, cp);
+  g.out = make_f3(st*cp, st*sp, z);
+  g.xi = make_f2(u01(r[2]), u01(r[3]));
+  return g;
+}
 
 // ---- operators --------------------------------------------------------------------------------------
 template<class B> struct EvalOp
 {
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;     // eval never reads the sampling tables
-  BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned;
+  BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
-    Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned), r;
+    Lanes3 a = load4x3(in, i, n, ld, aligned), b = load4x3(out, i, n, ld, aligned), r;
 #pragma unroll
     for(int k=0; k < kVec; ++k) { Spec<float> s = B::eval(bsdf, a.get(k), b.get(k), component); r.set(k, make_f3(s.r, s.g, s.b)); }
-    store4x3(rgb, i, n, aligned, r);
+    store4x3(rgb, i, n, ld, aligned, r);
   }
 };
 
@@ -70,10 +110,10 @@ template<class B> struct PdfOp
   static constexpr bool kOneWaveWithTables = true;            // cheap body: pay the CDF prologue once per SM slot (bbmcu_launch.cuh)
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
-  BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned;
+  BsdfDesc bsdf; int component; const float* in; const float* out; float* pdf; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
-    Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned); Lanes r;
+    Lanes3 a = load4x3(in, i, n, ld, aligned), b = load4x3(out, i, n, ld, aligned); Lanes r;
 #pragma unroll
     for(int k=0; k < kVec; ++k) r.v[k] = B::pdf(bsdf, a.get(k), b.get(k), component);
     store4(pdf, i, n, aligned, r);
@@ -84,13 +124,13 @@ template<class B> struct ReflectanceOp
 {
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;
-  BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned;
+  BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
-    Lanes3 b = load4x3(out, i, n, aligned), r;
+    Lanes3 b = load4x3(out, i, n, ld, aligned), r;
 #pragma unroll
     for(int k=0; k < kVec; ++k) { Spec<float> s = B::reflectance(bsdf, b.get(k), component); r.set(k, make_f3(s.r, s.g, s.b)); }
-    store4x3(rgb, i, n, aligned, r);
+    store4x3(rgb, i, n, ld, aligned, r);
   }
 };
 
@@ -99,26 +139,38 @@ template<class B> struct SampleOp
   static constexpr bool kOneWaveWithTables = true;
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
-  BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned;
+  BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* pdf; int32_t* flag; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
-    Lanes3 b = load4x3(out, i, n, aligned), d; Lanes u = load4(xi, i, n, aligned), v = load4(xi + n, i, n, aligned), p; int f[kVec];
+    Lanes3 b = load4x3(out, i, n, ld, aligned), d; Lanes u = load4(xi, i, n, aligned), v = load4(xi + ld, i, n, aligned), p; int f[kVec];
 #pragma unroll
     for(int k=0; k < kVec; ++k) { f3 dd; B::sample(bsdf, b.get(k), make_f2(u.v[k], v.v[k]), component, dd, p.v[k], f[k]); d.set(k, dd); }
-    store4x3(dir, i, n, aligned, d); store4(pdf, i, n, aligned, p); store4i(flag, i, n, aligned, f);
+    store4x3(dir, i, n, ld, aligned, d); store4(pdf, i, n, aligned, p); store4i(flag, i, n, aligned, f);
   }
 };
 
 // s = sample(out, xi); rgb = eval(s.direction, out); pdf = pdf(s.direction, out)   (20 B in, 36 B out per element)
-template<class B> struct SampleEvalPdfOp
+// Any OUTPUT pointer may be null: that plane is neither stored nor (host path) copied back.  Inputs are read from
+// `out` / `xi`, or - gen != 0 - drawn per element from generate_inputs(gen_seed, gen_first + i) (0 B in); the generated
+// inputs are written to `gen_out` / `gen_xi` when those are given.
+template<class B, bool GEN> struct SampleEvalPdfOpT
 {
   static constexpr bool kOneWaveWithTables = false;           // dominated by the model's eval, whose cost varies per element: keep many blocks for balance
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocksFused;     // (the hand-merged GGX kernel: 256 x 3 with 4736 blocks 94.6 G pairs/s, 256 x 4 94.1, 512 x 2 92.9, 128 x 8 93.1, 1024 x 1 91.3)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
-  BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned;
+  BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
+  uint64_t gen_seed = 0, gen_first = 0; float* gen_out = nullptr; float* gen_xi = nullptr;       // GEN only
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
   {
-    Lanes3 b = load4x3(out, i, n, aligned), d, c; Lanes u = load4(xi, i, n, aligned), v = load4(xi + n, i, n, aligned), sp, p; int f[kVec];
+    Lanes3 b, d, c; Lanes u, v, sp, p; int f[kVec];
+    if constexpr (GEN)
+    {
+#pragma unroll
+      for(int k=0; k < kVec; ++k) { GenInputs g = generate_inputs(gen_seed, gen_first + i + k); b.set(k, g.out); u.v[k] = g.xi.x; v.v[k] = g.xi.y; }
+      if(gen_out) store4x3(gen_out, i, n, ld, aligned, b);
+      if(gen_xi) { store4(gen_xi, i, n, aligned, u); store4(gen_xi + ld, i, n, aligned, v); }
+    }
+    else { b = load4x3(out, i, n, ld, aligned); u = load4(xi, i, n, aligned); v = load4(xi + ld, i, n, aligned); }
 #pragma unroll
     for(int k=0; k < kVec; ++k)
     {
@@ -146,8 +198,39 @@ template<class B> struct SampleEvalPdfOp
       }
       d.set(k, dd); c.set(k, make_f3(s.r, s.g, s.b));
     }
-    store4x3(dir, i, n, aligned, d); store4(spdf, i, n, aligned, sp); store4i(flag, i, n, aligned, f);
-    store4x3(rgb, i, n, aligned, c); store4(pdf, i, n, aligned, p);
+    if(dir) store4x3(dir, i, n, ld, aligned, d);
+    if(spdf) store4(spdf, i, n, aligned, sp);
+    if(flag) store4i(flag, i, n, aligned, f);
+    if(rgb) store4x3(rgb, i, n, ld, aligned, c);
+    if(pdf) store4(pdf, i, n, aligned, p);
+  }
+};
+
+template<class B> using SampleEvalPdfOp = SampleEvalPdfOpT<B, false>;
+template<class B> using SampleEvalPdfGenOp = SampleEvalPdfOpT<B, true>;      // inputs drawn in the kernel (0 B in)
+
+// eval over the MERL grid with the linearizer fused: element i is bin first + i, its direction pair comes from the
+// separable table in shared memory (bit-identical to MerlDirsOp), 0 B in + 12 B out per eval.
+// `in` / `out` (optional) receive the generated directions - the parity protocol of SURVEY.md section 7.
+template<class B> struct EvalGridOp
+{
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
+  static constexpr bool kHasBsdf = true, kTables = false, kLinTab = true;
+  BsdfDesc bsdf; int component; const float* lin_tab; uint32_t first; float* rgb; float* in; float* out; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf, const float* s_lin) const
+  {
+    Lanes3 a, b, r;
+#pragma unroll
+    for(int k=0; k < kVec; ++k)
+    {
+      f3 x, y;
+      merl_dirs_tab(s_lin, (i + k < n) ? first + (uint32_t)(i + k) : first, x, y);
+      Spec<float> s = B::eval(bsdf, x, y, component);
+      a.set(k, x); b.set(k, y); r.set(k, make_f3(s.r, s.g, s.b));
+    }
+    store4x3(rgb, i, n, ld, aligned, r);
+    if(in) store4x3(in, i, n, ld, aligned, a);
+    if(out) store4x3(out, i, n, ld, aligned, b);
   }
 };
 
@@ -155,10 +238,10 @@ struct MerlIndexOp
 {
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
-  const float* in; const float* out; uint32_t* index; size_t n; bool aligned;
+  const float* in; const float* out; uint32_t* index; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i) const
   {
-    Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned); int r[kVec];
+    Lanes3 a = load4x3(in, i, n, ld, aligned), b = load4x3(out, i, n, ld, aligned); int r[kVec];
 #pragma unroll
     for(int k=0; k < kVec; ++k) r[k] = (int)merl_index(a.get(k), b.get(k));
     store4i(reinterpret_cast<int32_t*>(index), i, n, aligned, r);
@@ -169,13 +252,13 @@ struct MerlDirsOp
 {
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
-  uint32_t first; float* in; float* out; size_t n; bool aligned;
+  uint32_t first; float* in; float* out; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i) const
   {
     Lanes3 a, b;
 #pragma unroll
     for(int k=0; k < kVec; ++k) { f3 x, y; merl_dirs(first + (uint32_t)(i + k), x, y); a.set(k, x); b.set(k, y); }
-    store4x3(in, i, n, aligned, a); store4x3(out, i, n, aligned, b);
+    store4x3(in, i, n, ld, aligned, a); store4x3(out, i, n, ld, aligned, b);
   }
 };
 
@@ -183,13 +266,13 @@ struct SphericalDirsOp
 {
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
-  SphericalGrid grid; uint64_t first; float* in; float* out; size_t n; bool aligned;
+  SphericalGrid grid; uint64_t first; float* in; float* out; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i) const
   {
     Lanes3 a, b;
 #pragma unroll
     for(int k=0; k < kVec; ++k) { f3 x, y; spherical_dirs(grid, first + i + k, x, y); a.set(k, x); b.set(k, y); }
-    store4x3(in, i, n, aligned, a); store4x3(out, i, n, aligned, b);
+    store4x3(in, i, n, ld, aligned, a); store4x3(out, i, n, ld, aligned, b);
   }
 };
 
@@ -198,10 +281,10 @@ struct MerlLookupOp
 {
   static constexpr int kBlock = 256, kMinBlocks = 1;
   static constexpr bool kHasBsdf = false, kTables = false;
-  const float* table; const float* in; const float* out; float* rgb; uint32_t* bad; size_t n; bool aligned;
+  const float* table; const float* in; const float* out; float* rgb; uint32_t* bad; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   BBMCU_D void group(size_t i) const
   {
-    Lanes3 a = load4x3(in, i, n, aligned), b = load4x3(out, i, n, aligned), r;
+    Lanes3 a = load4x3(in, i, n, ld, aligned), b = load4x3(out, i, n, ld, aligned), r;
 #pragma unroll
     for(int k=0; k < kVec; ++k)
     {
@@ -220,15 +303,28 @@ struct MerlLookupOp
       }
       r.set(k, s);
     }
-    store4x3(rgb, i, n, aligned, r);
+    store4x3(rgb, i, n, ld, aligned, r);
   }
 };
 
+template<class Op, class = void> struct UsesLinTab { static constexpr bool value = false; };
+template<class Op> struct UsesLinTab<Op, typename std::enable_if<Op::kLinTab>::type> { static constexpr bool value = true; };
+
 #ifdef __CUDACC__
+// the separable merl_linearizer table of this device (bbmcu_linearizer.cuh), built once by k_merl_lin_tab
+__global__ void k_merl_lin_tab(float* tab);
+
 template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks) k_foreach4(const Op op, size_t groups)
 {
   const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   if constexpr (!Op::kHasBsdf) { for(size_t g = first; g < groups; g += stride) op.group(g * kVec); }
+  else if constexpr (UsesLinTab<Op>::value)
+  {
+    __shared__ float s_lin[kMerlLinTabFloats];
+    for(int i = threadIdx.x; i < kMerlLinTabFloats; i += blockDim.x) s_lin[i] = __ldg(op.lin_tab + i);
+    __syncthreads();
+    for(size_t g = first; g < groups; g += stride) op.group(g * kVec, op.bsdf, s_lin);
+  }
   else
   {
     if constexpr (Op::kTables)

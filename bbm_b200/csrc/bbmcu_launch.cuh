@@ -11,9 +11,15 @@ namespace bbmcu {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // internal linkage: every translation unit keeps its own copy next to its own device symbols (bbmcu_tables.cuh)
-template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, const Op& op, size_t n)
+template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stream, const Op& op_in, size_t n)
 {
   if(n == 0) return;
+  Op op = op_in;
+  // planes of an SoA argument are n floats apart unless the context says otherwise (bbmcu_set_plane_stride; the host-pointer
+  // path stages with a padded stride).  16-byte vector access needs every plane start aligned: callers check the base
+  // pointers, the stride is checked here - so a batch of 2^26 + 1 elements keeps its vector loads when the planes are padded.
+  op.ld = ctx->ld ? ctx->ld : op.n;
+  if(op.ld % 4 != 0) op.aligned = false;
   size_t groups = (n + kVec - 1) / kVec;
   bind_device_tables();
   unsigned grid = grid_for(ctx, groups, Op::kBlock, 8*256/Op::kBlock);
@@ -81,8 +87,13 @@ static bool launch_pair_op(bbmcu_ctx* ctx, cudaStream_t stream, const BsdfDesc& 
 bool launch_pair_eval(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* rgb, size_t n, bool aligned);
 bool launch_pair_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* pdf, size_t n, bool aligned);
 bool launch_pair_sample(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi, float* dir, float* pdf, int32_t* flag, size_t n, bool aligned);
+// generated inputs of the fused pass (SampleEvalPdfOp): gen != 0 draws (out, xi) of element i from (seed, first + i)
+struct GenArgs { int gen = 0; uint64_t seed = 0, first = 0; float* out = nullptr; float* xi = nullptr; };
 bool launch_pair_sample_eval_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
                                  float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n, bool aligned);
+void launch_sample_eval_pdf_gen(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component,
+                                float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n, bool aligned, const GenArgs& g);
+bool launch_pair_eval_grid(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* lin_tab, uint32_t first, float* rgb, float* in, float* out, size_t n, bool aligned);
 
 // entry points implemented one per translation unit so the model instantiations compile in parallel
 void launch_eval(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* in, const float* out, float* rgb, size_t n);
@@ -90,6 +101,10 @@ void launch_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const 
 void launch_reflectance(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, float* rgb, size_t n);
 void launch_sample(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi, float* dir, float* pdf, int32_t* flag, size_t n);
 void launch_sample_eval_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
-                            float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n);
+                            float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n, const GenArgs& g = GenArgs());
+// eval over bins [first, first + n) of the MERL grid, directions generated in the kernel; in / out may be null
+void launch_eval_grid(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, uint32_t first, float* rgb, float* in, float* out, size_t n);
+// the device's separable merl_linearizer table (900 floats, built on first use, lives for the process)
+const float* merl_lin_table_device(int device);
 
 } // namespace bbmcu

@@ -303,4 +303,110 @@ BBMCU_D float glibc_erff(float x)
   return ((int32_t)hx >= 0) ? 1.0f - r / ax : r / ax - 1.0f;
 }
 
+// ---- glibc 2.39 tanf (sysdeps/ieee754/flt-32/s_tanf.c, k_tanf.c) and erfcf (fdlibm, s_erff.c) ---------------------------
+// Written from the published algorithms; both agree with the host glibc on EVERY float (erfcf: all 2^32 arguments;
+// tanf: every |x| <= 100) without a single differing bit (tools/libm_sweep.cpp; tests/test_linearizer_loss_hostsim.py
+// repeats a sample).  LowSmooth's sampler goes through tan and atan next to a cancelling E - 2, and the He family's
+// sampling CDF is built from erfc: a last-bit difference in either moved 5e-5 (LowSmooth) and 5e-6 (He: a xi within one
+// ulp of a CDF entry picks the neighbouring bin) of the sampled directions beyond the 1e-5 contract.
+BBMCU_D float glibc_kernel_tanf(float x, float y, int iy)
+{
+  const float pio4 = 7.8539812565e-01f, pio4lo = 3.7748947079e-08f;
+  const float T0 = u2f(0x3eaaaaab), T1 = u2f(0x3e088889), T2 = u2f(0x3d5d0dd1), T3 = u2f(0x3cb327a4), T4 = u2f(0x3c11371f), T5 = u2f(0x3b6b6916),
+              T6 = u2f(0x3abede48), T7 = u2f(0x3a1a26c8), T8 = u2f(0x398137b9), T9 = u2f(0x38a3f445), T10 = u2f(0x3895c07a), T11 = u2f(0xb79bae5f), T12 = u2f(0x37d95384);
+  int32_t hx = (int32_t)f2u(x), ix = hx & 0x7fffffff;
+  if(ix < 0x39000000) {                       /* |x| < 2**-13 */
+    if((int)x == 0) {
+      if((ix | (iy + 1)) == 0) return 1.0f / fabsf(x);
+      else if(iy == 1) return x;
+      else return -1.0f / x;
+    }
+  }
+  if(ix >= 0x3f2ca140) {                      /* |x| >= 0.6744 */
+    if(hx < 0) { x = -x; y = -y; }
+    float z = pio4 - x, w = pio4lo - y;
+    x = z + w; y = 0.0f;
+    if(fabsf(x) < 0x1p-13f) return (float)(1 - ((hx >> 30) & 2)) * (float)iy * (1.0f - 2.0f * (float)iy * x);
+  }
+  float z = x*x, w = z*z;
+  float r = T1 + w*(T3 + w*(T5 + w*(T7 + w*(T9 + w*T11))));
+  float v = z*(T2 + w*(T4 + w*(T6 + w*(T8 + w*(T10 + w*T12)))));
+  float s = z*x;
+  r = y + z*(s*(r + v) + y);
+  r += T0*s;
+  w = x + r;
+  if(ix >= 0x3f2ca140) {
+    v = (float)iy;
+    return (float)(1 - ((hx >> 30) & 2)) * (v - 2.0f*(x - (w*w/(w + v) - r)));
+  }
+  if(iy == 1) return w;
+  /* compute -1.0/(x+r) accurately */
+  float a, t;
+  z = u2f(f2u(w) & 0xfffff000u);
+  v = r - (z - x);
+  t = a = -1.0f / w;
+  t = u2f(f2u(t) & 0xfffff000u);
+  s = 1.0f + t*z;
+  return t + a*(s + t*v);
+}
+// glibc 2.39 tanf (sysdeps/ieee754/flt-32/s_tanf.c): |x| <= pi/4 goes straight to the kernel; otherwise the double-precision
+// quadrant reduction of sinf/cosf (n = round(x * 2/pi), x - n * pi/2 in double), the reduced argument split into a float
+// head and tail, and the fdlibm kernel with iy = +1 (n even) or -1 (n odd).  |x| < 120 (every caller passes an angle of a
+// few turns); the large-argument reduction is not restated.
+BBMCU_D float glibc_tanf(float x)
+{
+  int32_t ix = (int32_t)f2u(x) & 0x7fffffff;
+  if(ix <= 0x3f490fda) return glibc_kernel_tanf(x, 0.0f, 1);
+  if(ix >= 0x7f800000) return x - x;
+  double xd = (double)x;
+  double r = xd * 0x1.45F306DC9C883p+23;
+  int n = ((int32_t)r + 0x800000) >> 24;
+  xd = xd - (double)n * 0x1.921FB54442D18p0;
+  float y0 = (float)xd;
+  float y1 = (float)(xd - (double)y0);
+  return glibc_kernel_tanf(y0, y1, 1 - ((n & 1) << 1));
+}
+BBMCU_D float glibc_erfcf(float x)
+{
+  const float erx = 8.4506291151e-01f;
+  int32_t hx = (int32_t)f2u(x), ix = hx & 0x7fffffff;
+  if(ix >= 0x7f800000) return (float)(((uint32_t)hx >> 31) << 1) + 1.0f / x;
+  if(ix < 0x3f580000) {                       /* |x| < 0.84375 */
+    if(ix < 0x23800000) return 1.0f - x;
+    float z = x*x;
+    float r = u2f(0x3e0375d4) + z * (-u2f(0x3ea66beb) + z * (-u2f(0x3ce9528f) + z * (-u2f(0x3bbd1489) + z * u2f(0xb7c756b1))));
+    float s = 1.0f + z * (u2f(0x3ecbbbce) + z * (u2f(0x3d852a63) + z * (u2f(0x3ba68116) + z * (u2f(0x390aee49) + z * u2f(0xb684e21a)))));
+    float y = r / s;
+    if(hx < 0x3e800000) return 1.0f - (x + x*y);
+    r = x*y; r += (x - 0.5f);
+    return 0.5f - r;
+  }
+  if(ix < 0x3fa00000) {                       /* 0.84375 <= |x| < 1.25 */
+    float s = fabsf(x) - 1.0f;
+    float P = -u2f(0x3b1acdc6) + s * (u2f(0x3ed46805) + s * (-u2f(0x3ebe9208) + s * (u2f(0x3ea2fe54) + s * (-u2f(0x3de31cc2) + s * (u2f(0x3d1151b3) + s * u2f(0xbb0df9c0))))));
+    float Q = 1.0f + s * (u2f(0x3dd9f331) + s * (u2f(0x3f0a5785) + s * (u2f(0x3d931ae7) + s * (u2f(0x3e013307) + s * (u2f(0x3c5f6e13) + s * u2f(0x3c445aa3))))));
+    if(hx >= 0) { float z = 1.0f - erx; return z - P / Q; }
+    float z = erx + P / Q; return 1.0f + z;
+  }
+  if(ix < 0x41e00000) {                       /* |x| < 28 */
+    float ax = fabsf(x);
+    float s = 1.0f / (ax * ax);
+    float R, S;
+    if(ix < 0x4036DB6D) {
+      R = -u2f(0x3c21a093) + s * (-u2f(0x3f31a0b7) + s * (-u2f(0x4128f022) + s * (-u2f(0x42798057) + s * (-u2f(0x4322658c) + s * (-u2f(0x43389ae7) + s * (-u2f(0x42a2932b) + s * u2f(0xc11d077e)))))));
+      S = 1.0f + s * (u2f(0x419d35ce) + s * (u2f(0x4309a863) + s * (u2f(0x43d9486f) + s * (u2f(0x442158c9) + s * (u2f(0x43d6810b) + s * (u2f(0x42d9451f) + s * (u2f(0x40d23f7c) + s * u2f(0xbd777f97))))))));
+    } else {
+      if(hx < 0 && ix >= 0x40c00000) return 2.0f - 1e-30f;
+      R = -u2f(0x3c21a092) + s * (-u2f(0x3f4c9dd4) + s * (-u2f(0x418e104b) + s * (-u2f(0x4320a2ea) + s * (-u2f(0x441f6441) + s * (-u2f(0x4480230b) + s * u2f(0xc3f1c275))))));
+      S = 1.0f + s * (u2f(0x41f2b459) + s * (u2f(0x43a2e571) + s * (u2f(0x44c01759) + s * (u2f(0x4547fdbb) + s * (u2f(0x451f90ce) + s * (u2f(0x43ed43a7) + s * u2f(0xc1b38712)))))));
+    }
+    float z = u2f(f2u(ax) & 0xffffe000u);
+    float r = glibc_expf(-z * z - 0.5625f) * glibc_expf((z - ax) * (z + ax) + R / S);
+    if(hx > 0) return r / ax;
+    return 2.0f - r / ax;
+  }
+  if(hx > 0) return 1e-30f * 1e-30f;
+  return 2.0f - 1e-30f;
+}
+
 } // namespace bbmcu

@@ -58,27 +58,64 @@ BBMCU_D uint32_t merl_index(f3 in, f3 out)
 }
 
 // merl_linearizer::operator()(idx) -> (in, out) (merl_linearizer.h:50-83, with phi/theta of the
-// half vector re-derived from the vector as core/vec_transform.h:117-123 does)
+// half vector re-derived from the vector as core/vec_transform.h:117-123 does).
+//
+// The computation is separable: everything transcendental depends on ONE of the three bin coordinates
+//   iHt -> the two rotations  (cos/sin of theta(half), cos/sin of phi(half))        merl_lin_half
+//   iDt -> sin/cos of theta_d                                                       merl_lin_dtheta
+//   iDp -> cos/sin of phi_d                                                         merl_lin_dphi
+// and the rest (merl_dirs_assemble) is ~40 float operations.  merl_dirs() evaluates the three pieces per bin;
+// merl_dirs_tab() reads them from a 900-float table built once per device with the very same functions, so both
+// return identical bits - this is what lets eval and loss kernels generate the grid's directions in registers
+// instead of reading 24 B per sample ("fused linearizer").
+struct MerlLinHalf { float cy, sy, cz, sz; };
+BBMCU_D MerlLinHalf merl_lin_half(uint32_t iHt)
+{
+  float qh = (float)iHt / 90.0f;
+  // pow(float2, 2.0) * (0.5 * Sphere()): the product runs in double and is rounded once
+  float thh = (float)(((double)qh * (double)qh) * (double)(0.5f*kPi));
+  // spherical::convert(phi = 0, theta): cos(0) = 1, sin(0) = 0
+  float sth = glibc_sinf(thh), cth = glibc_cosf(thh);
+  f3 half = make_f3(1.0f*sth, 0.0f*sth, cth);
+  float ph = lin_phi(half), th = lin_theta(half);
+  MerlLinHalf r; r.cz = glibc_cosf(ph); r.sz = glibc_sinf(ph); r.cy = glibc_cosf(th); r.sy = glibc_sinf(th);
+  return r;
+}
+BBMCU_D void merl_lin_dtheta(uint32_t iDt, float& s, float& c) { float thd = ((float)iDt / 90.0f) * (0.5f*kPi); s = glibc_sinf(thd); c = glibc_cosf(thd); }
+BBMCU_D void merl_lin_dphi(uint32_t iDp, float& c, float& s) { float phd = ((float)iDp / 180.0f) * (0.5f*kTwoPi); c = glibc_cosf(phd); s = glibc_sinf(phd); }
+BBMCU_D void merl_dirs_assemble(const MerlLinHalf& h, float std_, float ctd, float cpd, float spd, f3& in, f3& out)
+{
+  f3 diff = make_f3(cpd*std_, spd*std_, ctd);
+  in = rot_z(h.cz, h.sz, rot_y(h.cy, h.sy, diff));
+  out = rot_z(h.cz, h.sz, rot_y(h.cy, h.sy, make_f3(-diff.x, -diff.y, diff.z)));
+  in.z = fmaxf(in.z, 0.0f);
+  out.z = fmaxf(out.z, 0.0f);
+}
 BBMCU_D void merl_dirs(uint32_t idx, f3& in, f3& out)
 {
   if(!(idx < kMerlBins)) { in = make_f3(0, 0, 0); out = make_f3(0, 0, 0); return; }
   uint32_t iDp = idx % 180u, iDt = (idx / 180u) % 90u, iHt = idx / 16200u;
-  float qh = (float)iHt / 90.0f;
-  // pow(float2, 2.0) * (0.5 * Sphere()): the product runs in double and is rounded once
-  float thh = (float)(((double)qh * (double)qh) * (double)(0.5f*kPi));
-  float phd = ((float)iDp / 180.0f) * (0.5f*kTwoPi);
-  float thd = ((float)iDt / 90.0f) * (0.5f*kPi);
-  // spherical::convert(phi = 0, theta): cos(0) = 1, sin(0) = 0
-  float sth = glibc_sinf(thh), cth = glibc_cosf(thh);
-  f3 half = make_f3(1.0f*sth, 0.0f*sth, cth);
-  float std_ = glibc_sinf(thd), ctd = glibc_cosf(thd);
-  f3 diff = make_f3(glibc_cosf(phd)*std_, glibc_sinf(phd)*std_, ctd);
-  float ph = lin_phi(half), th = lin_theta(half);
-  float cz = glibc_cosf(ph), sz = glibc_sinf(ph), cy = glibc_cosf(th), sy = glibc_sinf(th);
-  in = rot_z(cz, sz, rot_y(cy, sy, diff));
-  out = rot_z(cz, sz, rot_y(cy, sy, make_f3(-diff.x, -diff.y, diff.z)));
-  in.z = fmaxf(in.z, 0.0f);
-  out.z = fmaxf(out.z, 0.0f);
+  MerlLinHalf h = merl_lin_half(iHt);
+  float std_, ctd, cpd, spd;
+  merl_lin_dtheta(iDt, std_, ctd);
+  merl_lin_dphi(iDp, cpd, spd);
+  merl_dirs_assemble(h, std_, ctd, cpd, spd, in, out);
+}
+
+// table layout: [0, 360) = (cy, sy, cz, sz) per iHt; [360, 540) = (sin, cos) theta_d per iDt; [540, 900) = (cos, sin) phi_d per iDp
+constexpr int kMerlLinTabFloats = 900;
+BBMCU_D void merl_lin_tab_fill(float* tab, int j)           // entry j of 90 + 90 + 180 = 360 table rows
+{
+  if(j < 90) { MerlLinHalf h = merl_lin_half((uint32_t)j); tab[4*j] = h.cy; tab[4*j + 1] = h.sy; tab[4*j + 2] = h.cz; tab[4*j + 3] = h.sz; }
+  else if(j < 180) { float s, c; merl_lin_dtheta((uint32_t)(j - 90), s, c); tab[360 + 2*(j - 90)] = s; tab[360 + 2*(j - 90) + 1] = c; }
+  else if(j < 360) { float c, s; merl_lin_dphi((uint32_t)(j - 180), c, s); tab[540 + 2*(j - 180)] = c; tab[540 + 2*(j - 180) + 1] = s; }
+}
+BBMCU_D void merl_dirs_tab(const float* tab, uint32_t idx, f3& in, f3& out)
+{
+  if(!(idx < kMerlBins)) { in = make_f3(0, 0, 0); out = make_f3(0, 0, 0); return; }
+  uint32_t iDp = idx % 180u, iDt = (idx / 180u) % 90u, iHt = idx / 16200u;
+  MerlLinHalf h; h.cy = tab[4*iHt]; h.sy = tab[4*iHt + 1]; h.cz = tab[4*iHt + 2]; h.sz = tab[4*iHt + 3];
+  merl_dirs_assemble(h, tab[360 + 2*iDt], tab[360 + 2*iDt + 1], tab[540 + 2*iDp], tab[540 + 2*iDp + 1], in, out);
 }
 
 // spherical_linearizer (spherical_linearizer.h:37-111)

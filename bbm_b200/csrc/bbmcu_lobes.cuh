@@ -225,10 +225,11 @@ struct Ward
     if(!(component & FLAG_SPECULAR) || !xi_valid(xi)) return;
     float rx = a[3], ry = ANISO ? a[4] : a[3];
     float ph = kTwoPi * xi.x;
-    float cx = cosf(ph)*rx, cy = sinf(ph)*ry;
+    float sph_, cph_; glibc_sincosf_both(ph, sph_, cph_);            // the host libm's float functions (bbmcu_libm.cuh): bit-equal directions
+    float cx = cph_*rx, cy = sph_*ry;
     float rn = 1.0f / sqrtf(cx*cx + cy*cy); cx *= rn; cy *= rn;
     float qx = cx/rx, qy = cy/ry;
-    float cosT = (float)(1.0 / sqrt(1.0 - (double)(logf(xi.y) / (qx*qx + qy*qy))));
+    float cosT = (float)(1.0 / sqrt(1.0 - (double)(glibc_logf(xi.y) / (qx*qx + qy*qy))));
     float sinT = (float)safe_sqrt_d(1.0 - (double)(cosT*cosT));
     dir = reflect(out, make_f3(cx*sinT, cy*sinT, cosT));
     pdfv = pdf(dir, out, a, component);
@@ -414,16 +415,23 @@ struct LowSmooth
     dir = make_f3(0, 0, 0); pdfv = 0.0f; flag = FLAG_NONE;
     if(!(component & FLAG_SPECULAR) || !xi_valid(xi)) return;
     float B = a[3], ro2;
-    float t = md_temp(out, B, ro2);
-    t = (float)(-log(2.0) + (double)logf(1.0f + B*(1.0f - ro2) + m_safe_sqrt(t)));
+    // (lowsmooth.h:95: here the reference writes "1 - ro2" and "pow(.., 2)" with INT literals, so - unlike in pdf() - the
+    // square is a float powf and only 2 B (1.0 + ro2) runs in double.  Every libm call below is the host library's float
+    // function restated (bbmcu_libm.cuh): E - 2 cancels for small xi and would amplify a last-bit difference by 1e3.)
+    ro2 = sinTheta2(out);
+    const float bp = B*(1.0f - ro2);
+    float t = (float)((1.0 + (double)(2.0f*B) * (1.0 + (double)ro2)) + (double)(bp*bp));
+    t = (float)(-0x1.62e42fefa39efp-1 + (double)glibc_logf(1.0f + bp + m_safe_sqrt(t)));
     float MdPi = B * (1.0f / t);
-    float E = (float)(2.0 * (double)expf(xi.x * B * (1.0f / MdPi)));
+    float E = (float)(2.0 * (double)glibc_expf(xi.x * B * (1.0f / MdPi)));
     float ri = m_safe_sqrt((E - 2.0f)*(E + 2.0f*B*ro2) / (2.0f*E*B));
     float ro = sqrtf(ro2);
     double rp = (double)(ri + ro), rm = (double)(ri - ro);
     float scale = (float)sqrt((1.0 + (double)B*(rp*rp)) / (1.0 + (double)B*(rm*rm)));
-    float phi_i = (float)(2.0 * (double)atanf(tanf(xi.y * kPi) * scale) + (double)sph_phi(out));
-    dir = make_f3(cosf(phi_i)*ri, sinf(phi_i)*ri, (float)safe_sqrt_d(1.0 - (double)(ri*ri)));
+    float phi_o = glibc_atan2f(out.y, out.x); if(phi_o < 0.0f) phi_o += kTwoPi;                   // spherical::phi (core/spherical.h:42-46)
+    float phi_i = (float)(2.0 * (double)glibc_atanf(glibc_tanf(xi.y * kPi) * scale) + (double)phi_o);
+    float sp, cp; glibc_sincosf_both(phi_i, sp, cp);
+    dir = make_f3(cp*ri, sp*ri, (float)safe_sqrt_d(1.0 - (double)(ri*ri)));
     pdfv = pdf(dir, out, a, component);
     flag = FLAG_SPECULAR;
   }

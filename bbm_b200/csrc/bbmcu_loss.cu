@@ -26,6 +26,7 @@ struct PeerArgs
   size_t cap;
   unsigned char* win[kMaxPeers];
   unsigned int* status;
+  unsigned long long timeout_ns;       // a peer that has not delivered after this long fails the batch (BBMCU_PEER_TIMEOUT_MS, default 10 s)
 };
 
 namespace bbmcu { SphericalGrid to_device_grid(const bbmcu_spherical_grid& g); }
@@ -33,15 +34,19 @@ namespace bbmcu { SphericalGrid to_device_grid(const bbmcu_spherical_grid& g); }
 struct bbmcu_loss
 {
   bbmcu_ctx* ctx = nullptr;
+  int device = 0;            // copy of ctx->device (bbmcu_loss_free must not touch a context that may be gone)
   int metric = 0, component = BBMCU_ALL, unit = 0;
   bool merl_grid = true;
   SphericalGrid grid{};
   uint64_t N = 0;            // samples of the whole linearizer
   uint64_t first = 0;        // this shard
   size_t count = 0;
-  float* d_in = nullptr;     // 3 planes of count
+  int n_materials = 1;       // reference operands sharing this linearizer (bbmcu_loss_create_ex: a batch of measured tables)
+  bool fused = true;         // directions generated inside the kernels (no d_in / d_out planes kept)
+  const float* d_lin_tab = nullptr;   // the device's separable merl_linearizer table (owned by the library, per device)
+  float* d_in = nullptr;     // 3 planes of count (materialised mode only)
   float* d_out = nullptr;
-  float* d_ref = nullptr;
+  float* d_ref = nullptr;    // n_materials x 3 planes of count
   // scratch, grown on demand
   float* d_attrs = nullptr;   size_t attrs_cap = 0;
   float* h_attrs[2] = {nullptr, nullptr}; size_t h_attrs_cap[2] = {0, 0};   // pinned, double buffered
@@ -77,8 +82,11 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_generic(const LossArgs a,
 {
   extern __shared__ double s_red[];                 // [warps][1 + P]
   __shared__ BsdfDesc b;
-  const int k = blockIdx.y, P = a.P;
+  __shared__ float s_lin[kMerlLinTabFloats];
+  const int k = blockIdx.y, P = a.P;                // k runs over all materials' parameter sets
+  const float* refp = a.ref + (size_t)(k / a.k_per_material) * a.ref_stride;
   if(threadIdx.x == 0) { b = shape; }
+  loss_stage_lin(a, s_lin);
   __syncthreads();
   for(int i = threadIdx.x; i < a.n_attrs; i += blockDim.x) b.attrs[i] = loss_attr(a, (size_t)k*a.attr_stride + i);
   __syncthreads();
@@ -86,9 +94,9 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_generic(const LossArgs a,
   for(int j=0; j <= P; ++j) acc[j] = 0.0;
   for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x*blockDim.x)
   {
-    f3 in = make_f3(__ldg(a.in + i), __ldg(a.in + a.n + i), __ldg(a.in + 2*a.n + i));
-    f3 out = make_f3(__ldg(a.out + i), __ldg(a.out + a.n + i), __ldg(a.out + 2*a.n + i));
-    Spec<float> ref(__ldg(a.ref + i), __ldg(a.ref + a.n + i), __ldg(a.ref + 2*a.n + i));
+    f3 in, out;
+    loss_dirs(a, s_lin, i, in, out);
+    Spec<float> ref(__ldg(refp + i), __ldg(refp + a.n + i), __ldg(refp + 2*a.n + i));
     float g[kMaxParams];
     float e = loss_sample_generic(b, a.metric, a.component, in, out, ref, a.want_grad ? g : nullptr);
     acc[0] += (double)e;
@@ -187,7 +195,7 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_gather(unsigned int nva
         pending &= ~(1u << r);
       }
     }
-    if(pending && (global_ns() - t0 > 10000000000ull)) { bad = true; break; }
+    if(pending && (global_ns() - t0 > pa.timeout_ns)) { bad = true; break; }
   }
   double sum = 0.0;
 #pragma unroll
@@ -199,10 +207,13 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_gather(unsigned int nva
 // per-sample terms l(idx) (sampledlossfunction::operator()(idx))
 __global__ void __launch_bounds__(256) k_loss_terms(const LossArgs a, const BsdfDesc b, float* terms)
 {
+  __shared__ float s_lin[kMerlLinTabFloats];
+  loss_stage_lin(a, s_lin);
+  __syncthreads();
   for(size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x*blockDim.x)
   {
-    f3 in = make_f3(a.in[i], a.in[a.n + i], a.in[2*a.n + i]);
-    f3 out = make_f3(a.out[i], a.out[a.n + i], a.out[2*a.n + i]);
+    f3 in, out;
+    loss_dirs(a, s_lin, i, in, out);
     Spec<float> ref(a.ref[i], a.ref[a.n + i], a.ref[2*a.n + i]);
     terms[i] = loss_sample_generic(b, a.metric, a.component, in, out, ref, nullptr);
   }
@@ -217,39 +228,53 @@ template<class T> void grow(T*& p, size_t& cap, size_t need)
   cap = need;
 }
 
+// the part of LossArgs that says where samples come from (directions: generated or planes; reference planes)
+void fill_sample_source(const bbmcu_loss* L, LossArgs& a)
+{
+  a.lin_mode = !L->fused ? LIN_MATERIALISED : (L->merl_grid ? LIN_MERL_TABLES : LIN_SPHERICAL);
+  a.lin_tab = L->d_lin_tab; a.first = L->first; a.grid = L->grid;
+  a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.ref_stride = 3*L->count; a.n = L->count;
+  a.k_per_material = 1; a.n_materials = 1;
+}
+
 void check_metric(int metric) { if(metric < 0 || metric > 5) throw std::invalid_argument("BBM: unknown loss metric " + std::to_string(metric)); }
 
 } // anonymous namespace
 
 extern "C" {
 
-int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
-                      const bbmcu_bsdf* reference_bsdf, const float* reference_merl_rgb,
-                      uint64_t first, uint64_t count, bbmcu_loss** out)
+int bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
+                         const bbmcu_bsdf* reference_bsdf, const float* const* reference_merl_rgb, int n_materials,
+                         uint64_t first, uint64_t count, unsigned flags, bbmcu_loss** out)
 {
   return guarded(ctx, [&] {
     if(!ctx || !out) throw std::invalid_argument("BBM: null argument");
     check_metric(metric);
     if((reference_bsdf != nullptr) == (reference_merl_rgb != nullptr)) throw std::invalid_argument("BBM: exactly one of reference_bsdf / reference_merl_rgb must be given");
+    if(n_materials < 1 || (reference_bsdf && n_materials != 1)) throw std::invalid_argument("BBM: n_materials must be 1 for an analytic reference and >= 1 for measured tables");
+    if(reference_merl_rgb) for(int m=0; m < n_materials; ++m) if(!reference_merl_rgb[m]) throw std::invalid_argument("BBM: null measured table");
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<bbmcu_loss> L(new bbmcu_loss);
-    L->ctx = ctx; L->metric = metric; L->component = component; L->unit = unit;
+    L->ctx = ctx; L->device = ctx->device; L->metric = metric; L->component = component; L->unit = unit;
     L->merl_grid = (grid == nullptr);
+    L->n_materials = n_materials;
+    L->fused = !(flags & BBMCU_LOSS_MATERIALISE_DIRECTIONS);
     if(grid) { L->grid = to_device_grid(*grid); L->N = L->grid.size(); } else L->N = kMerlBins;
     if(first > L->N) throw std::out_of_range("BBM: loss shard starts beyond the linearizer size");
     if(count == 0) count = L->N - first;
     if(first + count > L->N) throw std::out_of_range("BBM: loss shard exceeds the linearizer size");
     L->first = first; L->count = (size_t)count;
     const size_t n = L->count;
+    if(L->merl_grid) L->d_lin_tab = merl_lin_table_device(ctx->device);
     if(n == 0) { *out = L.release(); return; }
     BBMCU_CUDA(cudaMalloc(&L->d_in, 3*n*sizeof(float)));
     BBMCU_CUDA(cudaMalloc(&L->d_out, 3*n*sizeof(float)));
-    BBMCU_CUDA(cudaMalloc(&L->d_ref, 3*n*sizeof(float)));
+    BBMCU_CUDA(cudaMalloc(&L->d_ref, (size_t)n_materials*3*n*sizeof(float)));
     BBMCU_CUDA(cudaMalloc(&L->d_bad, sizeof(uint32_t)));
     BBMCU_CUDA(cudaMemsetAsync(L->d_bad, 0, sizeof(uint32_t), ctx->stream));
-    // 1. the linearizer's directions for this shard (materialised once; both sides of every parity test
-    //    and every pass read these same float triples)
-    const bool al = (n % 4 == 0);
+    // 1. the linearizer's directions for this shard: needed here to tabulate the reference operand; kept only in
+    //    materialised mode (the fused kernels regenerate the same bits from the bin index)
+    const bool al = true;                     // cudaMalloc'ed planes; launch_foreach4 checks the plane stride
     if(L->merl_grid) { MerlDirsOp op; op.first = (uint32_t)first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
     else { SphericalDirsOp op; op.grid = L->grid; op.first = first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
     // 2. the reference operand tabulated at those directions (it never changes during a fit)
@@ -260,21 +285,23 @@ int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* gr
     }
     else
     {
-      // merl_data::eval: component must be exactly All (staticmodel/merl.h:83), nearest-bin lookup
+      // merl_data::eval: component must be exactly All (staticmodel/merl.h:83), nearest-bin lookup.  Host tables pass
+      // through one device staging buffer, one material after the other.
       float* d_table = nullptr;
-      const float* table = reference_merl_rgb;
-      if(!is_device_pointer(reference_merl_rgb))
+      for(int m=0; m < n_materials; ++m)
       {
-        BBMCU_CUDA(cudaMalloc(&d_table, 3*(size_t)kMerlBins*sizeof(float)));
-        BBMCU_CUDA(cudaMemcpyAsync(d_table, reference_merl_rgb, 3*(size_t)kMerlBins*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        table = d_table;
-      }
-      if(component == BBMCU_ALL)
-      {
-        MerlLookupOp op; op.table = table; op.in = L->d_in; op.out = L->d_out; op.rgb = L->d_ref; op.bad = L->d_bad; op.n = n; op.aligned = al;
+        float* ref_m = L->d_ref + (size_t)m*3*n;
+        if(component != BBMCU_ALL) { BBMCU_CUDA(cudaMemsetAsync(ref_m, 0, 3*n*sizeof(float), ctx->stream)); continue; }
+        const float* table = reference_merl_rgb[m];
+        if(!is_device_pointer(table))
+        {
+          if(!d_table) BBMCU_CUDA(cudaMalloc(&d_table, 3*(size_t)kMerlBins*sizeof(float)));
+          BBMCU_CUDA(cudaMemcpyAsync(d_table, table, 3*(size_t)kMerlBins*sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+          table = d_table;
+        }
+        MerlLookupOp op; op.table = table; op.in = L->d_in; op.out = L->d_out; op.rgb = ref_m; op.bad = L->d_bad; op.n = n; op.aligned = al;
         launch_foreach4(ctx, ctx->stream, op, n);
       }
-      else BBMCU_CUDA(cudaMemsetAsync(L->d_ref, 0, 3*n*sizeof(float), ctx->stream));
       uint32_t bad = 0;
       BBMCU_CUDA(cudaMemcpyAsync(&bad, L->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
       BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -283,20 +310,45 @@ int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* gr
       if(bad) throw std::out_of_range("BBM: " + std::to_string(bad) + " samples of the linearizer map outside the MERL table (NaN direction pairs); the reference throws 'lookup out of range' here");
     }
     BBMCU_CUDA(cudaStreamSynchronize(ctx->stream));
+    if(L->fused) { BBMCU_CUDA(cudaFree(L->d_in)); BBMCU_CUDA(cudaFree(L->d_out)); L->d_in = L->d_out = nullptr; }
     *out = L.release();
   });
 }
 
-void bbmcu_loss_free(bbmcu_loss* L) { if(L) { cudaSetDevice(L->ctx->device); cudaStreamSynchronize(L->ctx->stream); delete L; } }
+int bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
+                      const bbmcu_bsdf* reference_bsdf, const float* reference_merl_rgb,
+                      uint64_t first, uint64_t count, bbmcu_loss** out)
+{
+  return bbmcu_loss_create_ex(ctx, metric, grid, component, unit, reference_bsdf, reference_merl_rgb ? &reference_merl_rgb : nullptr, 1, first, count, 0u, out);
+}
+
+int bbmcu_loss_set_metric(bbmcu_loss* L, int metric)
+{
+  return guarded(L ? L->ctx : nullptr, [&] { if(!L) throw std::invalid_argument("BBM: null argument"); check_metric(metric); L->metric = metric; });
+}
+int bbmcu_loss_materials(const bbmcu_loss* L) { return L ? L->n_materials : 0; }
+
+// the loss keeps its own copy of the device index: the context may already be gone (Python shutdown order, a cuda_loss that
+// outlives its context), so nothing of *ctx is touched here
+void bbmcu_loss_free(bbmcu_loss* L) { if(L) { if(cudaSetDevice(L->device) == cudaSuccess) cudaDeviceSynchronize(); delete L; } }
 uint64_t bbmcu_loss_samples(const bbmcu_loss* L) { return L ? L->N : 0; }
+uint64_t bbmcu_loss_shard_count(const bbmcu_loss* L) { return L ? (uint64_t)L->count : 0; }
 
 int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params, size_t K, double* loss_out, double* grad_out, double* device_out)
+{
+  if(L && L->n_materials != 1) { bbmcu_ctx* c = L->ctx; return guarded(c, [&] { throw std::invalid_argument("BBM: this loss holds " + std::to_string(L->n_materials) + " materials: use bbmcu_loss_eval_multi"); }); }
+  return bbmcu_loss_eval_multi(L, bsdf, params, K, loss_out, grad_out, device_out);
+}
+
+// Kper parameter sets for EACH of the loss's M materials in one launch: params M x Kper x P (material-major), results M x Kper
+int bbmcu_loss_eval_multi(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params, size_t Kper, double* loss_out, double* grad_out, double* device_out)
 {
   bbmcu_ctx* ctx = L ? L->ctx : nullptr;
   return guarded(ctx, [&] {
     if(!L || !bsdf) throw std::invalid_argument("BBM: null argument");
-    if(K == 0) return;
-    if(!params && K != 1) throw std::invalid_argument("BBM: params == NULL requires K == 1");
+    if(Kper == 0) return;
+    const size_t M = (size_t)L->n_materials, K = M*Kper;                 // K: parameter sets of the whole launch
+    if(!params && K != 1) throw std::invalid_argument("BBM: params == NULL requires one material and K == 1");
     if(L->h_peer_status && *(volatile unsigned int*)L->h_peer_status) throw std::runtime_error("BBM: a peer shard did not arrive at an earlier loss exchange within 10 s");
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     const int P = bsdf->b.param_count(BBMCU_ATTR_ALL);
@@ -332,7 +384,9 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
       for(size_t k=0; k < K; ++k)
       {
         if(params) tmp.set_params(BBMCU_ATTR_ALL, params + k*P, P);
-        for(int i=0; i < A; ++i) h_attrs[k*A + i] = 0.0f;               // table gaps of He lobes are never read; keep them defined
+        // start from the descriptor's block: it carries what is not a parameter value - the device address of a Merl(...)
+        // lobe's table (two float slots, bbmcu_desc.hpp) and the zeroed table gaps of He lobes - then overlay the values
+        std::memcpy(h_attrs + k*A, shape.attrs, (size_t)A*sizeof(float));
         for(size_t l=0; l < tmp.lobes.size(); ++l)
         {
           size_t off = (size_t)shape.offset[l];
@@ -354,20 +408,21 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
     if(static_shape) bx = (unsigned)std::max<size_t>(1, (n + kTileSamples - 1) / kTileSamples);     // one partial row per sample tile
     grow(L->d_partial, L->partial_cap, K*(size_t)bx*cols);
     grow(L->d_result, L->result_cap, K*(size_t)cols);
-    a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = n; a.attrs = L->d_attrs; a.attr_stride = A; a.n_attrs = A;
+    fill_sample_source(L, a);
+    a.attrs = L->d_attrs; a.attr_stride = A; a.n_attrs = A; a.k_per_material = (int)Kper; a.n_materials = (int)M;
     a.metric = L->metric; a.component = L->component; a.want_grad = want_grad ? 1 : 0; a.partial = L->d_partial; a.P = P; a.sm_count = ctx->sm_count;
     bool done = false;
     if(n > 0)
     {
       const int m0 = shape.model[0];
       if(shape.n_lobes == 1 && !shape.aggregate)
-        done = launch_loss_single_g0(m0, ctx->stream, a, bx, (unsigned)K) || launch_loss_single_g1(m0, ctx->stream, a, bx, (unsigned)K) ||
-               launch_loss_single_g2(m0, ctx->stream, a, bx, (unsigned)K) || launch_loss_single_g3(m0, ctx->stream, a, bx, (unsigned)K);
+        done = launch_loss_single_g0(m0, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_single_g1(m0, ctx->stream, a, bx, (unsigned)Kper) ||
+               launch_loss_single_g2(m0, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_single_g3(m0, ctx->stream, a, bx, (unsigned)Kper);
       else if(shape.n_lobes == 2 && shape.aggregate && m0 == M_Lambertian)
       {
         const int m1 = shape.model[1];
-        done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)K) ||
-               launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)K) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)K);
+        done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)Kper) ||
+               launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)Kper);
       }
       if(!done) bind_device_tables();
       if(!done) k_loss_generic<<<dim3(bx, (unsigned)K), kLossThreads, (kLossThreads/32)*cols*sizeof(double), ctx->stream>>>(a, shape);
@@ -381,6 +436,8 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
       if(K*(size_t)cols > L->peer_cap) throw std::invalid_argument("BBM: K*(1+P) = " + std::to_string(K*(size_t)cols) + " exceeds the peer window (" + std::to_string(L->peer_cap) + " values)");
       PeerArgs pa{};
       pa.rank = L->peer_rank; pa.world = L->peer_world; pa.cap = L->peer_cap;
+      static const unsigned long long timeout_ns = [] { const char* e = std::getenv("BBMCU_PEER_TIMEOUT_MS"); long v = e ? std::atol(e) : 0; return (unsigned long long)(v > 0 ? v : 10000) * 1000000ull; }();
+      pa.timeout_ns = timeout_ns;
       if(++L->peer_seq == 0u) L->peer_seq = 2u;                     // 0 marks a fresh window; 2 keeps the parities alternating across the wrap
       pa.seq = L->peer_seq;
       for(int r=0; r < L->peer_world; ++r) pa.win[r] = L->peer_win[r];
@@ -486,16 +543,21 @@ int bbmcu_loss_peer_connect_ptrs(bbmcu_loss* L, void* const* windows)
   });
 }
 
-int bbmcu_loss_terms(bbmcu_loss* L, const bbmcu_bsdf* bsdf, float* terms)
+int bbmcu_loss_terms(bbmcu_loss* L, const bbmcu_bsdf* bsdf, float* terms) { return bbmcu_loss_terms_at(L, bsdf, 0, terms); }
+
+int bbmcu_loss_terms_at(bbmcu_loss* L, const bbmcu_bsdf* bsdf, int material, float* terms)
 {
   bbmcu_ctx* ctx = L ? L->ctx : nullptr;
   return guarded(ctx, [&] {
     if(!L || !bsdf || !terms) throw std::invalid_argument("BBM: null argument");
+    if(material < 0 || material >= L->n_materials) throw std::out_of_range("BBM: material index out of range");
     if(L->count == 0) return;
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     BsdfDesc shape = make_desc(bsdf->b, ctx->device);
     LossArgs a{};
-    a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.n = L->count; a.metric = L->metric; a.component = L->component;
+    fill_sample_source(L, a);
+    a.ref = L->d_ref + (size_t)material*a.ref_stride;
+    a.metric = L->metric; a.component = L->component;
     const bool dev = is_device_pointer(terms);
     float* d_terms = terms;
     if(!dev) BBMCU_CUDA(cudaMalloc(&d_terms, L->count*sizeof(float)));

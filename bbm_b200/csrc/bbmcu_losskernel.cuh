@@ -16,13 +16,24 @@
 
 namespace bbmcu {
 
+enum : int { LIN_MATERIALISED = 0, LIN_MERL_TABLES = 1, LIN_SPHERICAL = 2 };
 struct LossArgs
 {
-  const float* in;        // 3 planes of n
+  // where a sample's direction pair comes from: LIN_MATERIALISED reads the planes `in` / `out` (24 B per sample);
+  // LIN_MERL_TABLES forms merl_linearizer(first + i) from the 900-float separable table `lin_tab` staged in shared
+  // memory; LIN_SPHERICAL evaluates spherical_linearizer(first + i) in registers.  The fused modes return the very bits
+  // the materialised planes hold (same functions), so a pass reads only the 12 B per sample of measured data.
+  int lin_mode;
+  const float* lin_tab;
+  uint64_t first;         // linearizer index of the shard's sample 0
+  SphericalGrid grid;
+  const float* in;        // 3 planes of n (LIN_MATERIALISED)
   const float* out;       // 3 planes of n
-  const float* ref;       // 3 planes of n (reference BSDF tabulated at the samples)
+  const float* ref;       // M x 3 planes of n (reference operand tabulated at the samples, one set of planes per material)
+  size_t ref_stride;      // floats between the planes of consecutive materials (3 n)
+  int k_per_material;     // parameter sets per material (block z = material; sets m*K .. m*K + K - 1 belong to material m)
   size_t n;               // samples in this shard
-  const float* attrs;     // K x attr_stride attribute blocks
+  const float* attrs;     // (M x K) x attr_stride attribute blocks
   int attr_stride;
   int n_attrs;
   int metric, component;
@@ -30,6 +41,7 @@ struct LossArgs
   double* partial;        // K x (1 + P) x blocks_x
   int P;
   int sm_count;
+  int n_materials;        // grid z of the tile kernel
   // small batches (one compass step: K = 2P parameter sets) travel inside the kernel arguments: no staging buffer, no
   // host-to-device copy, no event on the path.  inline_count = K * n_attrs floats (0: read `attrs`)
   int inline_count;
@@ -37,6 +49,30 @@ struct LossArgs
 };
 constexpr int kInlineAttrFloats = 256;
 BBMCU_D float loss_attr(const LossArgs& a, size_t idx) { return a.inline_count ? a.inline_attrs[idx] : a.attrs[idx]; }
+
+// sample i of the shard: direction pair (generated or loaded) - s_lin is the shared-memory copy of a.lin_tab
+BBMCU_D void loss_dirs(const LossArgs& a, const float* s_lin, size_t i, f3& in, f3& out)
+{
+  if(a.lin_mode == LIN_MERL_TABLES) merl_dirs_tab(s_lin, (uint32_t)(a.first + i), in, out);
+  else if(a.lin_mode == LIN_SPHERICAL) spherical_dirs(a.grid, a.first + i, in, out);
+  else
+  {
+#ifdef __CUDA_ARCH__
+    in = make_f3(__ldg(a.in + i), __ldg(a.in + a.n + i), __ldg(a.in + 2*a.n + i));
+    out = make_f3(__ldg(a.out + i), __ldg(a.out + a.n + i), __ldg(a.out + 2*a.n + i));
+#else
+    in = make_f3(a.in[i], a.in[a.n + i], a.in[2*a.n + i]);
+    out = make_f3(a.out[i], a.out[a.n + i], a.out[2*a.n + i]);
+#endif
+  }
+}
+#ifdef __CUDACC__
+// stage the linearizer table (3.6 KB) in shared memory; no-op for the other modes.  Callers __syncthreads() afterwards.
+__device__ __forceinline__ void loss_stage_lin(const LossArgs& a, float* s_lin)
+{
+  if(a.lin_mode == LIN_MERL_TABLES) for(int i = threadIdx.x; i < kMerlLinTabFloats; i += blockDim.x) s_lin[i] = __ldg(a.lin_tab + i);
+}
+#endif
 
 constexpr int kLossThreads = 256;
 
@@ -108,10 +144,15 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
   constexpr int C = WG ? 1 + P : 1;
   extern __shared__ float s_attr_tile[];                       // (k1 - k0) x n_attrs
   __shared__ float s_red[kTileKChunk][kLossThreads/32][C];
-  const int tile = blockIdx.x;
+  __shared__ float s_lin[kMerlLinTabFloats];
+  const int tile = blockIdx.x, mat = blockIdx.z;
   const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
+  const size_t kbase = (size_t)mat * K;                        // first parameter set of this material
   for(int i = threadIdx.x; i < (k1 - k0)*a.n_attrs; i += blockDim.x)
-    s_attr_tile[i] = loss_attr(a, (size_t)(k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs));
+    s_attr_tile[i] = loss_attr(a, (kbase + k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs));
+  loss_stage_lin(a, s_lin);
+  if(a.lin_mode == LIN_MERL_TABLES) __syncthreads();
+  const float* refp = a.ref + (size_t)mat * a.ref_stride;
   f3 in[kTileSPT], out[kTileSPT]; Spec<float> ref[kTileSPT]; bool valid[kTileSPT];
 #pragma unroll
   for(int s=0; s < kTileSPT; ++s)
@@ -119,9 +160,8 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
     const size_t i = (size_t)tile*kTileSamples + (size_t)s*kLossThreads + threadIdx.x;
     valid[s] = i < a.n;
     const size_t ii = valid[s] ? i : 0;
-    in[s] = make_f3(__ldg(a.in + ii), __ldg(a.in + a.n + ii), __ldg(a.in + 2*a.n + ii));
-    out[s] = make_f3(__ldg(a.out + ii), __ldg(a.out + a.n + ii), __ldg(a.out + 2*a.n + ii));
-    ref[s] = Spec<float>(__ldg(a.ref + ii), __ldg(a.ref + a.n + ii), __ldg(a.ref + 2*a.n + ii));
+    loss_dirs(a, s_lin, ii, in[s], out[s]);
+    ref[s] = Spec<float>(__ldg(refp + ii), __ldg(refp + a.n + ii), __ldg(refp + 2*a.n + ii));
   }
   typename LossT::Geom geo[kTileSPT];                          // direction-only work, once per sample
 #pragma unroll
@@ -154,29 +194,32 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
       if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
     }
     __syncthreads();
-    if((int)threadIdx.x < nkk*(1 + a.P))
+    // one value per (parameter set of the chunk, column); a loop, so any P up to kMaxParams is covered
+    for(int t = threadIdx.x; t < nkk*(1 + a.P); t += blockDim.x)
     {
-      const int kk = threadIdx.x / (1 + a.P), j = threadIdx.x % (1 + a.P);
+      const int kk = t / (1 + a.P), j = t % (1 + a.P);
       double v = 0.0;
       if(j < C) {
 #pragma unroll
         for(int w=0; w < kLossThreads/32; ++w) v += (double)s_red[kk][w][j];
       }
-      a.partial[((size_t)(kc + kk)*(1 + a.P) + j)*gridDim.x + tile] = v;          // [k][column][tile]: the finish kernel reads tiles coalesced
+      a.partial[((kbase + kc + kk)*(1 + a.P) + j)*gridDim.x + tile] = v;          // [material, k][column][tile]: the finish kernel reads tiles coalesced
     }
     __syncthreads();
   }
 }
 
 // launch shape of the tile kernel for n samples, K parameter sets of n_attrs floats: tiles x k-splits
-inline void loss_tile_shape(size_t n, size_t K, int n_attrs, int sm_count, unsigned& tiles, unsigned& ksplit, int& k_per_block)
+// (Ktot = parameter sets of the whole launch, over all materials; K = per material: the k-split happens inside a material)
+inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm_count, unsigned& tiles, unsigned& ksplit, int& k_per_block)
 {
   tiles = (unsigned)((n + kTileSamples - 1) / kTileSamples);
   if(tiles < 1) tiles = 1;
   const size_t smem_k = (size_t)(40*1024) / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the static shared-memory budget
   size_t split_fit = (K + smem_k - 1) / (smem_k ? smem_k : 1);
   static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 16; }();
-  size_t split_fill = ((size_t)sm_count*fill + tiles - 1) / tiles;                      // ~16 blocks per SM over the launch (tuning override: BBMCU_LOSS_BLOCKS_PER_SM)
+  const size_t mats = K ? (Ktot + K - 1) / K : 1;
+  size_t split_fill = ((size_t)sm_count*fill + tiles*mats - 1) / (tiles*mats);          // ~16 blocks per SM over the launch (tuning override: BBMCU_LOSS_BLOCKS_PER_SM)
   size_t sp = split_fit > split_fill ? split_fit : split_fill;
   if(sp > K) sp = K;
   if(sp < 1) sp = 1;
@@ -185,15 +228,17 @@ inline void loss_tile_shape(size_t n, size_t K, int n_attrs, int sm_count, unsig
 }
 
 // internal linkage (see bbmcu_tables.cuh).  blocks_x is the tile count the caller sized `partial` with.
+// K = parameter sets per material, a.n_materials materials (grid z)
 template<class LossT> static void launch_loss_static(cudaStream_t s, const LossArgs& a, unsigned blocks_x, unsigned K)
 {
   bind_device_tables();
   unsigned tiles, ksplit; int kpb;
-  loss_tile_shape(a.n, K, a.n_attrs, a.sm_count, tiles, ksplit, kpb);
+  loss_tile_shape(a.n, (size_t)K*a.n_materials, K, a.n_attrs, a.sm_count, tiles, ksplit, kpb);
   const size_t smem = (size_t)kpb*a.n_attrs*sizeof(float);
   (void)blocks_x;
-  if(a.want_grad) k_loss_tile<LossT, true><<<dim3(tiles, ksplit), kLossThreads, smem, s>>>(a, (int)K, kpb);
-  else            k_loss_tile<LossT, false><<<dim3(tiles, ksplit), kLossThreads, smem, s>>>(a, (int)K, kpb);
+  const dim3 grid(tiles, ksplit, (unsigned)a.n_materials);
+  if(a.want_grad) k_loss_tile<LossT, true><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb);
+  else            k_loss_tile<LossT, false><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb);
 }
 
 // one translation unit per group of models (compile time); returns false if `model` is not in that group

@@ -22,12 +22,13 @@ struct NdfSamplerCdf
   {
     float q = (float)idx / (float)kHeCdfBins;
     float theta = (float)(((double)q*(double)q) * (double)kHalfPi);
-    f3 h = make_f3(1.0f*sinf(theta), 0.0f*sinf(theta), cosf(theta));
+    // (the host libm's sinf / cosf restated, bbmcu_libm.cuh: the CDF must reproduce the reference's entries bit for bit)
+    f3 h = make_f3(1.0f*glibc_sinf(theta), 0.0f*glibc_sinf(theta), glibc_cosf(theta));
     float s = 0.0f + M::backscatter(a, component, h);
     s /= 1.0f;
     float q1 = (float)(idx + 1) / (float)kHeCdfBins;
     float theta1 = (float)(((double)q1*(double)q1) * (double)kHalfPi);
-    return s * (sinf(theta1) * sqrtf(theta1));
+    return s * (glibc_sinf(theta1) * sqrtf(theta1));
   }
   // cdf(samples): sequential partial sum, then normalise by the last entry (util/cdf.h:36-44)
   BBMCU_D static void cdf_finish(float* cdf)

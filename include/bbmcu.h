@@ -15,8 +15,14 @@
  *    array-of-structs (std::array<float,3>, backbone/native/include/backbone/array.h:27); adapters
  *    transpose at the host boundary only.
  *  - data pointers may be HOST or DEVICE memory (detected with cudaPointerGetAttributes).  Device
- *    pointers run in place on the context's stream; host pointers are staged through pinned memory
- *    in chunks, copies overlapped with the kernels.  The caller owns every buffer.
+ *    pointers run in place on the context's stream.  Host pointers are processed in chunks of 2^21
+ *    elements through device staging buffers, the copies of a chunk overlapping the kernels and
+ *    copies of its neighbours: pinned or registered host memory (cudaMallocHost, cudaHostRegister,
+ *    bbmcu_host_register) is DMA'd in place; pageable memory goes through an internal pinned ring
+ *    filled and drained by a few host threads.  The caller owns every buffer.
+ *  - OUTPUT pointers of the batched calls may be NULL where documented: that plane is neither
+ *    stored by the kernel nor copied back.
+ *  - planes of one argument are n floats apart unless bbmcu_set_plane_stride says otherwise.
  *  - there is no CPU fallback: without a usable CUDA device bbmcu_init fails.
  *  - one context per host thread per device; calls on one context are serialised on its stream.
  */
@@ -61,6 +67,13 @@ BBMCU_API const char* bbmcu_last_error(bbmcu_ctx* ctx);          /* ctx may be N
 BBMCU_API int  bbmcu_synchronize(bbmcu_ctx* ctx);
 BBMCU_API void* bbmcu_stream(bbmcu_ctx* ctx);                    /* the cudaStream_t all work of this context is issued on */
 BBMCU_API uint64_t bbmcu_launch_count(bbmcu_ctx* ctx);           /* kernels launched by this context so far */
+/* planes of every SoA argument of the following batched calls are `ld` floats apart (ld >= n; 0 = n, the default).  With
+ * ld a multiple of 4 (and 16-byte aligned base pointers) the kernels keep their 16-byte vector accesses for ANY n; with
+ * the default stride a batch whose n is not a multiple of 4 has misaligned planes and runs on scalar accesses. */
+BBMCU_API int  bbmcu_set_plane_stride(bbmcu_ctx* ctx, size_t ld);
+/* page-lock caller memory once so the host-pointer path DMAs it in place (cudaHostRegister / cudaHostUnregister) */
+BBMCU_API int  bbmcu_host_register(bbmcu_ctx* ctx, void* ptr, size_t bytes);
+BBMCU_API int  bbmcu_host_unregister(bbmcu_ctx* ctx, void* ptr);
 
 /* ---- model registry (replaces the BBM_EXPORT_BSDFMODEL tables, include/export/bbm_fromstring.h:48-49) -- */
 typedef struct {
@@ -98,6 +111,19 @@ BBMCU_API int  bbmcu_reflectance(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int com
 BBMCU_API int  bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
                            const float* out_xyz, const float* xi_uv, size_t n,
                            float* dir_xyz, float* sample_pdf, int32_t* flag, float* rgb, float* pdf);
+
+/* (any of dir_xyz, sample_pdf, flag, rgb, pdf may be NULL: not stored, not copied)
+ * The same pass over inputs drawn ON THE DEVICE (0 bytes in): element i uses a counter-based generator (Philox4x32-10 of
+ * (seed, first + i)): `out` uniform on the upper hemisphere as bin/checkBsdf.cpp:38-45 draws it, xi uniform in [0,1)^2.
+ * gen_out_xyz / gen_xi_uv (may be NULL) receive the generated inputs, so a checker can evaluate the reference at exactly those. */
+BBMCU_API int  bbmcu_sample_eval_pdf_generated(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                                     uint64_t seed, uint64_t first, size_t n, float* gen_out_xyz, float* gen_xi_uv,
+                                     float* dir_xyz, float* sample_pdf, int32_t* flag, float* rgb, float* pdf);
+/* eval(in, out) for (in, out) = merl_linearizer(idx), idx = first .. first+n-1, the linearizer fused into the kernel
+ * (include/linearizer/merl_linearizer.h:50-83): 0 bytes in, 12 bytes out per eval.  in_xyz / out_xyz (may be NULL) receive
+ * the generated directions; they are bit-identical to bbmcu_merl_dirs. */
+BBMCU_API int  bbmcu_eval_merl_grid(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component, int unit,
+                          uint32_t first, size_t n, float* rgb, float* in_xyz, float* out_xyz);
 
 /* ---- linearizers (include/linearizer/merl_linearizer.h:50-123, spherical_linearizer.h:37-111) --------- */
 #define BBMCU_MERL_BINS 1458000u
@@ -138,8 +164,24 @@ BBMCU_API int  bbmcu_hp_precompute_g1(bbmcu_ctx* ctx, float* table);
 BBMCU_API int  bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
                        const bbmcu_bsdf* reference_bsdf, const float* reference_merl_rgb,
                        uint64_t first, uint64_t count, bbmcu_loss** out);
+/* The same with (a) a BATCH of n_materials measured tables sharing one linearizer and one launch (configs[4] of the
+ * benchmark: many materials x many parameter sets per launch; reference_merl_rgb = array of n_materials table pointers;
+ * an analytic reference_bsdf requires n_materials == 1), and (b) flags.  By default the kernels GENERATE each sample's
+ * direction pair from its linearizer index in registers (merl_linearizer(idx), include/linearizer/merl_linearizer.h:50-83,
+ * through a 900-float separable table staged in shared memory; spherical_linearizer(idx) directly): a pass then reads only
+ * the 12 B per sample of tabulated reference data and a loss object costs 17.5 MB per material instead of 52.5 MB.  The
+ * generated directions are bit-identical to bbmcu_merl_dirs / bbmcu_spherical_dirs.  BBMCU_LOSS_MATERIALISE_DIRECTIONS
+ * keeps the direction planes in device memory and reads them instead (36 B per sample; same results bit for bit). */
+enum { BBMCU_LOSS_MATERIALISE_DIRECTIONS = 1 };
+BBMCU_API int  bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
+                          const bbmcu_bsdf* reference_bsdf, const float* const* reference_merl_rgb, int n_materials,
+                          uint64_t first, uint64_t count, unsigned flags, bbmcu_loss** out);
 BBMCU_API void bbmcu_loss_free(bbmcu_loss* loss);
 BBMCU_API uint64_t bbmcu_loss_samples(const bbmcu_loss* loss);      /* N of the linearizer (sampledlossfunction::samples) */
+BBMCU_API uint64_t bbmcu_loss_shard_count(const bbmcu_loss* loss);  /* samples of this shard = floats bbmcu_loss_terms writes */
+BBMCU_API int  bbmcu_loss_materials(const bbmcu_loss* loss);
+/* the six metrics differ only in the per-sample functor: switching is free (the tabulated reference is metric independent) */
+BBMCU_API int  bbmcu_loss_set_metric(bbmcu_loss* loss, int metric);
 /* loss (and, if grad != NULL, d loss / d parameter) of `bsdf` at K parameter vectors.
  * params: K x P row-major, P = bbmcu_bsdf_param_count(bsdf, BBMCU_ATTR_ALL), forward enumeration order;
  * params == NULL with K == 1 evaluates the bsdf's current parameters.  loss: K doubles; grad: K x P doubles.
@@ -148,8 +190,15 @@ BBMCU_API uint64_t bbmcu_loss_samples(const bbmcu_loss* loss);      /* N of the 
  * bbmcu_loss_peer_connect - already combined over the shards). */
 BBMCU_API int  bbmcu_loss_eval(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
                      double* loss_out, double* grad_out, double* device_out);
-/* per-sample terms l(idx) of the shard (sampledlossfunction::operator()(idx)); `terms` = count floats */
+/* K parameter vectors for EACH of the loss's M materials in one launch (the loop of include/bbm/sampledlossfunction.h:62-87
+ * over M x K (reference, parameter) pairs): params M x K x P material-major (row m*K + k belongs to material m),
+ * loss M x K, grad M x K x P, device_out M x K x (1+P). */
+BBMCU_API int  bbmcu_loss_eval_multi(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
+                           double* loss_out, double* grad_out, double* device_out);
+/* per-sample terms l(idx) of the shard (sampledlossfunction::operator()(idx)); `terms` = bbmcu_loss_shard_count floats
+ * (host or device); _at: against material `material` of a batched loss */
 BBMCU_API int  bbmcu_loss_terms(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, float* terms);
+BBMCU_API int  bbmcu_loss_terms_at(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, int material, float* terms);
 
 /* ---- multi-GPU combine of the sample-axis shards over NVLink peer memory -------------------------------------------------
  * (no reference counterpart: bbm is single-threaded; this is the exchange step of SURVEY.md section 8e.)

@@ -16,8 +16,10 @@ using namespace bbmcu;
 static thread_local std::string g_err;
 #define GUARD(...) try { __VA_ARGS__; return 0; } catch(const std::exception& e) { g_err = e.what(); return 1; }
 
-template<class Op> static void run(const Op& op, size_t n)
+template<class Op> static void run(const Op& op_in, size_t n)
 {
+  Op op = op_in;
+  if(op.ld == 0) op.ld = op.n;
   if constexpr (Op::kHasBsdf)
   {
     BsdfDesc b = op.bsdf;                       // what the kernel prologue does per thread block
@@ -65,6 +67,31 @@ int hostsim_spherical_dirs(const uint32_t* samples, const float* ranges, uint64_
   )
 }
 
+// merl_dirs_tab (the fused-linearizer path) against merl_dirs over bins [first, first + n): number of bins whose six floats differ in any bit
+size_t hostsim_merl_dirs_tab_mismatches(uint32_t first, size_t n)
+{
+  std::vector<float> tab(kMerlLinTabFloats);
+  for(int j=0; j < 360; ++j) merl_lin_tab_fill(tab.data(), j);
+  size_t bad = 0;
+  for(size_t i=0; i < n; ++i)
+  {
+    f3 a, b, c, d;
+    merl_dirs(first + (uint32_t)i, a, b);
+    merl_dirs_tab(tab.data(), first + (uint32_t)i, c, d);
+    bad += (std::memcmp(&a, &c, sizeof(f3)) != 0) || (std::memcmp(&b, &d, sizeof(f3)) != 0);
+  }
+  return bad;
+}
+// the counter-based input generator of the kernels (generate_inputs): element i of (seed, first)
+void hostsim_generate_inputs(uint64_t seed, uint64_t first, size_t n, float* out_xyz, float* xi_uv)
+{
+  for(size_t i=0; i < n; ++i)
+  {
+    GenInputs g = generate_inputs(seed, first + i);
+    out_xyz[i] = g.out.x; out_xyz[n + i] = g.out.y; out_xyz[2*n + i] = g.out.z; xi_uv[i] = g.xi.x; xi_uv[n + i] = g.xi.y;
+  }
+}
+
 // glibc-port checks: the restated atan2f / sinf / cosf against this host's libm
 float hostsim_atan2f(float y, float x) { return glibc_atan2f(y, x); }
 float hostsim_sinf(float x) { return glibc_sinf(x); }
@@ -76,9 +103,11 @@ size_t hostsim_libm_mismatches(int which, const float* a, const float* b, size_t
   {
     float both_s, both_c; glibc_sincosf_both(a[i], both_s, both_c);     // which 3 / 4: the shared-reduction variant
     float mine = which == 0 ? glibc_atan2f(a[i], b[i]) : which == 1 ? glibc_sinf(a[i]) : which == 2 ? glibc_cosf(a[i]) : which == 3 ? both_s : which == 4 ? both_c
-               : which == 5 ? glibc_expf(a[i]) : which == 6 ? glibc_logf(a[i]) : glibc_erff(a[i]);
+               : which == 5 ? glibc_expf(a[i]) : which == 6 ? glibc_logf(a[i]) : which == 7 ? glibc_erff(a[i])
+               : which == 8 ? glibc_tanf(a[i]) : which == 9 ? glibc_erfcf(a[i]) : glibc_atanf(a[i]);
     float ref = which == 0 ? atan2f(a[i], b[i]) : (which == 1 || which == 3) ? sinf(a[i]) : (which == 2 || which == 4) ? cosf(a[i])
-              : which == 5 ? expf(a[i]) : which == 6 ? logf(a[i]) : erff(a[i]);
+              : which == 5 ? expf(a[i]) : which == 6 ? logf(a[i]) : which == 7 ? erff(a[i])
+              : which == 8 ? tanf(a[i]) : which == 9 ? erfcf(a[i]) : atanf(a[i]);
     if(mine != mine && ref != ref) continue;
     uint32_t u, v; std::memcpy(&u, &mine, 4); std::memcpy(&v, &ref, 4);
     bad += (u != v);

@@ -27,6 +27,19 @@ def test_glibc_trig_ports_match_host_libm(hostsim):
     assert hostsim.libm_mismatches(7, a) == 0                          # glibc_erff (a spans [-7, 7])
     z = np.float32(2 * np.pi) * rng.random(n, dtype=np.float32)       # the sampler's phi range
     assert hostsim.libm_mismatches(3, z) == 0 and hostsim.libm_mismatches(4, z) == 0
+    t = (rng.random(n, dtype=np.float32) * 2 - 1) * np.float32(np.pi)  # LowSmooth: tan(pi xi)
+    t[::4] = np.float32(np.pi / 2) + (rng.random(len(t[::4]), dtype=np.float32) - np.float32(0.5)) * np.float32(1e-3)
+    assert hostsim.libm_mismatches(8, t) == 0                          # glibc_tanf (every |x| <= 100 swept once: tools/libm_sweep.cpp)
+    c = (rng.random(n, dtype=np.float32) * 2 - 1) * np.float32(12.0)
+    c[::3] *= rng.random(len(c[::3]), dtype=np.float32)
+    assert hostsim.libm_mismatches(9, c) == 0                          # glibc_erfcf (all 2^32 floats swept once)
+    assert hostsim.libm_mismatches(10, (e * np.float32(0.3))) == 0     # glibc_atanf
+
+
+def test_fused_linearizer_tables_equal_direct_evaluation(hostsim):
+    """merl_dirs_tab (what the eval-grid and loss kernels use) returns the bits of merl_dirs for every bin"""
+    hostsim.lib.hostsim_merl_dirs_tab_mismatches.restype = __import__("ctypes").c_size_t
+    assert hostsim.lib.hostsim_merl_dirs_tab_mismatches(__import__("ctypes").c_uint32(0), __import__("ctypes").c_size_t(1458000)) == 0
 
 
 def test_merl_index_bit_exact(hostsim, golden_lin):
