@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the bbm hot path on B200 (BASELINE.json configs[1] and configs[2]).
+"""bench.py - benchmark of the bbm hot path on B200 (BASELINE.json configs[0..4]).
 
 A "step" is ONE pass of the fused sample -> eval -> pdf kernel (Walter GGX) over a batch of 2^26
 synthetic (out-direction, xi) pairs:  s = sample(out, xi); rgb = eval(s.dir, out); p = pdf(s.dir, out)
@@ -9,16 +9,23 @@ synthetic (out-direction, xi) pairs:  s = sample(out, xi); rgb = eval(s.dir, out
             the library's launch stream, max over ranks.  Inputs (1.34 GB) and outputs (2.4 GB) per
             step are far larger than the 126 MB L2, so no L2 flush is needed between steps.
   e2e       the same metric through the public C ABI with HOST (pinned) buffers: every step copies
-            the inputs host->device and all outputs device->host inside the timed region.
+            the inputs host->device and ALL five outputs device->host inside the timed region.
+  e2e_variants  the same call when the caller asks for less: (a) rgb + pdf only (the other output
+            pointers NULL: not stored, not copied), (b) rgb + pdf with the inputs drawn on the device
+            (bbmcu_sample_eval_pdf_generated; 0 B up), (c) pageable instead of pinned caller memory.
   roofline  HBM: 56 B x pairs / kernel time against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the UNMODIFIED reference (oracle/_ref, native backbone, -O3) on this box's host cores,
-            on a bounded sample of the same workload.
-  loss_grad (extra) loss + analytic-gradient passes/s of Aggregate(Lambertian, CookTorrance) with nganL2
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, native backbone, -O3) on this box's host cores.
+  eval_merl_grid   configs[0]: Cook-Torrance eval over the MERL-grid directions - materialised (36 B/eval), with the
+            linearizer fused into the kernel (12 B/eval), and the reference through bsdf_ptr on 1 and all host threads.
+  loss_grad configs[2]: loss + analytic-gradient passes/s of Aggregate(Lambertian, CookTorrance) with nganL2
             over the 1 458 000-sample MERL grid, K = 256 parameter sets per launch, the sample axis
-            sharded over ranks and combined with one NCCL all-reduce per step.
+            sharded over ranks and combined inside the library's kernels over NVLink peer memory.
+  epd       configs[3]: EPD ("Holzschuch-Pacanowski") eval over the grid and a compass fit, CPU reference beside it.
+  loss_multi / sweep   configs[4]: M measured materials x K parameter sets per launch (a true DRAM workload) and a
+            bounded miniature of the material x model x metric fit sweep (`--sweep` runs the full 100 x 34 x 6).
 
-`--impl reference` times the reference's own CPU implementation of the same step (all host threads,
-bounded sample per step) and prints the same JSON line with "impl": "reference".
+`--impl reference` times the reference's own CPU implementation of the same step (all host threads, the
+full 2^26-pair batch per step) and prints the same JSON line with "impl": "reference".
 """
 import argparse
 import json
@@ -40,15 +47,26 @@ LOSS_K = 256
 FITTED = "Aggregate(Lambertian(), CookTorrance())"
 TRUTH = "Aggregate(Lambertian([0.2, 0.1, 0.05]), CookTorrance([0.3, 0.3, 0.3], 0.2, 1.5))"
 METRIC = "BSDF sample+eval+pdf throughput, Walter GGX, 2^26 (direction, xi) pairs per step per GPU"
+SWEEP_MODELS_MINI = ["CookTorrance", "GGX", "NganWard", "Phong", "LowMicrofacet", "AshikhminShirleyFull"]
+
+
+def workload_config(log2_pairs):
+    n = 1 << log2_pairs
+    return {"workload": "Walter GGX sample + eval + pdf on 2^%d (out, xi) pairs per GPU (BASELINE configs[1])" % log2_pairs,
+            "bsdf": BSDF, "pairs_per_gpu": n, "bytes_per_pair": BYTES_PER_PAIR,
+            "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (BYTES_PER_PAIR * n / 1e9)}
 
 
 def measured_traffic(n):
-    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu --set full capture,
-    scaled from the capture's launch size to this launch (profiles/ncu_traffic.json); None if absent"""
+    """dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu --set full capture of THIS launch
+    size (profiles/ncu_traffic.json: measured at 2^26 pairs per launch); scaled only if the launch size differs"""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(p):
         return None
-    return float(json.load(open(p))["dram_bytes_per_pair"]) * n
+    t = json.load(open(p))
+    if "dram_bytes_per_launch" in t and int(t.get("pairs_per_launch", 0)) == n:
+        return float(t["dram_bytes_per_launch"])
+    return float(t["dram_bytes_per_pair"]) * n
 
 
 def measured_peak():
@@ -59,9 +77,8 @@ def measured_peak():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML through nvidia_ml_py (a
-    query takes ~0.1 ms, so a 15 ms timed region still gets tens of samples); the nvidia-smi command line of the recipe is
-    the fall-back (~50 ms per query)."""
+    """SM clock and throttle reasons DURING a timed region (B200_PROFILING.md recipe).  NVML through nvidia_ml_py; the
+    nvidia-smi command line of the recipe is the fall-back (~50 ms per query)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
@@ -71,7 +88,6 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            # CUDA_VISIBLE_DEVICES renumbers CUDA devices, not NVML's: map through the UUID-free common case (identity)
             vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
             phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
             self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
@@ -132,6 +148,34 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def bind_to_gpu_numa_node(local):
+    """per-rank CPU affinity: run (and first-touch the pinned buffers) on the NUMA node the GPU hangs off, when the box
+    exposes one (/sys/bus/pci/devices/<bus id>/numa_node, local_cpulist).  Returns what was done, for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return {"numa_node": None, "bound": False}
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, devid)
+        node = int(open(path + "/numa_node").read().strip())
+        cpus = open(path + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids |= set(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if not ids:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "bound": True, "cpus": len(ids)}
+    except Exception as e:                                  # noqa: BLE001 - affinity is an optimisation, never required
+        return {"numa_node": None, "bound": False, "error": str(e)[:80]}
+
+
 def synth_host(n, seed):
     """uniform upper-hemisphere directions and xi in [0,1)^2 (numpy, SoA float32)"""
     rng = np.random.default_rng(seed)
@@ -143,15 +187,8 @@ def synth_host(n, seed):
     return out, xi
 
 
-def reference_step(ref, n, threads, seed=1):
-    out, xi = synth_host(n, seed)
-    o, x = np.ascontiguousarray(out.T), np.ascontiguousarray(xi.T)
-    t = time.perf_counter()
-    ref.sample_eval_pdf(BSDF, o, x, threads=threads)
-    return time.perf_counter() - t
-
-
 def run_reference(args):
+    """the reference's own CPU implementation of the step, on the FULL batch of the workload (same config as our arm)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -161,22 +198,37 @@ def run_reference(args):
         return
     ref = refbind.Ref("float")
     cores = host_threads()
-    n = min(1 << LOG2_PAIRS, (1 << 19) * cores)
+    n = 1 << args.log2_pairs
     out, xi = synth_host(n, 1)
     o, x = np.ascontiguousarray(out.T), np.ascontiguousarray(xi.T)
-    for _ in range(args.warmup):
+    del out, xi
+    for _ in range(min(args.warmup, 1)):                      # ~1 s per step on 16 threads: one warm-up pass pages everything in
         ref.sample_eval_pdf(BSDF, o, x, threads=cores)
     t = time.perf_counter()
     for _ in range(args.steps):
         ref.sample_eval_pdf(BSDF, o, x, threads=cores)
     dt = time.perf_counter() - t
     v = n * args.steps / dt / 1e9
-    sample = f"{n} pairs per step ({n / 2**LOG2_PAIRS:.4f} of the 2^26-pair batch), {cores} threads, oracle/_ref = unmodified reference native backbone floatRGB, -O3 -DNDEBUG"
+    sample = f"the full step: {n} pairs per step, {cores} threads, oracle/_ref = unmodified reference native backbone floatRGB, -O3 -DNDEBUG"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "G pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": "GGX sample+eval+pdf, bounded sample of the 2^26-pair batch", "pairs_per_step": n, "bsdf": BSDF},
+                      "config": workload_config(args.log2_pairs),
                       "cpu_baseline": {"value": v, "unit": "G pairs/s", "cores": cores, "kind": "reference", "sample": sample},
                       "e2e": {"value": v, "unit": "G pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def synthetic_materials(count, seed=2026):
+    """BSDF strings of `count` synthetic MERL-shaped materials: Lambertian + Cook-Torrance with seeded parameters in the range
+    of the reference's fits/low_cooktorrance_E1.fit entries (diffuse/specular albedo 0.005-0.5, roughness 0.01-0.5, eta 1.2-2.5)"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for m in range(count):
+        d = np.exp(rng.uniform(np.log(0.005), np.log(0.5), 3))
+        s = np.exp(rng.uniform(np.log(0.005), np.log(0.5), 3))
+        r = float(np.exp(rng.uniform(np.log(0.01), np.log(0.5))))
+        eta = float(rng.uniform(1.2, 2.5))
+        out["material-%03d" % m] = "Aggregate(Lambertian([%.5g, %.5g, %.5g]), LowCookTorrance([%.5g, %.5g, %.5g], %.5g, %.5g))" % (*d, *s, r, eta)
+    return out
 
 
 def main():
@@ -189,6 +241,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-loss", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[0], [3], [4] legs")
+    ap.add_argument("--sweep", action="store_true", help="run the FULL configs[4] sweep (100 materials x 34 models x 6 metrics) instead of the miniature")
+    ap.add_argument("--sweep-steps", type=int, default=30)
+    ap.add_argument("--sweep-materials", type=int, default=100)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -202,6 +258,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # affinity only in the multi-GPU runs: at N = 1 the CPU baseline of the same process must see every host core
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"numa_node": None, "bound": False}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -209,6 +267,7 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     bsdf = bb.Bsdf(BSDF)
     n = 1 << args.log2_pairs
+    peak, peak_src = measured_peak()
 
     def barrier():
         torch.cuda.synchronize()
@@ -222,6 +281,19 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def timed(step, steps, warm=3):
+        """ms per step: CUDA events on the library's stream around `steps` calls, max over ranks"""
+        for _ in range(warm):
+            step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            step()
+        b.record(stream)
+        ctx.synchronize()
+        return max_over_ranks(a.elapsed_time(b)) / steps
 
     # ---- device-resident inputs (synthetic, generated on the device) --------------------------------
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -243,32 +315,38 @@ def main():
     barrier()
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-        ctx.synchronize()
-        launches = ctx.launches - l0
-        in_region = len(clocks.sm)
-        # a query takes milliseconds and K steps may take fewer: keep the same kernel running (untimed, after e1) until the
-        # sampler has seen the device under this load a few times
-        t_stop = time.perf_counter() + 0.5
-        while len(clocks.sm) < in_region + 5 and time.perf_counter() < t_stop:
-            step()
-            ctx.synchronize()
-        barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    ctx.synchronize()
+    launches = ctx.launches - l0
+    barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     ms_per_step = ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e9
     kernel_ms = e0.elapsed_time(e1) / args.steps            # one launch per step: the step IS the dominant kernel
-    peak, peak_src = measured_peak()
     achieved = BYTES_PER_PAIR * n / (kernel_ms * 1e-3) / 1e9
+    # clocks: the K timed steps above last ~15 ms, fewer than an NVML query on some boxes; a SECOND timed region of the same
+    # step, long enough (>= 150 ms of kernels) to be sampled from inside, gives the clocks and a sustained rate beside them
+    long_steps = max(args.steps, int(np.ceil(150.0 / max(kernel_ms, 1e-3))))
+    with ClockSampler(local) as clocks:
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = len(clocks.sm)
+        c0.record(stream)
+        for _ in range(long_steps):
+            step()
+        c1.record(stream)
+        ctx.synchronize()
+        in_region = len(clocks.sm) - before
     clk = clocks.summary()
-    clk["samples_in_timed_region"] = in_region
+    sustained_ms = max_over_ranks(c0.elapsed_time(c1)) / long_steps
+    clk.update({"samples_in_timed_region": in_region, "region": "%d further steps of the same kernel, timed with CUDA events (%.0f ms)" % (long_steps, sustained_ms * long_steps),
+                "sustained_value": world * n / (sustained_ms * 1e-3) / 1e9})
 
-    # ---- e2e: host (pinned) buffers through the same public call -----------------------------------
-    e2e = None
+    # ---- e2e: host buffers through the same public call -----------------------------------------------------------
+    e2e, e2e_variants = None, None
     if not args.no_e2e:
         pin = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, pin_memory=True)
         h_out, h_xi = pin((3, n)), pin((2, n))
@@ -276,19 +354,41 @@ def main():
         h_res = (pin((3, n)), pin(n), pin(n, torch.int32), pin((3, n)), pin(n))
         a_out, a_xi = h_out.numpy(), h_xi.numpy()
         a_res = tuple(t.numpy() for t in h_res)
-        for _ in range(2):
-            ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res)       # returns after the D2H copies completed
-        torch.cuda.synchronize()
-        dt_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-        e2e = {"value": world * n / (dt_ms / args.steps * 1e-3) / 1e9, "unit": "G pairs/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 36 * n,
-               "ms_per_step": dt_ms / args.steps}
-        # sanity: the host path returns what the device path computed
+
+        def wall(fn, steps):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()                                                 # returns after the D2H copies completed
+            torch.cuda.synchronize()
+            return max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+
+        full_ms = wall(lambda: ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res), args.steps)
+        e2e = {"value": world * n / (full_ms * 1e-3) / 1e9, "unit": "G pairs/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 36 * n,
+               "ms_per_step": full_ms, "contract": "host (pinned) inputs, all five outputs copied back", "numa": numa}
+        # the host path returns exactly what the device path computed
         chk = slice(0, 1 << 16)
-        assert np.array_equal(a_res[4][chk].view(np.uint32), outs[4][chk].cpu().numpy().view(np.uint32)) or rank != 0 or True
+        for host_arr, dev_t in zip(a_res, outs):
+            assert np.array_equal(np.ascontiguousarray(host_arr[..., chk]).view(np.uint32), dev_t[..., chk].cpu().numpy().view(np.uint32)), "host path differs from device path"
+        e2e_variants = []
+        two = (None, None, None, a_res[3], a_res[4])
+        red_ms = wall(lambda: ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=two), args.steps)
+        e2e_variants.append({"contract": "host (pinned) inputs, rgb + pdf copied back (other output pointers NULL)", "value": world * n / (red_ms * 1e-3) / 1e9,
+                             "unit": "G pairs/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 16 * n, "ms_per_step": red_ms})
+        gen_ms = wall(lambda: ctx.sample_eval_pdf_generated(bsdf, 1 + rank, 0, n, outputs=two), args.steps)
+        e2e_variants.append({"contract": "inputs drawn on the device (Philox; bbmcu_sample_eval_pdf_generated), rgb + pdf copied back", "value": world * n / (gen_ms * 1e-3) / 1e9,
+                             "unit": "G pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16 * n, "ms_per_step": gen_ms})
+        assert np.array_equal(a_res[4][chk].view(np.uint32), ctx.sample_eval_pdf_generated(bsdf, 1 + rank, 0, 1 << 16, like=out, want=("pdf",))[4].cpu().numpy().view(np.uint32))
+        if rank == 0 and world == 1:
+            np_ = 1 << 24                                            # pageable caller memory (numpy), a quarter of a... 1/4 of the batch
+            p_out, p_xi = np.array(a_out[:, :np_]), np.array(a_xi[:, :np_])
+            p_res = (np.empty((3, np_), np.float32), np.empty(np_, np.float32), np.empty(np_, np.int32), np.empty((3, np_), np.float32), np.empty(np_, np.float32))
+            pg_ms = wall(lambda: ctx.sample_eval_pdf(bsdf, p_out, p_xi, outputs=p_res), 5)
+            e2e_variants.append({"contract": "PAGEABLE host inputs and outputs (internal pinned ring), all five outputs, 2^24 pairs per call", "value": np_ / (pg_ms * 1e-3) / 1e9,
+                                 "unit": "G pairs/s", "h2d_bytes_per_step": 20 * np_, "d2h_bytes_per_step": 36 * np_, "ms_per_step": pg_ms})
+            del p_out, p_xi, p_res
         del h_out, h_xi, h_res
 
     # ---- loss + gradient passes (BASELINE configs[2]), sample axis sharded over ranks --------------------
@@ -364,16 +464,11 @@ def main():
         for kk in (1, 16):
             pk = params[:kk]
             rk = torch.zeros((kk, 1 + P), device=dev, dtype=torch.float64)
-            for _ in range(3):
-                L.eval_device(fitted, pk, rk)
-            ctx.synchronize()
-            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            h0.record(stream)
-            for _ in range(20):
-                L.eval_device(fitted, pk, rk)
-            h1.record(stream)
-            ctx.synchronize()
-            by_k[str(kk)] = kk / (max_over_ranks(h0.elapsed_time(h1)) / 20 * 1e-3)       # this rank's shard only, no collective
+            by_k[str(kk)] = kk / (timed(lambda: L.eval_device(fitted, pk, rk), 20) * 1e-3)       # this rank's shard only, no collective
+        # the same pass reading MATERIALISED direction planes (36 B per sample instead of 12): what round 1 shipped
+        Lm = ctx.loss("nganL2", truth, None, first=first, count=count, materialise=True)
+        mat_ms = timed(lambda: Lm.eval_device(fitted, params, res), nl)
+        del Lm
         if world == 1:
             collective = None
         elif L_peer is not None:
@@ -381,65 +476,191 @@ def main():
         else:
             collective = "nccl all_reduce of K x (1+P) doubles (peer windows unavailable: %s)" % peer_error
         loss_info = {"value": passes, "passes_per_s_by_K_no_collective": by_k, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
-                     "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": collective,
+                     "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": collective, "linearizer": "fused into the kernel (12 B per sample)",
+                     "passes_per_s_with_materialised_directions_no_collective": LOSS_K / (mat_ms * 1e-3),
                      "passes_per_s_with_nccl_all_reduce": (LOSS_K / (nccl_ms * 1e-3)) if nccl_ms else None,
-                     "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / peak,
+                     "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / (world * peak),
+                     "frac_note": "whole-job passes/s x 12 B x N / (n_gpus x measured HBM peak); the grid is L2-resident, the kernel is issue-bound",
                      "gpu_launches": launches_loss, "loss0": loss0}
 
-    # ---- extra (BASELINE configs[0], GPU side): Cook-Torrance eval over the MERL-grid directions ---------------------
-    # materialised SoA directions, 24 B in + 12 B out = 36 B/eval; the 1 458 000 grid directions are tiled 32x so the
-    # working set (1.7 GB) is far beyond L2
+    # ---- configs[0]: Cook-Torrance eval over the MERL-grid directions -------------------------------------------------
     eval_info = None
     if not args.no_loss:
         N = bb.MERL_BINS
         gi, go = ctx.merl_dirs(0, N, like=out)
         ctx.synchronize()
-        reps = 32
+        reps = 32                                                    # the 1 458 000 grid directions tiled 32x: working set 1.7 GB, far beyond L2
         gi, go = gi.repeat(1, reps).contiguous(), go.repeat(1, reps).contiguous()
         ne = N * reps
         rgb = torch.empty((3, ne), device=dev)
         ct = bb.Bsdf("CookTorrance()")
         torch.cuda.synchronize()
-        for _ in range(3):
-            ctx.eval(ct, gi, go, rgb=rgb)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(args.steps):
-            ctx.eval(ct, gi, go, rgb=rgb)
-        g1.record(stream)
-        ctx.synchronize()
-        ms_e = max_over_ranks(g0.elapsed_time(g1)) / args.steps
+        ms_e = timed(lambda: ctx.eval(ct, gi, go, rgb=rgb), args.steps)
         ev_s = world * ne / (ms_e * 1e-3) / 1e9
+        del gi, go
+        # linearizer fused into the kernel: 0 B in, 12 B out per eval; 32 launches over the grid write 32 different output
+        # slices so the stores go to DRAM like the materialised run's
+        rgb1 = [torch.empty((3, N), device=dev) for _ in range(reps)]
+        ms_f = timed(lambda: [ctx.eval_merl_grid(ct, 0, N, rgb=t) for t in rgb1], max(3, args.steps // 4)) / reps
+        fused_s = world * N / (ms_f * 1e-3) / 1e9
         eval_info = {"value": ev_s, "unit": "G evals/s", "bsdf": "CookTorrance()", "evals_per_gpu": ne, "bytes_per_eval": 36,
                      "achieved_gbs_per_gpu": 36 * ne / (ms_e * 1e-3) / 1e9, "frac_of_hbm_roofline": 36 * ne / (ms_e * 1e-3) / 1e9 / peak,
-                     "kernel": "k_foreach4<EvalOp<BsdfSingle<CookTorrance>>>"}
-        del gi, go, rgb
+                     "kernel": "k_foreach4<EvalOp<BsdfSingle<CookTorrance>>>",
+                     "fused_linearizer": {"value": fused_s, "unit": "G evals/s", "bytes_per_eval": 12, "evals_per_launch": N,
+                                          "achieved_gbs_per_gpu": 12 * N / (ms_f * 1e-3) / 1e9, "frac_of_hbm_roofline": 12 * N / (ms_f * 1e-3) / 1e9 / peak,
+                                          "kernel": "k_foreach4<EvalGridOp<BsdfSingle<CookTorrance>>>", "note": "one launch per grid (1.458 M evals, ~8 us): launch-bound; bound by instruction issue, not HBM"}}
+        del rgb, rgb1
 
-    # ---- CPU baseline: the unmodified reference on this box's host cores (rank 0, N = 1 only) -------------
+    # ---- CPU baselines: the unmodified reference on this box's host cores (rank 0, N = 1 only) -------------
     cpu = None
+    ref = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import refbind
             if refbind.available():
                 ref = refbind.Ref("float")
                 cores = host_threads()
-                nb = n                                                    # the whole 2^26-pair step: ~1 s on 16 threads, ~20 core-seconds with the repeats
-                reference_step(ref, min(nb, 1 << 18), cores)                       # warm
-                dt = min(reference_step(ref, nb, cores) for _ in range(2))
-                cpu = {"value": nb / dt / 1e9, "unit": "G pairs/s", "cores": cores, "kind": "reference",
-                       "sample": f"{nb} pairs ({nb / n:.4f} of one step), best of 2, oracle/_ref = unmodified reference native backbone floatRGB (-O3 -DNDEBUG, no -march=native), {cores} threads"}
+                o_h, x_h = synth_host(n, 1)
+                o_a, x_a = np.ascontiguousarray(o_h.T), np.ascontiguousarray(x_h.T)
+                del o_h, x_h
+                ref.sample_eval_pdf(BSDF, o_a[:1 << 18], x_a[:1 << 18], threads=cores)                       # warm
+                dts = []
+                for _ in range(2):
+                    t0 = time.perf_counter()
+                    ref.sample_eval_pdf(BSDF, o_a, x_a, threads=cores)
+                    dts.append(time.perf_counter() - t0)
+                dt = min(dts)
+                cpu = {"value": n / dt / 1e9, "unit": "G pairs/s", "cores": cores, "kind": "reference",
+                       "sample": f"{n} pairs (1.0000 of one step), best of 2, oracle/_ref = unmodified reference native backbone floatRGB (-O3 -DNDEBUG, no -march=native), {cores} threads"}
+                del o_a, x_a
         except Exception as e:   # the baseline is reported, never required
             cpu = {"value": None, "unit": "G pairs/s", "cores": host_threads(), "kind": "reference", "sample": f"failed: {e}"}
+    if ref is not None and eval_info is not None:
+        # configs[0], CPU side: Cook-Torrance eval over all 1 458 000 grid directions through bsdf_ptr (checkBsdf-style,
+        # bin/checkBsdf.cpp:123-141), 1 thread exactly as shipped and all host threads
+        gi_h, go_h = ctx.merl_dirs(0, bb.MERL_BINS)
+        ai, ao = np.ascontiguousarray(gi_h.T), np.ascontiguousarray(go_h.T)
+        cores = host_threads()
+        def best(threads, reps_):
+            b = 1e30
+            for _ in range(reps_):
+                t0 = time.perf_counter(); ref.eval("CookTorrance()", ai, ao, threads=threads); b = min(b, time.perf_counter() - t0)
+            return b
+        t1, tall = best(1, 3), best(cores, 5)
+        eval_info["cpu_reference"] = {"unit": "G evals/s", "evals": bb.MERL_BINS, "one_thread": bb.MERL_BINS / t1 / 1e9, "all_threads": bb.MERL_BINS / tall / 1e9, "cores": cores,
+                                      "how": "oracle/_ref: bsdf_import('CookTorrance()') -> bsdf_ptr::eval per direction pair, best of 3 / 5"}
+
+    # ---- configs[3]: EPD ("Holzschuch-Pacanowski") eval over the grid and a fit, tables staged on chip ---------------------------------------
+    epd_info = None
+    if not args.no_extras and not args.no_loss:
+        N = bb.MERL_BINS
+        epd = bb.Bsdf("EPD(0.05, 0.5, [1.5, 0.5])")
+        reps = 8
+        gi, go = ctx.merl_dirs(0, N, like=out)
+        gi, go = gi.repeat(1, reps).contiguous(), go.repeat(1, reps).contiguous()
+        rgb = torch.empty((3, N * reps), device=dev)
+        ms_e = timed(lambda: ctx.eval(epd, gi, go, rgb=rgb), max(3, args.steps // 2))
+        del gi, go, rgb
+        grid = bb.spherical_grid((31, 16), (1, 9))
+        epd_truth, epd_start = "EPD(0.05, 0.8, [1.5, 0.5])", "EPD(0.1, 0.5, [1.3, 0.2])"
+        from bbm_b200 import fit as bfit
+        Le = ctx.loss("standardLog", bb.Bsdf(epd_truth), grid)
+        fb = bb.Bsdf(epd_start)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        opt = bfit.CompassBatched(Le, fb, fb.parameter_lower_bound(), fb.parameter_upper_bound())
+        nsteps = 0
+        for _ in range(60):
+            if opt.is_converged():
+                break
+            opt.step(); nsteps += 1
+        fit_s = time.perf_counter() - t0
+        epd_info = {"eval": {"value": world * N * reps / (ms_e * 1e-3) / 1e9, "unit": "G evals/s", "bsdf": "EPD(0.05, 0.5, [1.5, 0.5])", "evals_per_gpu": N * reps,
+                             "note": "G1 rows of the launch-uniform p staged in shared memory (2 x 1000 floats)"},
+                    "fit": {"steps": nsteps, "seconds": fit_s, "steps_per_s": nsteps / fit_s, "samples": 31 * 16 * 9, "P": 4, "final_loss": float(opt.loss_value),
+                            "truth": epd_truth, "start": epd_start, "metric": "standardLog", "optimizer": "compass, all 2P probes of a step in one launch"}}
+        if ref is not None:
+            from oracle.refbind import sph_desc
+            gi_h, go_h = ctx.merl_dirs(0, N)
+            sub = slice(0, 1 << 18)
+            ai, ao = np.ascontiguousarray(gi_h.T[sub]), np.ascontiguousarray(go_h.T[sub])
+            cores = host_threads()
+            t0 = time.perf_counter(); ref.eval("EPD(0.05, 0.5, [1.5, 0.5])", ai, ao, threads=cores); te = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            trace, _, _ = ref.compass("standardLog", sph_desc((31, 16), (1, 9)), epd_start, epd_truth, 10)
+            tf = time.perf_counter() - t0
+            epd_info["cpu_reference"] = {"eval_G_evals_per_s_all_threads": (1 << 18) / te / 1e9, "cores": cores, "fit_steps_per_s_one_thread": len(trace) / tf,
+                                         "fit_steps_timed": int(len(trace)), "how": "oracle/_ref: bsdf_ptr eval on 2^18 grid directions; unmodified bbm::compass, 10 steps"}
+
+    # ---- configs[4]: many materials per launch, and the fit sweep ---------------------------------------------------------------------------
+    multi_info, sweep_info = None, None
+    if not args.no_extras and not args.no_loss:
+        from bbm_b200 import fit as bfit
+        n_mat_total = args.sweep_materials if args.sweep else 8 * world
+        mats = synthetic_materials(n_mat_total)
+        names = sorted(mats)
+        from bbm_b200.shard import shard_range
+        f0_, c0_ = shard_range(len(names), rank, world)
+        mine = names[f0_:f0_ + c0_]
+        tables = {m: ctx.eval_merl_grid(bb.Bsdf(mats[m]), like=out) for m in mine}          # resident on the device, 17.5 MB each
+        ctx.synchronize()
+        Lmulti = ctx.loss("nganL2", [tables[m] for m in mine], None)
+        fitted = bb.Bsdf(FITTED)
+        P = len(fitted.parameter_values())
+        M = len(mine)
+        # (a) M materials x 1 parameter set, value only: every launch streams M x 17.5 MB of measured data once
+        p1 = np.tile(fitted.parameter_values(), (M, 1, 1))
+        res16 = torch.zeros((M, 16, 1 + P), device=dev, dtype=torch.float64)
+        p16 = np.tile(p1, (1, 16, 1))
+        Lv = Lmulti
+        ms_v = timed(lambda: Lv.eval_multi(fitted, p1), max(5, args.steps // 2))        # value only (host result: includes the D2H of M doubles)
+        ms_g = timed(lambda: Lv.eval_multi_device(fitted, p16, res16), max(5, args.steps // 2))
+        bytes_v = 12 * bb.MERL_BINS * M
+        multi_info = {"materials_per_gpu": M, "value_only_K1": {"passes_per_s": world * M / (ms_v * 1e-3), "ms_per_launch": ms_v, "algorithmic_bytes_per_launch": bytes_v,
+                                                                 "achieved_gbs_per_gpu": bytes_v / (ms_v * 1e-3) / 1e9, "frac_of_hbm_roofline": bytes_v / (ms_v * 1e-3) / 1e9 / peak},
+                      "loss_grad_K16": {"passes_per_s": world * M * 16 / (ms_g * 1e-3), "ms_per_launch": ms_g},
+                      "note": "one launch = M materials x K parameter sets (grid z = material); %d x 17.5 MB of tabulated data per GPU%s" % (M, " exceed the 126 MB L2" if M * 17.5 > 126 else " (fits the 126 MB L2: not a DRAM roofline at this M)")}
+        del res16
+        # (b) the fit sweep, split by material over the ranks; no collective
+        models = [m for m in bb.model_names() if m != "Merl"] if args.sweep else SWEEP_MODELS_MINI
+        metrics = bb.METRICS if args.sweep else ["nganL2", "standardLog"]
+        max_steps = args.sweep_steps if args.sweep else 10
+        per_model = {}
+        def progress(mod, met, secs, steps, nm, k):
+            per_model.setdefault(mod, [0.0, 0])
+            per_model[mod][0] += secs; per_model[mod][1] += steps * nm * k
+        barrier()
+        t0 = time.perf_counter()
+        result = bfit.run_sweep_by_material(ctx, tables, models, metrics, 0, 1, max_steps, None, loss=Lmulti, progress=progress)      # this rank's materials only
+        ctx.synchronize()
+        mine_s = time.perf_counter() - t0
+        total_s = max_over_ranks(mine_s * 1e3) / 1e3
+        fits = len(models) * len(metrics) * n_mat_total
+        finite = sum(1 for v in result.values() if np.isfinite(v[1]))
+        if world > 1:
+            times = [None] * world
+            dist.all_gather_object(times, mine_s)
+        else:
+            times = [mine_s]
+        sweep_info = {"kind": "full (BASELINE configs[4])" if args.sweep else "miniature of configs[4] (bench.py --sweep runs 100 materials x 34 models x 6 metrics)",
+                      "materials": n_mat_total, "models": len(models), "metrics": len(metrics), "fits": fits, "compass_steps_per_fit": max_steps,
+                      "seconds": total_s, "fits_per_s": fits / total_s, "rank_seconds": [round(float(t), 3) for t in times], "finite_fits_this_rank": finite, "fits_this_rank": len(result),
+                      "partition": "by material (each rank keeps its materials' tables resident as one batched loss; one launch per compass step for all of them); no collective",
+                      "seconds_by_model_this_rank": {k: round(v[0], 3) for k, v in sorted(per_model.items(), key=lambda kv: -kv[1][0])[:8]},
+                      "loss_passes_this_rank": int(sum(v[1] for v in per_model.values())), "data": "synthetic Lambertian + LowCookTorrance materials (seeded), tabulated on the MERL grid"}
+        if args.sweep and rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump({"sweep": sweep_info, "seconds_by_model_rank0": {k: v[0] for k, v in per_model.items()},
+                       "sample_results": {"|".join(k): v for k, v in list(result.items())[:40]}}, open(os.path.join(ROOT, "gpurun_out", "sweep_full.json"), "w"), indent=1)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "G pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "Walter GGX sample + eval + pdf on 2^%d (out, xi) pairs per GPU (BASELINE configs[1])" % args.log2_pairs,
-                           "bsdf": BSDF, "pairs_per_gpu": n, "bytes_per_pair": BYTES_PER_PAIR, "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (BYTES_PER_PAIR * n / 1e9)},
+                "config": workload_config(args.log2_pairs),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(n), "peak_source": peak_src,
-                             "kernel": "k_foreach4<SampleEvalPdfOp<BsdfSingle<GGX>>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info, "eval_merl_grid": eval_info}
+                             "kernel": "k_foreach4<SampleEvalPdfOpT<BsdfSingle<GGX>, false>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
+                "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info, "eval_merl_grid": eval_info,
+                "epd": epd_info, "loss_multi": multi_info, "sweep": sweep_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

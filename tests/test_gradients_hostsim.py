@@ -15,7 +15,11 @@ CASES = [
     ("Phong([0.4, 0.3, 0.2], 12)", "Phong([0.5, 0.2, 0.1], 20)"),
     ("Lafortune([0.4, 0.3, 0.2], [-0.6, -0.5], 0.6, 9)", "Lafortune([0.5, 0.2, 0.1], [-0.58, -0.58], 0.57, 12)"),
     ("NganLafortune([0.4, 0.3, 0.2], -0.62, 0.6, 9)", "NganLafortune([0.5, 0.2, 0.1], -0.58, 0.57, 12)"),
+    ("Ward([0.4, 0.3, 0.2], [0.2, 0.3])", "Ward([0.5, 0.2, 0.1], [0.25, 0.25])"),
+    ("WardDuer([0.4, 0.3, 0.2], [0.2, 0.3])", "WardDuer([0.5, 0.2, 0.1], [0.25, 0.25])"),
     ("WardDuerGeislerMoroder([0.4, 0.3, 0.2], [0.2, 0.3])", "WardDuerGeislerMoroder([0.5, 0.2, 0.1], [0.25, 0.25])"),
+    ("NganWard([0.4, 0.3, 0.2], 0.2)", "NganWard([0.5, 0.2, 0.1], 0.25)"),
+    ("NganWardDuer([0.4, 0.3, 0.2], 0.2)", "NganWardDuer([0.5, 0.2, 0.1], 0.25)"),
     ("AshikhminShirley([0.2, 0.3, 0.4], [20, 30])", "AshikhminShirley([0.3, 0.3, 0.3], [25, 25])"),
     ("AshikhminShirleyFull([0.3, 0.2, 0.1], [0.2, 0.3, 0.4], [20, 30])", "AshikhminShirleyFull([0.2, 0.2, 0.2], [0.3, 0.3, 0.3], [25, 25])"),
     ("NganAshikhminShirley([0.4, 0.3, 0.2], 0.2, 20)", "NganAshikhminShirley([0.5, 0.2, 0.1], 0.3, 25)"),
@@ -41,54 +45,65 @@ CASES = [
 ]
 
 
+GRID = ((11, 6), (4, 5))
+T0, TP = 0.05, 1.4            # stay off the zenith (He's geometrical factor is 0/0 at normal incidence) and off the horizon (Ward-type models are NaN/Inf at z == 0, fact 7)
+
+
+def check_gradient_case(ref, refd, metric, fitted, truth, loss, grad):
+    """loss / grad of `fitted` against `truth` over GRID (computed by the caller: host-compiled or device kernels):
+    value against the floatRGB reference's per-sample terms accumulated in double, gradient against
+    central differences of the doubleRGB reference loss.  Tolerance per component: 1e-4 relative plus 3e-6 of the largest
+    component (central differences of a double loss with h = 1e-6 carry ~1e-10 / 1e-6 of absolute noise)."""
+    import bbm_b200 as bb
+    hp = float(np.float32(2) * np.float32(np.pi))
+    df = sph_desc(*GRID, start_in=(0, T0), start_out=(0, T0), end_in=(hp, TP), end_out=(hp, TP))
+    dd = sph_desc(*GRID, real=np.float64, start_in=(0, T0), start_out=(0, T0), end_in=(2 * np.pi, TP), end_out=(2 * np.pi, TP))
+    p0 = bb.Bsdf(fitted).parameter_values()
+    P = len(p0)
+
+    def central(r, desc, h_rel):
+        rows = []
+        for j in range(P):
+            h = h_rel * max(1.0, abs(p0[j]))
+            pp, pm = p0.copy(), p0.copy()
+            pp[j] += h
+            pm[j] -= h
+            rows += [pp, pm]
+        l = r.loss_at(metric, desc, fitted, truth, np.stack(rows))
+        return np.array([(l[2 * j] - l[2 * j + 1]) / (2 * h_rel * max(1.0, abs(p0[j]))) for j in range(P)])
+    lf = ref.loss_at(metric, df, fitted, truth, p0[None])[0]
+    assert abs(loss - lf) <= 1e-5 * abs(lf), (fitted, loss, lf)
+    l0 = refd.loss_at(metric, dd, fitted, truth, p0[None])[0]
+    if abs(lf - l0) <= 2e-5 * abs(l0):
+        fd, rel, floor = central(refd, dd, 1e-6), 1e-4, 3e-6
+    else:
+        # the He family is a DIFFERENT function in floatRGB and doubleRGB: its adaptive Taylor series stops on
+        # hmin(term) < Constants::Epsilon() (he.h:459), i.e. FLT_EPSILON vs DBL_EPSILON, and the channel with
+        # the smallest term truncates the others (0.6 % in blue here).  The float function is the parity target,
+        # so its gradient is checked against differences of the floatRGB reference.  That function also JUMPS
+        # whenever the number of series terms changes with g(roughness) - a wide finite difference averages over the
+        # jumps, a derivative does not - so the oracle is the MEDIAN slope of 40 short segments per parameter.
+        assert "He" in fitted
+        fd = np.empty(P)
+        for j in range(P):
+            d = 2.5e-5 * max(1.0, abs(p0[j]))
+            pts = np.tile(p0, (41, 1))
+            pts[:, j] += np.arange(-20, 21) * d
+            fd[j] = np.median(np.diff(ref.loss_at(metric, df, fitted, truth, pts)) / d)
+        rel, floor = 5e-3, 5e-3
+    tol = rel * np.abs(fd) + floor * np.abs(fd).max()
+    assert np.all(np.abs(grad - fd) <= tol), (fitted, metric, rel, grad, fd, np.abs(grad - fd) / tol)
+
+
 @pytest.mark.parametrize("metric", ["nganL2", "standardLog"])
 def test_gradient_vs_finite_differences_of_double_reference(hostsim, ref, refd, metric):
     import bbm_b200 as bb
-    hp, tp = float(np.float32(2) * np.float32(np.pi)), float(np.float32(0.5) * np.float32(np.pi))
-    grid = ((11, 6), (4, 5))
+    hp = float(np.float32(2) * np.float32(np.pi))
     N = 11 * 6 * 4 * 5
-    tp = 1.4                                   # stay off the horizon: Ward-type models are NaN/Inf at z == 0 (fact 7)
-    t0 = 0.05                                  # ... and off the zenith: He's geometrical factor is 0/0 at normal incidence
-    df = sph_desc(*grid, start_in=(0, t0), start_out=(0, t0), end_in=(hp, tp), end_out=(hp, tp))
-    dd = sph_desc(*grid, real=np.float64, start_in=(0, t0), start_out=(0, t0), end_in=(2 * np.pi, tp), end_out=(2 * np.pi, tp))
-    i, o = hostsim.spherical_dirs([11, 6, 4, 5], [0, t0, hp, tp, 0, t0, hp, tp], 0, N)
+    i, o = hostsim.spherical_dirs([11, 6, 4, 5], [0, T0, hp, TP, 0, T0, hp, TP], 0, N)
     m = bb.METRICS.index(metric)
     for fitted, truth in CASES:
-        p0 = bb.Bsdf(fitted).parameter_values()
-        P = len(p0)
+        P = len(bb.Bsdf(fitted).parameter_values())
         tv = hostsim.eval(truth, i, o)
         loss, grad, _ = hostsim.loss(fitted, m, i, o, tv, nparams=P)
-        def central(r, desc, h_rel):
-            rows = []
-            for j in range(P):
-                h = h_rel * max(1.0, abs(p0[j]))
-                pp, pm = p0.copy(), p0.copy()
-                pp[j] += h
-                pm[j] -= h
-                rows += [pp, pm]
-            l = r.loss_at(metric, desc, fitted, truth, np.stack(rows))
-            return np.array([(l[2 * j] - l[2 * j + 1]) / (2 * h_rel * max(1.0, abs(p0[j]))) for j in range(P)])
-        # value: against the floatRGB reference's per-sample terms accumulated in double
-        lf = ref.loss_at(metric, df, fitted, truth, p0[None])[0]
-        assert abs(loss - lf) <= 1e-5 * abs(lf), (fitted, loss, lf)
-        l0 = refd.loss_at(metric, dd, fitted, truth, p0[None])[0]
-        if abs(lf - l0) <= 2e-5 * abs(l0):
-            # gradient oracle proper: 1e-4 against central differences of the doubleRGB reference loss
-            fd, rel = central(refd, dd, 1e-6), 1e-4
-        else:
-            # the He family is a DIFFERENT function in floatRGB and doubleRGB: its adaptive Taylor series stops on
-            # hmin(term) < Constants::Epsilon() (he.h:459), i.e. FLT_EPSILON vs DBL_EPSILON, and the channel with
-            # the smallest term truncates the others (0.6 % in blue here).  The float function is the parity target,
-            # so its gradient is checked against differences of the floatRGB reference.  That function also JUMPS
-            # whenever the number of series terms changes with g(roughness) - a wide finite difference averages over the
-            # jumps, a derivative does not - so the oracle is the MEDIAN slope of 40 short segments per parameter.
-            assert "He" in fitted
-            fd = np.empty(P)
-            for j in range(P):
-                d = 2.5e-5 * max(1.0, abs(p0[j]))
-                pts = np.tile(p0, (41, 1))
-                pts[:, j] += np.arange(-20, 21) * d
-                fd[j] = np.median(np.diff(ref.loss_at(metric, df, fitted, truth, pts)) / d)
-            rel = 5e-3
-        tol = rel * np.abs(fd) + rel * np.abs(fd).max()
-        assert np.all(np.abs(grad - fd) <= tol), (fitted, metric, rel, grad, fd)
+        check_gradient_case(ref, refd, metric, fitted, truth, loss, grad)
