@@ -491,10 +491,12 @@ class Loss:
                                            g.ctypes.data_as(C.c_void_p) if grad else None, None), self.ctx._h)
         return (loss, g) if grad else loss
 
-    def eval_multi_device(self, bsdf, params, device_out):
+    def eval_multi_device(self, bsdf, params, device_out, grad=True):
+        """same, rows [loss, gradient...] left in a CUDA buffer of (M, K, 1+P) doubles on the context's stream; grad=False
+        runs the value-only kernel (the gradient columns are then zero)"""
         params = np.ascontiguousarray(params, np.float64)
-        _check(lib().bbmcu_loss_eval_multi(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(params.shape[1]), None, None,
-                                           _ptr(device_out)), self.ctx._h)
+        _check(lib().bbmcu_loss_eval_multi_ex(self._h, bsdf._h, params.ctypes.data_as(C.c_void_p), C.c_size_t(params.shape[1]), None, None, _ptr(device_out),
+                                              C.c_int(1 if grad else 0)), self.ctx._h)
 
     def terms(self, bsdf, count=None, material=0):
         """per-sample terms l(idx) of this shard (sampledlossfunction::operator()(idx)); `count` is ignored (kept for

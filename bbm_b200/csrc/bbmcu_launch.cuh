@@ -23,6 +23,19 @@ template<class Op> static void launch_foreach4(bbmcu_ctx* ctx, cudaStream_t stre
   size_t groups = (n + kVec - 1) / kVec;
   bind_device_tables();
   unsigned grid = grid_for(ctx, groups, Op::kBlock, 8*256/Op::kBlock);
+  if constexpr (UsesLinTab<Op>::value)
+  {
+    // every block stages the 3.6 KB linearizer table first: one resident wave striding over the grid pays that once per SM slot
+    // (the whole MERL grid is 1424 blocks' worth of work - a prologue per block would be a fifth of the kernel)
+    static int per_sm = 0;
+    if(per_sm == 0)
+    {
+      BBMCU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_foreach4<Op>, Op::kBlock, 0));
+      if(per_sm < 1) per_sm = 1;
+    }
+    const unsigned wave = (unsigned)ctx->sm_count * (unsigned)per_sm;
+    if(grid > wave) grid = wave;
+  }
   if constexpr (Op::kHasBsdf)
   {
     if constexpr (Op::kTables)

@@ -26,10 +26,27 @@ namespace bbmcu {
 BBMCU_D float lin_phi(f3 v) { float r = glibc_atan2f(v.y, v.x); return r < 0.0f ? r + kTwoPi : r; }
 BBMCU_D float lin_theta(f3 v) { return sph_theta(v); }
 
+// products and sums rounded one by one whatever the translation unit's -fmad setting: these run inside the loss kernels
+// (built -fmad=true) as well and must return the bits of the -fmad=false build there too
+BBMCU_D float mul_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+BBMCU_D float add_rn(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+BBMCU_D float dot3_rn(float a0, float a1, float a2, f3 v) { return add_rn(add_rn(add_rn(0.0f, mul_rn(a0, v.x)), mul_rn(a1, v.y)), mul_rn(a2, v.z)); }   // ((0 + a0 x) + a1 y) + a2 z  (horizontal.h:87-91)
 BBMCU_D f3 rot_z(float c, float s, f3 v)   // rotationZ(cossin) * v: rows (c,-s,0), (s,c,0), (0,0,1)  (transform.h:74-81, mat.h:107-116)
-{ return make_f3((0.0f + c*v.x) + (-s)*v.y + 0.0f*v.z, (0.0f + s*v.x) + c*v.y + 0.0f*v.z, (0.0f + 0.0f*v.x) + 0.0f*v.y + 1.0f*v.z); }
+{ return make_f3(dot3_rn(c, -s, 0.0f, v), dot3_rn(s, c, 0.0f, v), dot3_rn(0.0f, 0.0f, 1.0f, v)); }
 BBMCU_D f3 rot_y(float c, float s, f3 v)   // rotationY(cossin) * v: rows (c,0,s), (0,1,0), (-s,0,c)  (transform.h:47-54)
-{ return make_f3((0.0f + c*v.x) + 0.0f*v.y + s*v.z, (0.0f + 0.0f*v.x) + 1.0f*v.y + 0.0f*v.z, (0.0f + (-s)*v.x) + 0.0f*v.y + c*v.z); }
+{ return make_f3(dot3_rn(c, 0.0f, s, v), dot3_rn(0.0f, 1.0f, 0.0f, v), dot3_rn(-s, 0.0f, c, v)); }
 
 constexpr uint32_t kMerlBins = 90u*90u*180u;
 
@@ -129,24 +146,57 @@ struct SphericalGrid
 
 BBMCU_D f3 snap_eps(f3 v) { return make_f3(fabsf(v.x) < kEps ? 0.0f : v.x, fabsf(v.y) < kEps ? 0.0f : v.y, fabsf(v.z) < kEps ? 0.0f : v.z); }
 
+// spherical_linearizer(idx) is separable like the MERL one: (cos, sin) of each phi sample and (sin, cos) of each theta
+// sample, then two products and the epsilon snap per direction.  spherical_dirs() evaluates the four pieces per index;
+// spherical_dirs_tab() reads them from a table of 2 (n_in_phi + n_in_theta + n_out_phi + n_out_theta) floats built once
+// per loss object with the same functions - identical bits, no transcendental per sample.
+BBMCU_D void sph_lin_split(const SphericalGrid& g, uint64_t idx, uint32_t& ip, uint32_t& it, uint32_t& op, uint32_t& ot)
+{
+  uint64_t t = idx;
+  ot = (uint32_t)(t % g.n_out_theta); t /= g.n_out_theta;
+  op = (uint32_t)(t % g.n_out_phi);   t /= g.n_out_phi;
+  it = (uint32_t)(t % g.n_in_theta);  t /= g.n_in_theta;
+  ip = (uint32_t)t;
+}
+// entry j of the table: [in phi | in theta | out phi | out theta], two floats each: (cos, sin) for phi, (sin, cos) for theta
+BBMCU_D void sph_lin_entry(const SphericalGrid& g, uint32_t j, float& a, float& b)
+{
+  // theta includes both end points (/(n-1), at least 1); phi does not (/n)
+  if(j < g.n_in_phi) { float ph = (float)j * g.size_in_phi / (float)g.n_in_phi + g.start_in_phi; a = glibc_cosf(ph); b = glibc_sinf(ph); return; }
+  j -= g.n_in_phi;
+  if(j < g.n_in_theta) { float th = (float)j * g.size_in_theta / (float)(g.n_in_theta > 1 ? g.n_in_theta - 1 : 1) + g.start_in_theta; a = glibc_sinf(th); b = glibc_cosf(th); return; }
+  j -= g.n_in_theta;
+  if(j < g.n_out_phi) { float ph = (float)j * g.size_out_phi / (float)g.n_out_phi + g.start_out_phi; a = glibc_cosf(ph); b = glibc_sinf(ph); return; }
+  j -= g.n_out_phi;
+  { float th = (float)j * g.size_out_theta / (float)(g.n_out_theta > 1 ? g.n_out_theta - 1 : 1) + g.start_out_theta; a = glibc_sinf(th); b = glibc_cosf(th); }
+}
+BBMCU_HD uint64_t sph_lin_entries(const SphericalGrid& g) { return (uint64_t)g.n_in_phi + g.n_in_theta + g.n_out_phi + g.n_out_theta; }
+BBMCU_D f3 sph_lin_assemble(float cp, float sp, float st, float ct) { return snap_eps(make_f3(mul_rn(cp, st), mul_rn(sp, st), ct)); }
+
 BBMCU_D void spherical_dirs(const SphericalGrid& g, uint64_t idx, f3& in, f3& out)
 {
   if(!(idx < g.size())) { in = make_f3(0, 0, 0); out = make_f3(0, 0, 0); return; }
-  uint64_t t = idx;
-  uint32_t ot = (uint32_t)(t % g.n_out_theta); t /= g.n_out_theta;
-  uint32_t op = (uint32_t)(t % g.n_out_phi);   t /= g.n_out_phi;
-  uint32_t it = (uint32_t)(t % g.n_in_theta);  t /= g.n_in_theta;
-  uint32_t ip = (uint32_t)t;
-  // theta includes both end points (/(n-1), at least 1); phi does not (/n)
-  float s_it = (float)(g.n_in_theta > 1 ? g.n_in_theta - 1 : 1), s_ot = (float)(g.n_out_theta > 1 ? g.n_out_theta - 1 : 1);
-  float in_phi = (float)ip * g.size_in_phi / (float)g.n_in_phi + g.start_in_phi;
-  float in_theta = (float)it * g.size_in_theta / s_it + g.start_in_theta;
-  float out_phi = (float)op * g.size_out_phi / (float)g.n_out_phi + g.start_out_phi;
-  float out_theta = (float)ot * g.size_out_theta / s_ot + g.start_out_theta;
-  float st = glibc_sinf(in_theta);
-  in = snap_eps(make_f3(glibc_cosf(in_phi)*st, glibc_sinf(in_phi)*st, glibc_cosf(in_theta)));
-  st = glibc_sinf(out_theta);
-  out = snap_eps(make_f3(glibc_cosf(out_phi)*st, glibc_sinf(out_phi)*st, glibc_cosf(out_theta)));
+  uint32_t ip, it, op, ot;
+  sph_lin_split(g, idx, ip, it, op, ot);
+  float cp, sp, st, ct;
+  sph_lin_entry(g, ip, cp, sp); sph_lin_entry(g, g.n_in_phi + it, st, ct);
+  in = sph_lin_assemble(cp, sp, st, ct);
+  sph_lin_entry(g, g.n_in_phi + g.n_in_theta + op, cp, sp); sph_lin_entry(g, g.n_in_phi + g.n_in_theta + g.n_out_phi + ot, st, ct);
+  out = sph_lin_assemble(cp, sp, st, ct);
+}
+BBMCU_D void spherical_dirs_tab(const SphericalGrid& g, const float* tab, uint64_t idx, f3& in, f3& out)
+{
+  if(!(idx < g.size())) { in = make_f3(0, 0, 0); out = make_f3(0, 0, 0); return; }
+  uint32_t ip, it, op, ot;
+  sph_lin_split(g, idx, ip, it, op, ot);
+  const float* t1 = tab + 2*(size_t)g.n_in_phi; const float* t2 = t1 + 2*(size_t)g.n_in_theta; const float* t3 = t2 + 2*(size_t)g.n_out_phi;
+#ifdef __CUDA_ARCH__
+  in = sph_lin_assemble(__ldg(tab + 2*ip), __ldg(tab + 2*ip + 1), __ldg(t1 + 2*it), __ldg(t1 + 2*it + 1));
+  out = sph_lin_assemble(__ldg(t2 + 2*op), __ldg(t2 + 2*op + 1), __ldg(t3 + 2*ot), __ldg(t3 + 2*ot + 1));
+#else
+  in = sph_lin_assemble(tab[2*ip], tab[2*ip + 1], t1[2*it], t1[2*it + 1]);
+  out = sph_lin_assemble(t2[2*op], t2[2*op + 1], t3[2*ot], t3[2*ot + 1]);
+#endif
 }
 
 } // namespace bbmcu

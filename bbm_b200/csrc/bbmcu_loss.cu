@@ -43,7 +43,8 @@ struct bbmcu_loss
   size_t count = 0;
   int n_materials = 1;       // reference operands sharing this linearizer (bbmcu_loss_create_ex: a batch of measured tables)
   bool fused = true;         // directions generated inside the kernels (no d_in / d_out planes kept)
-  const float* d_lin_tab = nullptr;   // the device's separable merl_linearizer table (owned by the library, per device)
+  const float* d_lin_tab = nullptr;   // the device's separable merl_linearizer table (owned by the library, per device), or d_sph_tab
+  float* d_sph_tab = nullptr;         // this loss's spherical_linearizer table (sph_lin_entries x 2 floats)
   float* d_in = nullptr;     // 3 planes of count (materialised mode only)
   float* d_out = nullptr;
   float* d_ref = nullptr;    // n_materials x 3 planes of count
@@ -69,7 +70,7 @@ struct bbmcu_loss
     for(int r=0; r < kMaxPeers; ++r) if(peer_ipc[r] && peer_win[r]) cudaIpcCloseMemHandle(peer_win[r]);
     if(peer_win[peer_rank]) cudaFree(peer_win[peer_rank]);
     if(h_peer_status) cudaFreeHost(h_peer_status);
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ref); cudaFree(d_sph_tab); cudaFree(d_attrs); cudaFree(d_partial); cudaFree(d_result); cudaFree(d_bad);
     for(int i=0; i < 2; ++i) { if(h_attrs[i]) cudaFreeHost(h_attrs[i]); if(h_attrs_free[i]) cudaEventDestroy(h_attrs_free[i]); }
     if(h_result) cudaFreeHost(h_result);
   }
@@ -204,6 +205,13 @@ __global__ void __launch_bounds__(kFinishThreads) k_loss_gather(unsigned int nva
   result[i] = sum;
 }
 
+// the phi / theta sample table of a spherical_linearizer (bbmcu_linearizer.cuh); this translation unit is built -fmad=false
+__global__ void k_sph_lin_tab(const SphericalGrid g, float* tab)
+{
+  const uint64_t n = sph_lin_entries(g);
+  for(uint64_t j = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x*blockDim.x) sph_lin_entry(g, (uint32_t)j, tab[2*j], tab[2*j + 1]);
+}
+
 // per-sample terms l(idx) (sampledlossfunction::operator()(idx))
 __global__ void __launch_bounds__(256) k_loss_terms(const LossArgs a, const BsdfDesc b, float* terms)
 {
@@ -266,6 +274,18 @@ int bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid*
     L->first = first; L->count = (size_t)count;
     const size_t n = L->count;
     if(L->merl_grid) L->d_lin_tab = merl_lin_table_device(ctx->device);
+    else if(L->fused)
+    {
+      const uint64_t entries = sph_lin_entries(L->grid);
+      if(entries > (uint64_t(1) << 22)) L->fused = false;              // a 32 MB table would not stay on chip: keep the planes instead
+      else
+      {
+        BBMCU_CUDA(cudaMalloc(&L->d_sph_tab, 2*entries*sizeof(float)));
+        k_sph_lin_tab<<<(unsigned)std::min<uint64_t>(1024, (entries + 255) / 256), 256, 0, ctx->stream>>>(L->grid, L->d_sph_tab);
+        BBMCU_CUDA(cudaGetLastError());
+        L->d_lin_tab = L->d_sph_tab;
+      }
+    }
     if(n == 0) { *out = L.release(); return; }
     BBMCU_CUDA(cudaMalloc(&L->d_in, 3*n*sizeof(float)));
     BBMCU_CUDA(cudaMalloc(&L->d_out, 3*n*sizeof(float)));
@@ -340,8 +360,11 @@ int bbmcu_loss_eval(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params,
   return bbmcu_loss_eval_multi(L, bsdf, params, K, loss_out, grad_out, device_out);
 }
 
-// Kper parameter sets for EACH of the loss's M materials in one launch: params M x Kper x P (material-major), results M x Kper
 int bbmcu_loss_eval_multi(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params, size_t Kper, double* loss_out, double* grad_out, double* device_out)
+{ return bbmcu_loss_eval_multi_ex(L, bsdf, params, Kper, loss_out, grad_out, device_out, -1); }
+
+// Kper parameter sets for EACH of the loss's M materials in one launch: params M x Kper x P (material-major), results M x Kper
+int bbmcu_loss_eval_multi_ex(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* params, size_t Kper, double* loss_out, double* grad_out, double* device_out, int gradient)
 {
   bbmcu_ctx* ctx = L ? L->ctx : nullptr;
   return guarded(ctx, [&] {
@@ -355,7 +378,8 @@ int bbmcu_loss_eval_multi(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double* p
     if(P > kMaxParams) throw std::invalid_argument("BBM: more than " + std::to_string(kMaxParams) + " fit parameters");
     BsdfDesc shape = make_desc(bsdf->b, ctx->device);
     const int A = shape.n_floats;                 // device floats per parameter set (He lobes carry an unused table gap)
-    const bool want_grad = (grad_out != nullptr) || (device_out != nullptr);
+    const bool want_grad = gradient < 0 ? ((grad_out != nullptr) || (device_out != nullptr)) : (gradient != 0);
+    if(!want_grad && grad_out) throw std::invalid_argument("BBM: grad_out given but gradient == 0");
     const int cols = 1 + P;
     // attribute blocks for the K parameter sets: inside the kernel arguments when they fit (one compass step), else
     // through two pinned staging buffers - packing the next batch never waits for the kernels of the previous one, only

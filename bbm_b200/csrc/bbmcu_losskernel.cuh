@@ -21,7 +21,8 @@ struct LossArgs
 {
   // where a sample's direction pair comes from: LIN_MATERIALISED reads the planes `in` / `out` (24 B per sample);
   // LIN_MERL_TABLES forms merl_linearizer(first + i) from the 900-float separable table `lin_tab` staged in shared
-  // memory; LIN_SPHERICAL evaluates spherical_linearizer(first + i) in registers.  The fused modes return the very bits
+  // memory; LIN_SPHERICAL forms spherical_linearizer(first + i) from the per-loss table `lin_tab` of its phi / theta
+  // samples (global memory, L1-resident).  The fused modes return the very bits
   // the materialised planes hold (same functions), so a pass reads only the 12 B per sample of measured data.
   int lin_mode;
   const float* lin_tab;
@@ -54,7 +55,7 @@ BBMCU_D float loss_attr(const LossArgs& a, size_t idx) { return a.inline_count ?
 BBMCU_D void loss_dirs(const LossArgs& a, const float* s_lin, size_t i, f3& in, f3& out)
 {
   if(a.lin_mode == LIN_MERL_TABLES) merl_dirs_tab(s_lin, (uint32_t)(a.first + i), in, out);
-  else if(a.lin_mode == LIN_SPHERICAL) spherical_dirs(a.grid, a.first + i, in, out);
+  else if(a.lin_mode == LIN_SPHERICAL) spherical_dirs_tab(a.grid, a.lin_tab, a.first + i, in, out);
   else
   {
 #ifdef __CUDA_ARCH__

@@ -607,20 +607,30 @@ def main():
         Lmulti = ctx.loss("nganL2", [tables[m] for m in mine], None)
         fitted = bb.Bsdf(FITTED)
         P = len(fitted.parameter_values())
-        M = len(mine)
-        # (a) M materials x 1 parameter set, value only: every launch streams M x 17.5 MB of measured data once
-        p1 = np.tile(fitted.parameter_values(), (M, 1, 1))
-        res16 = torch.zeros((M, 16, 1 + P), device=dev, dtype=torch.float64)
+        # (a) a true DRAM workload: MD = 64 materials (1.12 GB of tabulated data >> the 126 MB L2) x K parameter sets in one
+        # launch; K = 1 value-only streams every material once per pass
+        MD = 64
+        big = synthetic_materials(MD, seed=77)
+        tabs = [ctx.eval_merl_grid(bb.Bsdf(v), like=out) for _, v in sorted(big.items())]
+        ctx.synchronize()
+        Lbig = ctx.loss("nganL2", tabs, None)
+        del tabs
+        p1 = np.tile(fitted.parameter_values(), (MD, 1, 1))
         p16 = np.tile(p1, (1, 16, 1))
-        Lv = Lmulti
-        ms_v = timed(lambda: Lv.eval_multi(fitted, p1), max(5, args.steps // 2))        # value only (host result: includes the D2H of M doubles)
-        ms_g = timed(lambda: Lv.eval_multi_device(fitted, p16, res16), max(5, args.steps // 2))
-        bytes_v = 12 * bb.MERL_BINS * M
-        multi_info = {"materials_per_gpu": M, "value_only_K1": {"passes_per_s": world * M / (ms_v * 1e-3), "ms_per_launch": ms_v, "algorithmic_bytes_per_launch": bytes_v,
-                                                                 "achieved_gbs_per_gpu": bytes_v / (ms_v * 1e-3) / 1e9, "frac_of_hbm_roofline": bytes_v / (ms_v * 1e-3) / 1e9 / peak},
-                      "loss_grad_K16": {"passes_per_s": world * M * 16 / (ms_g * 1e-3), "ms_per_launch": ms_g},
-                      "note": "one launch = M materials x K parameter sets (grid z = material); %d x 17.5 MB of tabulated data per GPU%s" % (M, " exceed the 126 MB L2" if M * 17.5 > 126 else " (fits the 126 MB L2: not a DRAM roofline at this M)")}
-        del res16
+        res1 = torch.zeros((MD, 1, 1 + P), device=dev, dtype=torch.float64)
+        res16 = torch.zeros((MD, 16, 1 + P), device=dev, dtype=torch.float64)
+        ms_v = timed(lambda: Lbig.eval_multi_device(fitted, p1, res1, grad=False), max(5, args.steps // 2))
+        ms_g1 = timed(lambda: Lbig.eval_multi_device(fitted, p1, res1), max(5, args.steps // 2))
+        ms_g = timed(lambda: Lbig.eval_multi_device(fitted, p16, res16), max(3, args.steps // 4))
+        bytes_v = 12 * bb.MERL_BINS * MD
+        gbs = lambda ms_: bytes_v / (ms_ * 1e-3) / 1e9
+        multi_info = {"materials_per_launch": MD, "bytes_of_tabulated_data_per_gpu": bytes_v,
+                      "value_only_K1": {"passes_per_s": world * MD / (ms_v * 1e-3), "ms_per_launch": ms_v, "achieved_gbs_per_gpu": gbs(ms_v), "frac_of_hbm_roofline": gbs(ms_v) / peak},
+                      "loss_grad_K1": {"passes_per_s": world * MD / (ms_g1 * 1e-3), "ms_per_launch": ms_g1, "achieved_gbs_per_gpu": gbs(ms_g1), "frac_of_hbm_roofline": gbs(ms_g1) / peak},
+                      "loss_grad_K16": {"passes_per_s": world * MD * 16 / (ms_g * 1e-3), "ms_per_launch": ms_g},
+                      "note": "one launch = 64 materials x K parameter sets (grid z = material), 12 B x 1 458 000 per material read once per launch: "
+                              "1.12 GB per GPU, far beyond the 126 MB L2 - the true-DRAM case of SURVEY 8(d); each rank holds its own 64 materials (weak scaling)"}
+        del Lbig, res1, res16
         # (b) the fit sweep, split by material over the ranks; no collective
         models = [m for m in bb.model_names() if m != "Merl"] if args.sweep else SWEEP_MODELS_MINI
         metrics = bb.METRICS if args.sweep else ["nganL2", "standardLog"]

@@ -195,6 +195,10 @@ BBMCU_API int  bbmcu_loss_eval(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const d
  * loss M x K, grad M x K x P, device_out M x K x (1+P). */
 BBMCU_API int  bbmcu_loss_eval_multi(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
                            double* loss_out, double* grad_out, double* device_out);
+/* gradient: 1 = compute it, 0 = value-only kernel (device_out rows then carry zeros in the gradient columns), -1 = decide from
+ * the output pointers as bbmcu_loss_eval does (gradient iff grad_out or device_out is given) */
+BBMCU_API int  bbmcu_loss_eval_multi_ex(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, const double* params, size_t K,
+                              double* loss_out, double* grad_out, double* device_out, int gradient);
 /* per-sample terms l(idx) of the shard (sampledlossfunction::operator()(idx)); `terms` = bbmcu_loss_shard_count floats
  * (host or device); _at: against material `material` of a batched loss */
 BBMCU_API int  bbmcu_loss_terms(bbmcu_loss* loss, const bbmcu_bsdf* bsdf, float* terms);

@@ -1,10 +1,13 @@
 // bbmcu/loss.hpp - the reference's loss functions on the CUDA backbone.
 //
-// cuda_loss satisfies concepts::lossfunction (include/concepts/lossfunction.h:28-35): update() and
-// Value operator()(Mask = true) const, so that an optimizer written against the reference's interface
-// (include/optimizer/compass.h:82-140) drives it unchanged: the optimizer writes the live parameter vector, calls
-// update() and then operator().  It also satisfies sampledlossfunction (include/bbm/sampledlossfunction.h:26-36:
-// samples()).  New on this backbone: evaluation of K parameter vectors in ONE launch and the analytic gradient.
+// cuda_loss has the METHODS of concepts::lossfunction (include/concepts/lossfunction.h:28-35: update() and
+// Value operator()(Mask = true) const) and samples(), but it is a stand-alone class over the C ABI that knows nothing of
+// bbm's Config types, so it does not itself satisfy the concept (which requires a Config typedef,
+// include/concepts/config.h:53).  The class that does - and that the UNMODIFIED bbm::compass (include/optimizer/compass.h:39-185)
+// drives - is bbm::cuda::loss in backbone/cuda/include/bbm_cuda/loss.h, a thin shell over this one compiled against the
+// reference's headers (tests/cpp/test_reference_boundary.cpp checks the concepts with static_assert).  The optimizers of
+// optimizer.hpp run against this class directly.  New on this backbone: evaluation of K parameter vectors in ONE launch
+// and the analytic gradient.
 //
 // The six metrics are the error functors of include/loss/cosine_weighted_l2.h:25-34,96-105,166-176 and
 // include/loss/cosine_weighted_log.h:32-43,101-112,170-181 (nganL2, lowL2, bieronL2, lowLog, bieronLog, standardLog).
@@ -49,6 +52,7 @@ public:
     return (float)l;
   }
   size_t samples() const { return (size_t)bbmcu_loss_samples(_loss.get()); }
+  bbmcu_loss* handle() const { return _loss.get(); }
 
   // ---- batched / gradient (new) -------------------------------------------------------------------------------------
   size_t parameters() const { return _params->size(); }
