@@ -21,6 +21,7 @@ ATTR_DIFFUSE_SCALE, ATTR_DIFFUSE_PARAMETER, ATTR_SPECULAR_SCALE, ATTR_SPECULAR_P
 METRICS = ["nganL2", "lowL2", "bieronL2", "lowLog", "bieronLog", "standardLog"]
 PARAM_VALUE, PARAM_DEFAULT, PARAM_LOWER, PARAM_UPPER = 0, 1, 2, 3
 MERL_BINS = 1458000
+CONFIGS = ["floatRGB", "doubleRGB"]
 
 
 class BbmError(RuntimeError):
@@ -169,12 +170,14 @@ class Bsdf:
     """bbm::bsdf_ptr (include/bbm/bsdf_ptr.h:20-165): import from / export to the BSDF string grammar and
     the parameter enumeration of include/bbm/bsdf_enumerate.h:102-237 (forward order)."""
 
-    def __init__(self, string, _handle=None):
+    def __init__(self, string, _handle=None, config="floatRGB"):
+        """config: which of the reference's native configurations the host side mirrors - "floatRGB" parses with std::stof and
+        prints floats, "doubleRGB" keeps doubles (needed e.g. for fits/bagher_sgd.fit); the kernels compute in FP32 either way"""
         self._h = C.c_void_p()
         if _handle is not None:
             self._h = _handle
         else:
-            _check(lib().bbmcu_bsdf_from_string(None, string.encode(), C.byref(self._h)))
+            _check(lib().bbmcu_bsdf_from_string_ex(None, string.encode(), C.c_int(CONFIGS.index(config)), C.byref(self._h)))
 
     def __del__(self):
         if getattr(self, "_h", None) and _lib is not None:
@@ -506,11 +509,11 @@ class Loss:
         return t
 
 
-def import_fit(filename):
-    """io::importFIT (include/io/fit.h:34-52): {key: Bsdf}, keys sorted like the reference's std::map"""
+def import_fit(filename, config="floatRGB"):
+    """io::importFIT (include/io/fit.h:34-52): {key: Bsdf}, keys sorted like the reference's std::map.  config as in Bsdf()"""
     L = lib()
     h = C.c_void_p()
-    _check(L.bbmcu_fit_import(None, filename.encode(), C.byref(h)))
+    _check(L.bbmcu_fit_import_ex(None, filename.encode(), C.c_int(CONFIGS.index(config)), C.byref(h)))
     try:
         out = {}
         for i in range(L.bbmcu_fit_count(h)):

@@ -349,12 +349,14 @@ int bbmcu_model_layout(int id, bbmcu_attr* attrs, int* n_attrs)
 }
 
 // ---- BSDF objects -------------------------------------------------------------------------------------
-int bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out)
+int bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out) { return bbmcu_bsdf_from_string_ex(ctx, str, BBMCU_FLOAT_RGB, out); }
+int bbmcu_bsdf_from_string_ex(bbmcu_ctx* ctx, const char* str, int config, bbmcu_bsdf** out)
 {
   return guarded(ctx, [&] {
     if(!str || !out) throw std::invalid_argument("BBM: null argument");
+    if(config != BBMCU_FLOAT_RGB && config != BBMCU_DOUBLE_RGB) throw std::invalid_argument("BBM: unknown configuration");
     std::unique_ptr<bbmcu_bsdf> b(new bbmcu_bsdf);
-    b->b = bbmcu_host::parse_bsdf(str);
+    b->b = bbmcu_host::parse_bsdf(str, config == BBMCU_DOUBLE_RGB);
     make_desc(b->b, -1);                                // validates lobe/attribute limits early (no device touched)
     *out = b.release();
   });
@@ -579,12 +581,14 @@ int bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const float* rgb)
 }
 
 // ---- .fit files ------------------------------------------------------------------------------------------------
-int bbmcu_fit_import(bbmcu_ctx* ctx, const char* filename, bbmcu_fit** out)
+int bbmcu_fit_import(bbmcu_ctx* ctx, const char* filename, bbmcu_fit** out) { return bbmcu_fit_import_ex(ctx, filename, BBMCU_FLOAT_RGB, out); }
+int bbmcu_fit_import_ex(bbmcu_ctx* ctx, const char* filename, int config, bbmcu_fit** out)
 {
   return guarded(ctx, [&] {
     if(!filename || !out) throw std::invalid_argument("BBM: null argument");
+    if(config != BBMCU_FLOAT_RGB && config != BBMCU_DOUBLE_RGB) throw std::invalid_argument("BBM: unknown configuration");
     std::unique_ptr<bbmcu_fit> f(new bbmcu_fit);
-    f->entries = bbmcu_host::import_fit(filename);
+    f->entries = bbmcu_host::import_fit(filename, config == BBMCU_DOUBLE_RGB);
     *out = f.release();
   });
 }

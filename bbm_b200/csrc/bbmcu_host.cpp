@@ -140,10 +140,17 @@ std::vector<std::string> split_args(const std::string& str)
   return out;
 }
 
+// which of the reference's two native configurations the host side mirrors while parsing / printing (thread local; set by
+// parse_bsdf / import_fit for the duration of a call): floatRGB rounds every value to float, doubleRGB keeps doubles
+static thread_local bool g_double_config = false;
+struct ConfigScope { bool saved; explicit ConfigScope(bool dbl) : saved(g_double_config) { g_double_config = dbl; } ~ConfigScope() { g_double_config = saved; } };
+
 double parse_scalar(const std::string& s)
 {
-  // floatRGB semantics: std::stof (throws std::out_of_range on overflow, e.g. fits/bagher_sgd.fit; SURVEY.md fact 10)
   size_t pos = 0;
+  // doubleRGB: std::stod (core/stringconvert.h:144 is generic over Value); e.g. fits/bagher_sgd.fit needs it (c = 1.3e49)
+  if(g_double_config) return std::stod(s, &pos);
+  // floatRGB semantics: std::stof (throws std::out_of_range on overflow, e.g. fits/bagher_sgd.fit; SURVEY.md fact 10)
   float v = std::stof(s, &pos);
   return (double)v;
 }
@@ -259,12 +266,16 @@ const ModelInfo* find_model(const std::string& name)
 
 std::string format_float(double v)
 {
-  std::stringstream ss; ss << (float)v; return ss.str();
+  std::stringstream ss;
+  if(g_double_config) ss << v; else ss << (float)v;
+  return ss.str();
 }
 
-Bsdf parse_bsdf(const std::string& str)
+Bsdf parse_bsdf(const std::string& str, bool double_config)
 {
+  ConfigScope scope(double_config);
   Bsdf b;
+  b.double_config = double_config;
   auto kw = get_keyword(trim(str));
   if(kw.first == "Aggregate")
   {
@@ -278,6 +289,7 @@ Bsdf parse_bsdf(const std::string& str)
 
 std::string Bsdf::to_string() const
 {
+  ConfigScope scope(double_config);
   auto one = [](const Lobe& l) {
     if(l.merl) return l.model->name + "(\"" + l.merl->filename + "\")";          // merl_data::toString (merl.h:161-164)
     std::string s = l.model->name + "(";
@@ -370,7 +382,7 @@ void write_merl(const std::string& filename, const float* rgb)
   ofs.write(reinterpret_cast<const char*>(buf.data()), 3*N*sizeof(double));
 }
 
-std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename)
+std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename, bool double_config)
 {
   std::ifstream ifs(filename.c_str());
   if(!ifs) throw std::runtime_error("BBM: unable to open FIT file: " + filename);
@@ -383,7 +395,7 @@ std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename
     if(pos != std::string::npos) line = line.substr(0, pos);
     auto kv = split_eq(line);
     if(kv.first.empty()) continue;
-    try { m.emplace(kv.first, parse_bsdf(kv.second)); }
+    try { m.emplace(kv.first, parse_bsdf(kv.second, double_config)); }
     catch(const std::exception& e) { throw std::invalid_argument(std::string(e.what()) + " (key " + kv.first + ")"); }
   }
   return std::vector<std::pair<std::string, Bsdf>>(m.begin(), m.end());

@@ -64,6 +64,7 @@ struct Lobe
 struct Bsdf
 {
   bool aggregate = false;
+  bool double_config = false;        // parsed / printed as the reference's doubleRGB does (values not rounded to float on the host)
   std::vector<Lobe> lobes;
 
   std::string to_string() const;
@@ -76,10 +77,10 @@ struct Bsdf
 };
 
 // throws std::invalid_argument / std::runtime_error with the reference's wording where it has one
-Bsdf parse_bsdf(const std::string& str);
+Bsdf parse_bsdf(const std::string& str, bool double_config = false);
 std::string format_float(double v);                            // default ostream << float (6 significant digits)
 
-std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename);   // file order preserved
+std::vector<std::pair<std::string, Bsdf>> import_fit(const std::string& filename, bool double_config = false);   // file order preserved
 void export_fit(const std::string& filename, const std::vector<std::pair<std::string, Bsdf>>& data, const std::string& comment);
 
 } // namespace bbmcu_host

@@ -102,9 +102,17 @@ BBMCU_D void merl_lin_dtheta(uint32_t iDt, float& s, float& c) { float thd = ((f
 BBMCU_D void merl_lin_dphi(uint32_t iDp, float& c, float& s) { float phd = ((float)iDp / 180.0f) * (0.5f*kTwoPi); c = glibc_cosf(phd); s = glibc_sinf(phd); }
 BBMCU_D void merl_dirs_assemble(const MerlLinHalf& h, float std_, float ctd, float cpd, float spd, f3& in, f3& out)
 {
-  f3 diff = make_f3(cpd*std_, spd*std_, ctd);
-  in = rot_z(h.cz, h.sz, rot_y(h.cy, h.sy, diff));
-  out = rot_z(h.cz, h.sz, rot_y(h.cy, h.sy, make_f3(-diff.x, -diff.y, diff.z)));
+  f3 diff = make_f3(mul_rn(cpd, std_), mul_rn(spd, std_), ctd);
+  in = rot_y(h.cy, h.sy, diff);
+  out = rot_y(h.cy, h.sy, make_f3(-diff.x, -diff.y, diff.z));
+  if(h.cz == 1.0f && h.sz == 0.0f)
+  {
+    // phi(half) is exactly 0 for every bin of this grid (half = (sin, 0, cos)), so rotationZ is the identity matrix; its
+    // row sums ((0 + 1 x) + (-0) y) + 0 z leave every finite x unchanged except that -0 becomes +0: x + 0 does the same
+    in = make_f3(add_rn(in.x, 0.0f), add_rn(in.y, 0.0f), add_rn(in.z, 0.0f));
+    out = make_f3(add_rn(out.x, 0.0f), add_rn(out.y, 0.0f), add_rn(out.z, 0.0f));
+  }
+  else { in = rot_z(h.cz, h.sz, in); out = rot_z(h.cz, h.sz, out); }
   in.z = fmaxf(in.z, 0.0f);
   out.z = fmaxf(out.z, 0.0f);
 }

@@ -427,7 +427,7 @@ int bbmcu_loss_eval_multi_ex(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double
     const size_t n = L->count;
     const bool static_shape = (shape.n_lobes == 1 && !shape.aggregate) || (shape.n_lobes == 2 && shape.aggregate && shape.model[0] == M_Lambertian);
     unsigned max_bx = (unsigned)std::max<size_t>(1, (n + kLossThreads - 1) / kLossThreads);
-    unsigned bx = (unsigned)std::max<size_t>(1, ((size_t)ctx->sm_count*8 + K - 1) / K);
+    unsigned bx = (unsigned)std::max<size_t>(1, ((size_t)ctx->sm_count*8 + Kper - 1) / Kper);     // from the per-material count: a material's sums do not depend on how many others share the launch
     if(bx > max_bx) bx = max_bx;
     if(static_shape) bx = (unsigned)std::max<size_t>(1, (n + kTileSamples - 1) / kTileSamples);     // one partial row per sample tile
     grow(L->d_partial, L->partial_cap, K*(size_t)bx*cols);

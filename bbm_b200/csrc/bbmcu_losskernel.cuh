@@ -139,74 +139,79 @@ template<int C> __device__ __forceinline__ void warp_reduce_multi(const float (&
 // (launch bounds: block size only, which lets the compiler settle at 128 registers = 2 resident blocks: 2.65 ms for K = 256;
 // measured alternatives: (256, 1) -> 255 registers allowed, 3.81 ms; (256, 2) 2.71 ms; (256, 3) -> 80 registers, spills, 2.80 ms)
 template<class LossT, bool WG>
-__global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, int K, int k_per_block)
+__global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, int K, int k_per_block, int n_tiles)
 {
   constexpr int P = LossT::P;
   constexpr int C = WG ? 1 + P : 1;
   extern __shared__ float s_attr_tile[];                       // (k1 - k0) x n_attrs
   __shared__ float s_red[kTileKChunk][kLossThreads/32][C];
   __shared__ float s_lin[kMerlLinTabFloats];
-  const int tile = blockIdx.x, mat = blockIdx.z;
+  const int mat = blockIdx.z;
   const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
   const size_t kbase = (size_t)mat * K;                        // first parameter set of this material
   for(int i = threadIdx.x; i < (k1 - k0)*a.n_attrs; i += blockDim.x)
     s_attr_tile[i] = loss_attr(a, (kbase + k0 + i / a.n_attrs)*a.attr_stride + (i % a.n_attrs));
   loss_stage_lin(a, s_lin);
-  if(a.lin_mode == LIN_MERL_TABLES) __syncthreads();
-  const float* refp = a.ref + (size_t)mat * a.ref_stride;
-  f3 in[kTileSPT], out[kTileSPT]; Spec<float> ref[kTileSPT]; bool valid[kTileSPT];
-#pragma unroll
-  for(int s=0; s < kTileSPT; ++s)
-  {
-    const size_t i = (size_t)tile*kTileSamples + (size_t)s*kLossThreads + threadIdx.x;
-    valid[s] = i < a.n;
-    const size_t ii = valid[s] ? i : 0;
-    loss_dirs(a, s_lin, ii, in[s], out[s]);
-    ref[s] = Spec<float>(__ldg(refp + ii), __ldg(refp + a.n + ii), __ldg(refp + 2*a.n + ii));
-  }
-  typename LossT::Geom geo[kTileSPT];                          // direction-only work, once per sample
-#pragma unroll
-  for(int s=0; s < kTileSPT; ++s) geo[s] = LossT::geom(a.metric, in[s], out[s]);
   __syncthreads();
+  const float* refp = a.ref + (size_t)mat * a.ref_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for(int kc = k0; kc < k1; kc += kTileKChunk)
+  // a block walks over tiles blockIdx.x, blockIdx.x + gridDim.x, ...: with few parameter sets per block (small K, or many
+  // materials) the launch uses fewer, longer-lived blocks so that the staging above is paid once per block, not per tile;
+  // partial rows stay per (parameter set, tile), so the result does not depend on the launch shape
+  for(int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
-    const int nkk = min(kTileKChunk, k1 - kc);
-    for(int kk=0; kk < nkk; ++kk)
+    f3 in[kTileSPT], out[kTileSPT]; Spec<float> ref[kTileSPT]; bool valid[kTileSPT];
+#pragma unroll
+    for(int s=0; s < kTileSPT; ++s)
     {
-      const float* at = s_attr_tile + (size_t)(kc + kk - k0)*a.n_attrs;
-      float acc[C];
+      const size_t i = (size_t)tile*kTileSamples + (size_t)s*kLossThreads + threadIdx.x;
+      valid[s] = i < a.n;
+      const size_t ii = valid[s] ? i : 0;
+      loss_dirs(a, s_lin, ii, in[s], out[s]);
+      ref[s] = Spec<float>(__ldg(refp + ii), __ldg(refp + a.n + ii), __ldg(refp + 2*a.n + ii));
+    }
+    typename LossT::Geom geo[kTileSPT];                          // direction-only work, once per sample
 #pragma unroll
-      for(int j=0; j < C; ++j) acc[j] = 0.0f;
-#pragma unroll
-      for(int s=0; s < kTileSPT; ++s)
+    for(int s=0; s < kTileSPT; ++s) geo[s] = LossT::geom(a.metric, in[s], out[s]);
+    for(int kc = k0; kc < k1; kc += kTileKChunk)
+    {
+      const int nkk = min(kTileKChunk, k1 - kc);
+      for(int kk=0; kk < nkk; ++kk)
       {
-        if(!valid[s]) continue;
-        float g[P];
-        const float e = LossT::sample(at, a.metric, a.component, geo[s], in[s], out[s], ref[s], g, WG);
-        acc[0] += e;
-        if(WG) {
+        const float* at = s_attr_tile + (size_t)(kc + kk - k0)*a.n_attrs;
+        float acc[C];
 #pragma unroll
-          for(int j=0; j < P; ++j) acc[1 + j] += g[j];
+        for(int j=0; j < C; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for(int s=0; s < kTileSPT; ++s)
+        {
+          if(!valid[s]) continue;
+          float g[P];
+          const float e = LossT::sample(at, a.metric, a.component, geo[s], in[s], out[s], ref[s], g, WG);
+          acc[0] += e;
+          if(WG) {
+#pragma unroll
+            for(int j=0; j < P; ++j) acc[1 + j] += g[j];
+          }
         }
+        int ridx; float rval; bool rwriter;
+        warp_reduce_multi<C>(acc, lane, ridx, rval, rwriter);
+        if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
       }
-      int ridx; float rval; bool rwriter;
-      warp_reduce_multi<C>(acc, lane, ridx, rval, rwriter);
-      if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
-    }
-    __syncthreads();
-    // one value per (parameter set of the chunk, column); a loop, so any P up to kMaxParams is covered
-    for(int t = threadIdx.x; t < nkk*(1 + a.P); t += blockDim.x)
-    {
-      const int kk = t / (1 + a.P), j = t % (1 + a.P);
-      double v = 0.0;
-      if(j < C) {
+      __syncthreads();
+      // one value per (parameter set of the chunk, column); a loop, so any P up to kMaxParams is covered
+      for(int t = threadIdx.x; t < nkk*(1 + a.P); t += blockDim.x)
+      {
+        const int kk = t / (1 + a.P), j = t % (1 + a.P);
+        double v = 0.0;
+        if(j < C) {
 #pragma unroll
-        for(int w=0; w < kLossThreads/32; ++w) v += (double)s_red[kk][w][j];
+          for(int w=0; w < kLossThreads/32; ++w) v += (double)s_red[kk][w][j];
+        }
+        a.partial[((kbase + kc + kk)*(1 + a.P) + j)*n_tiles + tile] = v;          // [material, k][column][tile]: the finish kernel reads tiles coalesced
       }
-      a.partial[((kbase + kc + kk)*(1 + a.P) + j)*gridDim.x + tile] = v;          // [material, k][column][tile]: the finish kernel reads tiles coalesced
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -237,9 +242,17 @@ template<class LossT> static void launch_loss_static(cudaStream_t s, const LossA
   loss_tile_shape(a.n, (size_t)K*a.n_materials, K, a.n_attrs, a.sm_count, tiles, ksplit, kpb);
   const size_t smem = (size_t)kpb*a.n_attrs*sizeof(float);
   (void)blocks_x;
-  const dim3 grid(tiles, ksplit, (unsigned)a.n_materials);
-  if(a.want_grad) k_loss_tile<LossT, true><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb);
-  else            k_loss_tile<LossT, false><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb);
+  // blocks along the tile axis: all tiles when the launch is small, else about `fill` blocks per SM in total, each walking
+  // over several tiles (K = 1 passes and many-material launches: the table / attribute staging is then paid once per block)
+  static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 16; }();
+  // (with fewer than 8 parameter sets per block a tile is little work: two resident waves of long-lived blocks)
+  const size_t target = (size_t)a.sm_count * (kpb >= 8 ? fill : 4), other = (size_t)ksplit * a.n_materials;
+  unsigned gx = tiles;
+  if((size_t)tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
+  if(gx > tiles) gx = tiles;
+  const dim3 grid(gx, ksplit, (unsigned)a.n_materials);
+  if(a.want_grad) k_loss_tile<LossT, true><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
+  else            k_loss_tile<LossT, false><<<grid, kLossThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
 }
 
 // one translation unit per group of models (compile time); returns false if `model` is not in that group

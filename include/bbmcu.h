@@ -91,6 +91,12 @@ BBMCU_API int  bbmcu_model_layout(int model_id, bbmcu_attr* attrs, int* n_attrs)
 /* ---- BSDF objects: bsdf_import / toString / parameter enumeration ------------------------------------ */
 /* bbm::bsdf_import<floatRGB>(str) (include/bbm/bsdf_import.h:22-26): "Model(args)" or "Aggregate(m1, m2, ...)" */
 BBMCU_API int  bbmcu_bsdf_from_string(bbmcu_ctx* ctx, const char* str, bbmcu_bsdf** out);
+/* which of the reference's native configurations (backbone/native/include/backbone.h:41-42) the HOST side of the object
+ * mirrors: floatRGB parses with std::stof and prints floats (a value beyond FLT_MAX is an error, as in the reference:
+ * fits/bagher_sgd.fit); doubleRGB parses with std::stod and keeps doubles in the parameter vectors and strings.  Kernels
+ * compute in FP32 either way (attribute values are rounded when they travel to the device). */
+enum { BBMCU_FLOAT_RGB = 0, BBMCU_DOUBLE_RGB = 1 };
+BBMCU_API int  bbmcu_bsdf_from_string_ex(bbmcu_ctx* ctx, const char* str, int config, bbmcu_bsdf** out);
 BBMCU_API void bbmcu_bsdf_free(bbmcu_bsdf* bsdf);
 BBMCU_API int  bbmcu_bsdf_to_string(const bbmcu_bsdf* bsdf, char* buf, size_t cap);           /* bsdf_ptr::toString */
 BBMCU_API int  bbmcu_bsdf_param_count(const bbmcu_bsdf* bsdf, int attr_flags);
@@ -227,6 +233,7 @@ BBMCU_API int  bbmcu_loss_peer_connect_ptrs(bbmcu_loss* loss, void* const* windo
 /* ---- .fit files (include/io/fit.h:34-77) -------------------------------------------------------------- */
 typedef struct bbmcu_fit bbmcu_fit;
 BBMCU_API int  bbmcu_fit_import(bbmcu_ctx* ctx, const char* filename, bbmcu_fit** out);
+BBMCU_API int  bbmcu_fit_import_ex(bbmcu_ctx* ctx, const char* filename, int config, bbmcu_fit** out);   /* config: BBMCU_FLOAT_RGB / BBMCU_DOUBLE_RGB */
 BBMCU_API int  bbmcu_fit_count(const bbmcu_fit* fit);
 BBMCU_API const char* bbmcu_fit_key(const bbmcu_fit* fit, int i);
 BBMCU_API int  bbmcu_fit_bsdf(const bbmcu_fit* fit, int i, bbmcu_bsdf** out);     /* a copy the caller frees */

@@ -32,3 +32,44 @@ def test_all_shipped_fit_files_import_like_the_reference(ref):
             assert got[k].to_string() == want[k], (path, k)
         imported += 1
     assert imported == 13
+
+
+@pytest.mark.skipif(not FITS, reason="reference tree not mounted")
+def test_bagher_fit_imports_in_the_double_configuration(refd):
+    """fits/bagher_sgd.fit needs the reference's doubleRGB configuration (c = 1.3e49 overflows std::stof, SURVEY.md fact 10):
+    config="doubleRGB" parses with std::stod and prints doubles - keys and strings equal the doubleRGB reference's"""
+    import bbm_b200 as bb
+    path = [p for p in FITS if p.endswith("bagher_sgd.fit")][0]
+    want = refd.import_fit(path)
+    got = bb.import_fit(path, config="doubleRGB")
+    assert list(got) == list(want) and len(got) == 100
+    for k in want:
+        assert got[k].to_string() == want[k], k
+    assert "e+49" in got["alumina-oxide"].to_string() or any("e+4" in v.to_string() for v in got.values())
+    with pytest.raises(bb.BbmError):
+        bb.import_fit(path)                                    # floatRGB: fails, as in the reference
+
+
+@pytest.mark.skipif(not FITS, reason="reference tree not mounted")
+def test_reference_import_fits_script_runs_unchanged(ref):
+    """the reference's own fits/import_fits.py - which eval()s every line of a .fit file against a Python module's names -
+    runs UNCHANGED against bbm_b200.floatRGB (the reference's module surface: one factory per model, Aggregate, BsdfPtr)"""
+    import importlib.util
+    import bbm_b200.floatRGB as bbm
+    import bbm_b200.doubleRGB as bbmd
+    spec = importlib.util.spec_from_file_location("import_fits", "/root/reference/fits/import_fits.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    done = 0
+    for path in FITS:
+        if path.endswith("bagher_sgd.fit"):
+            fits = mod.import_fits(path, bbmd)
+            assert len(fits) == 100
+            continue
+        want = ref.import_fit(path)
+        fits = mod.import_fits(path, bbm)
+        assert sorted(fits) == sorted(want), path
+        for k, v in want.items():
+            assert str(fits[k]) == v, (path, k)
+        done += 1
+    assert done == 13
