@@ -242,6 +242,45 @@ BBMCU_API int  bbmcu_fit_add(bbmcu_fit* fit, const char* key, const bbmcu_bsdf* 
 BBMCU_API int  bbmcu_fit_export(bbmcu_ctx* ctx, const bbmcu_fit* fit, const char* filename, const char* comment);
 BBMCU_API void bbmcu_fit_free(bbmcu_fit* fit);
 
+/* ---- checkBsdf on the device (bin/checkBsdf.cpp:51-430) -----------------------------------------------------------------
+ * The reference's six consistency tests as fused generate -> evaluate -> reduce kernels: every sample of the reference's
+ * scalar loops is one item, the per-sample terms are summed on the device (float terms, double sums).  `rng` selects
+ * where the random numbers come from:
+ *   BBMCU_RNG_PHILOX   drawn in the kernel from a counter-based generator of `seed` (0 bytes in; any sample count);
+ *   BBMCU_RNG_MT19937  the reference's own stream - a default-seeded std::mt19937 read through
+ *                      std::uniform_real_distribution<float>(0,1) in the reference's call order (bin/checkBsdf.cpp:18-25;
+ *                      rndVec2d draws its second component first) - drawn on the host and uploaded, so the printed numbers
+ *                      can be compared with the reference's for the same command line (`seed` ignored).
+ * Sums are double where the reference accumulates in float, so agreement is to the float accumulation error of the
+ * reference (~1e-4 relative at 10^5 samples), not bit for bit.  All output pointers are HOST memory. */
+enum { BBMCU_RNG_PHILOX = 0, BBMCU_RNG_MT19937 = 1 };
+/* testReflectance (:51-97): for out = (theta_idx * pi/2 / n_theta, phi = 0): estimate[3 i ..] = mean of eval * cos / pdf over
+ * `samples` directions (uniform over the sphere, or bsdf.sample(out, xi) if importance), reflectance[3 i ..] = bsdf.reflectance(out),
+ * out_dirs[3 i ..] = out */
+BBMCU_API int  bbmcu_check_reflectance(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, uint64_t samples, int n_theta, int importance,
+                                       int rng, uint64_t seed, double* estimate, float* reflectance, float* out_dirs);
+/* testReciprocity (:102-152) and testAdjoint (:157-201): mean[3] and max_diff[3] of |eval(a, b) - eval(b, a)| over uniform
+ * direction pairs, max_pair[6] = (a, b) of the first pair with the largest channel sum (zeros if every difference is 0).
+ * Radiance, importance and adjoint give the same numbers: no model of the reference reads unit_t. */
+BBMCU_API int  bbmcu_check_reciprocity(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, uint64_t samples, int rng, uint64_t seed,
+                                       double* mean, float* max_diff, float* max_pair);
+/* testPdf (:206-267): counts[4] = negative pdfs (radiance, importance), sampled directions below the horizon (radiance,
+ * importance; 0 unless check_below_horizon); mismatch[2] = mean |sample.pdf - pdf(sample.direction, view)|.  The whole
+ * sample count is evaluated (the reference stops once a counter reaches maxError).  offenders (may be NULL): up to
+ * max_offenders records of 8 floats {kind (0/1 below horizon rad/imp, 2/3 negative pdf rad/imp), pdf, direction[3], view[3]};
+ * n_offenders receives how many were written. */
+BBMCU_API int  bbmcu_check_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, uint64_t samples, int sample_sphere, int check_below_horizon,
+                               int rng, uint64_t seed, uint64_t* counts, double* mismatch, float* offenders, int max_offenders, int* n_offenders);
+/* testPdfInt (:272-316): integral[t] = MC integral over the sphere of pdf(., dirs[3 t ..]) for `trials` random directions */
+BBMCU_API int  bbmcu_check_pdf_integral(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, uint64_t samples, int trials, int sample_sphere,
+                                        int rng, uint64_t seed, double* integral, float* dirs);
+/* testSample (:321-430): per trial, the pdf integrated over n_theta x n_phi bins (pdf_samples per bin), the histogram of
+ * `samples` sampled directions, chi2 / df as the reference forms them and P = gamma_q((df - 1)/2, chi2/2) (NaN when df <= 1).
+ * bin_pdf / bin_count (may be NULL): trials x n_theta x n_phi. */
+BBMCU_API int  bbmcu_check_sample(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, uint64_t pdf_samples, uint64_t samples, int n_theta, int n_phi,
+                                  int trials, int sample_sphere, int include_zero_pdf_samples, int rng, uint64_t seed,
+                                  double* chi2, double* df, double* P, float* dirs, double* bin_pdf, uint64_t* bin_count);
+
 #ifdef __cplusplus
 }
 #endif
