@@ -370,6 +370,13 @@ class Context:
         _check(lib().bbmcu_hp_precompute_g1(self._h, _ptr(t)), self._h)
         return t
 
+    def hp_precompute_normalization(self):
+        """the (100, 100, 100) renormalisation table sigma_rel^2 / sigma_s^2 over (b, c, sin theta_i), recomputed on the GPU
+        (precompute/HolzschuchPacanowski/normalization.cpp; the reference ships no copy of it)"""
+        t = np.empty((100, 100, 100), np.float32)
+        _check(lib().bbmcu_hp_precompute_normalization(self._h, _ptr(t)), self._h)
+        return t
+
     # ---- losses ------------------------------------------------------------------------------------
     def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False):
         return Loss(self, metric, reference, grid, component, unit, first, count, materialise)

@@ -66,23 +66,28 @@ BBMCU_D float epd_g1_lookup(double ip, double it, float* d_ip, float* d_it)
 }
 
 // ---- regularised incomplete gamma functions in float (util/gamma.h, MaxTerms = 100) -----------------
-BBMCU_D float epd_gamma_series_p(float a, float x)          // detail::gamma<100, true>
+// `norm` = lgammaf(a): a = 1/p is the same for every sample of a launch, so callers evaluate it once per inverse instead of
+// once per series / continued fraction (three to five times per sample).  The reciprocal inside the series loop takes the
+// unguarded IEEE fast path (ieee_rcp_raw: the same bits as 1.0f / x for operands that are normal and far from the
+// exponent limits, bbmcu_math.cuh); the guarded form in the continued fraction measured slower than the plain operator
+// (the sampler is bound by the latency of these dependent chains, not by instruction issue: profiles/r02_s5_ncu_epd_sample.txt).
+BBMCU_D float epd_gamma_series_p(float a, float x, float norm)          // detail::gamma<100, true>
 {
   if(!((x >= 0.0f) && (a > 0.0f))) return 0.0f;
   float ap = a + 1.0f;
   float sum = 1.0f / a, term = sum;
   bool converged = false;
+  const bool fast = (a > 1e-30f) && (a < 1e29f);              // a + m, m <= 101, is then in range as well
   for(int m=1; m <= 100 && !converged; ++m, ap += 1.0f)
   {
-    term *= x * (1.0f / ap);
+    term *= x * (fast ? ieee_rcp_raw(ap) : 1.0f / ap);
     sum += term;
     converged = fabsf(term) < fabsf(sum)*kEps;
   }
-  float norm = lgammaf(a);
   sum *= expf(-x + a*logf(x) - norm);
   return sum;
 }
-BBMCU_D float epd_gamma_cf_q(float a, float x)              // detail::Gamma<100, true> (modified Lentz)
+BBMCU_D float epd_gamma_cf_q(float a, float x, float norm)  // detail::Gamma<100, true> (modified Lentz)
 {
   if(!((x >= 0.0f) && (a > 0.0f))) return 0.0f;
   const float tiny = 1.17549435e-38f / kEps;
@@ -100,13 +105,12 @@ BBMCU_D float epd_gamma_cf_q(float a, float x)              // detail::Gamma<100
     G = G*delta;
     converged = fabsf(delta - 1.0f) <= kEps;
   }
-  float norm = lgammaf(a);
   return expf(-x + a*logf(x) - norm) * G;
 }
-BBMCU_D void epd_gamma_pq(float a, float x, float& p, float& q)   // gamma_pq (gamma.h:620-660) without the Temme branch
+BBMCU_D void epd_gamma_pq(float a, float x, float norm, float& p, float& q)   // gamma_pq (gamma.h:620-660) without the Temme branch; norm = lgammaf(a)
 {
-  if(x <= a + 1.0f) { p = epd_gamma_series_p(a, x); q = 1.0f - p; }
-  else if(x > a + 1.0f) { q = epd_gamma_cf_q(a, x); p = 1.0f - q; }
+  if(x <= a + 1.0f) { p = epd_gamma_series_p(a, x, norm); q = 1.0f - p; }
+  else if(x > a + 1.0f) { q = epd_gamma_cf_q(a, x, norm); p = 1.0f - q; }
   else { p = 0.0f; q = 0.0f; }                                  // NaN x
 }
 
@@ -199,7 +203,7 @@ BBMCU_D float epd_Sn(int N, float x, float a, float tol)
   return sum;
 }
 BBMCU_D float epd_Fn(int N, float x, float a, float v) { return expf((v + x - logf(epd_Sn(N, x, a, 0.0f))) / a); }
-BBMCU_D float epd_a_greater_one(float a, float p, float q, bool& converged)
+BBMCU_D float epd_a_greater_one(float a, float p, float q, float lg, bool& converged)      // lg = lgammaf(a)
 {
   float w = epd_eq31(a, p, q);
   if((a >= 500.0f) && ((double)fabsf(1.0f - w/a) < 1e-6)) { converged = true; return w; }
@@ -207,7 +211,6 @@ BBMCU_D float epd_a_greater_one(float a, float p, float q, bool& converged)
   {
     if(w < 3.0f*a) return w;
     float D = fmaxf(a*(a - 1.0f), 2.0f);
-    float lg = lgammaf(a);
     float lb = logf(q) + lg;
     if((double)lb <= (double)(-D)*2.3) return epd_eq25(a, -lb);
     return epd_eq33(a, -lb, w);
@@ -235,11 +238,11 @@ BBMCU_D float epd_gamma_q_inv(float a, float q)
   float p = 1.0f - q;
   bool converged = false;
   float x;
+  const float lg = lgammaf(a);
   if(a == 1.0f) { x = -logf(q); converged = true; }
   else if(a < 1.0f) x = epd_a_less_one(a, p, q);
-  else if(a > 1.0f) x = epd_a_greater_one(a, p, q, converged);
+  else if(a > 1.0f) x = epd_a_greater_one(a, p, q, lg, converged);
   else x = 0.0f;
-  float lg = lgammaf(a);
   for(int itr=0; itr < 3 && !converged; ++itr)
   {
     float r;
@@ -251,7 +254,7 @@ BBMCU_D float epd_gamma_q_inv(float a, float q)
       float phi = lambda - 1.0f - logf(lambda);
       r = (float)(sqrt(0.5*(double)a/kPiD) * (double)expf(-a*phi - delta));
     }
-    float P, Q; epd_gamma_pq(a, x, P, Q);
+    float P, Q; epd_gamma_pq(a, x, lg, P, Q);
     float t = (((double)p <= 0.5) ? (P - p) : (q - Q)) / r;
     float w = (float)(0.5 * (double)(a - 1.0f - x));
     bool m = ((double)fabsf(t) <= 0.1) && ((double)fabsf(w*t) <= 0.1);

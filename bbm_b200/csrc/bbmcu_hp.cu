@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "bbmcu_ctx.hpp"
+#include "bbmcu_hpnorm.cuh"
 
 using namespace bbmcu;
 
@@ -37,6 +38,22 @@ __global__ void __launch_bounds__(128) k_hp_p2(const float* __restrict__ q, cons
     integral += dq[k] * expf(-powf(r2 + qk*qk, p));
   }
   p2[pi*kJ + j] = (float)(2.0 * (double)norm[pi] * (double)integral);
+}
+
+// ---- the renormalisation table sigma_rel^2 / sigma_s^2 (precompute/HolzschuchPacanowski/normalization.cpp) ---------------
+// 100 x 100 x 100 entries over (b, c, sin theta_i); each is the generator's integralSH (normalization.cpp:133-155): a
+// sequential sum over f = 1 - sin .. 1 + sin in steps of 0.01 degree of  alpha(f) f df S_HS(f)  - up to 11 459 terms of a
+// double pow and a double acos - plus the closed form of the inner disc.  The generator runs the 5.7e9 terms on one core;
+// here one thread owns one entry and walks it in the generator's order with the generator's float / double mix (float f
+// and float running sum, double pow / acos / products), so an entry differs from the generator's only where the device's
+// double pow / acos round differently from the host libm's.  Threads of a warp share sin theta_i (equal trip counts).
+__global__ void __launch_bounds__(128) k_hp_normalization(float* __restrict__ table)
+{
+  const int si = blockIdx.y;                                   // sin(theta) index: uniform per block
+  const int bc = blockIdx.x * blockDim.x + threadIdx.x;        // b index * 100 + c index
+  if(bc >= kHpNormN*kHpNormN) return;
+  const int bi = bc / kHpNormN, ci = bc % kHpNormN;
+  table[((size_t)bi*kHpNormN + ci)*kHpNormN + si] = hp_normalization_entry(bi, ci, si);
 }
 
 float conv_f(float x) { return std::pow(std::log(1.0f / x), 20.0f); }
@@ -110,5 +127,23 @@ extern "C" int bbmcu_hp_precompute_g1(bbmcu_ctx* ctx, float* table)
       }
       for(int j=0; j < kJ; ++j) integral[j] = (float)(1.0 / (1.0 + (double)integral[j]));
     }
+  });
+}
+
+extern "C" int bbmcu_hp_precompute_normalization(bbmcu_ctx* ctx, float* table)
+{
+  return guarded(ctx, [&] {
+    if(!ctx || !table) throw std::invalid_argument("BBM: null argument");
+    BBMCU_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)kHpNormN*kHpNormN*kHpNormN;
+    float* d_table = nullptr;
+    BBMCU_CUDA(cudaMalloc(&d_table, n*sizeof(float)));
+    k_hp_normalization<<<dim3((kHpNormN*kHpNormN + 127)/128, kHpNormN), 128, 0, ctx->stream>>>(d_table);
+    cudaError_t e = cudaGetLastError();
+    if(e == cudaSuccess) e = cudaMemcpyAsync(table, d_table, n*sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_table);
+    ++ctx->launches;
+    if(e != cudaSuccess) throw CudaError(std::string("bbmcu_hp_precompute_normalization: ") + cudaGetErrorString(e));
   });
 }

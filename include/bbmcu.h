@@ -155,6 +155,11 @@ BBMCU_API int  bbmcu_merl_write(bbmcu_ctx* ctx, const char* filename, const floa
 /* regenerates the 100 x 1000 G1 table of include/precomputed/holzschuchpacanowski/G1.h (row = 5/p - 1, column = the
  * table's tan(theta) map) into `table` (HOST memory, 100000 floats): ~1e9 quadrature terms on the GPU */
 BBMCU_API int  bbmcu_hp_precompute_g1(bbmcu_ctx* ctx, float* table);
+/* regenerates the 100 x 100 x 100 renormalisation table sigma_rel^2 / sigma_s^2 of precompute/HolzschuchPacanowski/
+ * normalization.cpp (index = (b, c, sin theta_i) as its main() maps them, :214-236; integralSH :133-155: 5.7e9 terms of a
+ * double pow and acos) into `table` (HOST memory, 1 000 000 floats, sin theta_i fastest).  The reference ships no copy of
+ * this table (it is one of its missing large blobs); entries follow the generator's own operation order. */
+BBMCU_API int  bbmcu_hp_precompute_normalization(bbmcu_ctx* ctx, float* table);
 
 /* ---- losses (include/loss/{cosine_weighted_l2,cosine_weighted_log}.h, include/bbm/sampledlossfunction.h:62-87) ---------------------------------- */
 /* The reference evaluates  loss = (1/N) sum_i e(in_i, out_i, fitted.eval(in_i,out_i), reference.eval(in_i,out_i))

@@ -10,6 +10,7 @@
 #include "bbmcu_desc.hpp"
 #include "bbmcu_kernels.cuh"
 #include "bbmcu_lossop.cuh"
+#include "bbmcu_hpnorm.cuh"
 
 using namespace bbmcu;
 
@@ -37,6 +38,7 @@ const char* hostsim_last_error() { return g_err.c_str(); }
 // the EPD G1 table (bbm_b200/data/epd_g1.f32), owned by the caller
 void hostsim_set_epd_table(const float* table) { g_epd_g1_host = table; }
 float hostsim_gamma_q_inv(float a, float q) { return epd_gamma_q_inv(a, q); }
+float hostsim_hp_normalization_entry(int bi, int ci, int si) { return hp_normalization_entry(bi, ci, si); }
 
 int hostsim_eval(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
 { GUARD( EvalOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
