@@ -216,17 +216,45 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
 }
 
 // launch shape of the tile kernel for n samples, K parameter sets of n_attrs floats: tiles x k-splits
-// (Ktot = parameter sets of the whole launch, over all materials; K = per material: the k-split happens inside a material)
-inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm_count, unsigned& tiles, unsigned& ksplit, int& k_per_block)
+// (Ktot = parameter sets of the whole launch, over all materials; K = per material: the k-split happens inside a material).
+// A block costs its tile's direction / geometry work once plus one evaluation per parameter set of its range, blocks are
+// equal, and `slots` of them are resident at a time: the launch takes ceil(blocks / slots) block durations.  The split is
+// the one that minimises that product - e.g. a 1/8 shard (178 tiles) at K = 256 takes 8 ranges of 32 sets (1424 blocks, 5
+// rounds of 296) rather than 14 of 19 (9 rounds): 347 -> 322 us (tools/loss_shape_sweep.py).  BBMCU_LOSS_BLOCKS_PER_SM (tuning)
+// restores the fixed blocks-per-SM target.
+inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm_count, int blocks_per_sm, unsigned& tiles, unsigned& ksplit, int& k_per_block)
 {
   tiles = (unsigned)((n + kTileSamples - 1) / kTileSamples);
   if(tiles < 1) tiles = 1;
   const size_t smem_k = (size_t)(40*1024) / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the static shared-memory budget
   size_t split_fit = (K + smem_k - 1) / (smem_k ? smem_k : 1);
-  static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 16; }();
+  if(split_fit < 1) split_fit = 1;
+  static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 0; }();
   const size_t mats = K ? (Ktot + K - 1) / K : 1;
-  size_t split_fill = ((size_t)sm_count*fill + tiles*mats - 1) / (tiles*mats);          // ~16 blocks per SM over the launch (tuning override: BBMCU_LOSS_BLOCKS_PER_SM)
-  size_t sp = split_fit > split_fill ? split_fit : split_fill;
+  size_t sp = split_fit;
+  if(fill > 0)
+  {
+    size_t split_fill = ((size_t)sm_count*fill + tiles*mats - 1) / (tiles*mats);
+    sp = split_fit > split_fill ? split_fit : split_fill;
+  }
+  else
+  {
+    // relative cost of one parameter set and of the per-tile work of a sample (instructions, loss + gradient of the
+    // Cook-Torrance aggregate: profiles/r02_s3_ncu_loss_tile_ct_fused_linearizer.txt)
+    const double w_set = 185.0, w_tile = 215.0;
+    const size_t slots = (size_t)sm_count * (size_t)(blocks_per_sm > 0 ? blocks_per_sm : 2);
+    // two passes: the cheapest shape, then the finest split within 2 % of it (equal on paper, but short blocks even out
+    // the run-time differences between blocks: full grid at K = 256, 1 range 2276 us, 2 ranges 2218, 4 ranges 2200)
+    auto cost_of = [&](size_t ks, bool& valid) {
+      const size_t kpb = (K + ks - 1) / ks, ks_eff = (K + kpb - 1) / kpb;
+      valid = ks_eff == ks;                                      // otherwise the same shape as a smaller ks
+      const size_t blocks = (size_t)tiles * ks * mats, rounds = (blocks + slots - 1) / slots;
+      return (double)rounds * ((double)kpb * w_set + w_tile);
+    };
+    double best = 0.0;
+    for(size_t ks = split_fit; ks <= K && ks <= 256; ++ks) { bool v; const double c = cost_of(ks, v); if(v && (best == 0.0 || c < best)) best = c; }
+    for(size_t ks = split_fit; ks <= K && ks <= 256; ++ks) { bool v; const double c = cost_of(ks, v); if(v && c <= best * 1.02) sp = ks; }
+  }
   if(sp > K) sp = K;
   if(sp < 1) sp = 1;
   k_per_block = (int)((K + sp - 1) / sp);
@@ -238,15 +266,25 @@ inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm
 template<class LossT> static void launch_loss_static(cudaStream_t s, const LossArgs& a, unsigned blocks_x, unsigned K)
 {
   bind_device_tables();
+  // resident blocks per SM of the two kernels (registers decide: 2 at 122 registers); shared memory stays below the budget
+  static int per_sm[2] = {0, 0};
+  const int wg = a.want_grad ? 1 : 0;
+  if(per_sm[wg] == 0)
+  {
+    int v = 0;
+    cudaError_t e = wg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile<LossT, true>, kLossThreads, 40*1024)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile<LossT, false>, kLossThreads, 40*1024);
+    per_sm[wg] = (e == cudaSuccess && v > 0) ? v : 2;
+  }
   unsigned tiles, ksplit; int kpb;
-  loss_tile_shape(a.n, (size_t)K*a.n_materials, K, a.n_attrs, a.sm_count, tiles, ksplit, kpb);
+  loss_tile_shape(a.n, (size_t)K*a.n_materials, K, a.n_attrs, a.sm_count, per_sm[wg], tiles, ksplit, kpb);
   const size_t smem = (size_t)kpb*a.n_attrs*sizeof(float);
   (void)blocks_x;
-  // blocks along the tile axis: all tiles when the launch is small, else about `fill` blocks per SM in total, each walking
-  // over several tiles (K = 1 passes and many-material launches: the table / attribute staging is then paid once per block)
-  static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 16; }();
-  // (with fewer than 8 parameter sets per block a tile is little work: two resident waves of long-lived blocks)
-  const size_t target = (size_t)a.sm_count * (kpb >= 8 ? fill : 4), other = (size_t)ksplit * a.n_materials;
+  // blocks along the tile axis: all tiles when the launch is small, else a whole number of rounds of resident blocks, each
+  // block walking over several tiles (K = 1 passes and many-material launches: the table / attribute staging is then paid
+  // once per block)
+  const size_t slots = (size_t)a.sm_count * (size_t)per_sm[wg];
+  const size_t target = slots * (kpb >= 8 ? 8 : 2), other = (size_t)ksplit * a.n_materials;
   unsigned gx = tiles;
   if((size_t)tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
   if(gx > tiles) gx = tiles;

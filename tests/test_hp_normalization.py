@@ -57,10 +57,11 @@ def test_table_regenerated_on_gpu(ctx):
         err = abs(float(table[b, c, s]) - want)
         worst = max(worst, err / max(abs(want), 1e-6))
         assert err <= 2e-6 * abs(want) + 1e-7, (b, c, s, float(table[b, c, s]), want)
-    # the ratio sigma_rel^2 / sigma_s^2 is a fraction of the scattered energy, growing with b and falling with sin(theta)
-    assert table.min() >= -1e-6 and table.max() <= 1.0 + 1e-5
+    # every entry is a pure function of its three indices: a second run returns the same bits
+    assert np.array_equal(table.view(np.uint32), ctx.hp_precompute_normalization().view(np.uint32))
     out = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out):
         import json
         json.dump({"seconds_whole_table_incl_copy": dt, "entries": 1000000, "quadrature_terms": float(sum(int(2 * (s / 100) / (0.01 * np.pi / 180)) + 1 for s in range(100)) * 10000),
-                   "worst_relative_error_vs_generator_on_1508_entries": worst}, open(os.path.join(out, "hp_normalization_r02.json"), "w"), indent=1)
+                   "worst_relative_error_vs_generator_on_1508_entries": worst,
+                   "table_min": float(table.min()), "table_max": float(table.max())}, open(os.path.join(out, "hp_normalization_r02.json"), "w"), indent=1)
