@@ -197,4 +197,30 @@ struct BsdfSingle
   BBMCU_D static void sample(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, float& pdfv, int& flag) { M::sample(out, xi, b.attrs, component, dir, pdfv, flag); }
 };
 
+// ---- EPD: which BSDF types can reach the G1 table, and the prologue that stages its two rows (bbmcu_epd.cuh) ----------------
+using EpdModel = typename ModelOf<M_EPD>::type;
+template<class B> struct UsesEpd { static constexpr bool value = false; };
+template<> struct UsesEpd<BsdfSingle<EpdModel>> { static constexpr bool value = true; };
+template<> struct UsesEpd<BsdfGeneric> { static constexpr bool value = true; };
+template<class M0> struct UsesEpd<BsdfPair<M0, EpdModel>> { static constexpr bool value = true; };
+#if defined(__CUDACC__) && !defined(BBMCU_EPD_NO_STAGE)
+// every thread of the block calls this before the first evaluation; callers __syncthreads() afterwards
+__device__ __forceinline__ void epd_stage_rows(const BsdfDesc& b, int tid, int nthreads)
+{
+  EpdStage& st = epd_stage();
+  int lobe = -1;
+  for(int l = 0; l < b.n_lobes; ++l) if(b.model[l] == M_EPD) { lobe = l; break; }
+  int r0 = -1, r1 = -1;
+  if(lobe >= 0)
+  {
+    const float p = b.attrs[b.offset[lobe] + EpdModel::OFF_NDF + 1];
+    const double ip = 5.0 / (double)p - 1.0;                   // the row map of G1.h, as NdfEPD::G1v forms it
+    r0 = epd_clamp_index(floor(ip), kEpdRows); r1 = epd_clamp_index(ceil(ip), kEpdRows);
+    const float* tab = epd_table();
+    for(int i = tid; i < kEpdCols; i += nthreads) { st.rows[i] = __ldg(tab + r0*kEpdCols + i); st.rows[kEpdCols + i] = __ldg(tab + r1*kEpdCols + i); }
+  }
+  if(tid == 0) { st.r0 = r0; st.r1 = r1; }
+}
+#endif
+
 } // namespace bbmcu

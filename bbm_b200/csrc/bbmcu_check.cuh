@@ -217,7 +217,7 @@ BBMCU_D void check_item(const CheckArgs& a, const BsdfDesc& bsdf, unsigned long 
 // which calls of the model a kernel instance holds (keeps each of the three kernels per model small):
 //   CheckE: eval only (reflectance over the sphere, reciprocity)      CheckS: sample + pdf (pdf test, bin counts)
 //   CheckSE: sample + eval (reflectance with importance sampling)     CheckP: pdf only (pdf integral, bin pdf)
-template<class B, bool EVAL, bool SAMPLE> struct CheckView : B { static constexpr bool kCheckEval = EVAL, kCheckSample = SAMPLE; };
+template<class B, bool EVAL, bool SAMPLE> struct CheckView : B { using Base = B; static constexpr bool kCheckEval = EVAL, kCheckSample = SAMPLE; };
 
 #ifdef __CUDACC__
 template<class V>
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kCheckThreads) k_check(const CheckArgs a, cons
   __shared__ unsigned int s_hist[kCheckSharedBins];
   __shared__ BsdfDesc sb;
   const BsdfDesc* bsdf = &desc;
+  if constexpr (UsesEpd<typename V::Base>::value) { epd_stage_rows(desc, threadIdx.x, blockDim.x); __syncthreads(); }
   if constexpr (V::kTables)
   {
     if(desc.n_tables)                          // He-family / measured lobe: build the sampling CDF first (as k_foreach4 does)

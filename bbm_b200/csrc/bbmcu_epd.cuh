@@ -35,6 +35,18 @@ BBMCU_D const float* epd_table()
 #endif
 }
 
+// ---- the two G1 rows of a launch-uniform p, staged in shared memory ---------------------------------------------------
+// A lookup touches the rows floor(5/p - 1) and ceil(5/p - 1) only (include/ndf/epd.h:142-152,
+// include/precomputed/holzschuchpacanowski/G1.h:14-16).  In every element-wise kernel the BSDF - hence p - is the same for
+// the whole launch, so the kernel prologue (epd_stage_rows, bbmcu_bsdf.cuh) copies those two rows (2 x 1000 floats, 8 KB)
+// from the device table into shared memory and the eight taps of an eval come from there.  Kernels that evaluate MANY
+// parameter sets per launch (the batched losses: p differs per set) are compiled with BBMCU_EPD_NO_STAGE and read the
+// table - 400 KB, L2-resident - through the read-only path instead.
+struct EpdStage { int r0, r1; float rows[2*kEpdCols]; };
+#if defined(__CUDACC__) && !defined(BBMCU_EPD_NO_STAGE)
+__device__ __forceinline__ EpdStage& epd_stage() { __shared__ EpdStage st; return st; }
+#endif
+
 // ---- tab<float, {100,1000}>::interpolate(p, t) with derivative of the bilinear patch ------------------
 BBMCU_D int epd_clamp_index(double v, int dim)
 {
@@ -57,7 +69,20 @@ BBMCU_D float epd_g1_lookup(double ip, double it, float* d_ip, float* d_it)
   double fc = floor(it), cc = ceil(it), wc = it - fc;
   int r0 = epd_clamp_index(fr, kEpdRows), r1 = epd_clamp_index(cr, kEpdRows);
   int c0 = epd_clamp_index(fc, kEpdCols), c1 = epd_clamp_index(cc, kEpdCols);
-  float v00 = tab[r0*kEpdCols + c0], v01 = tab[r0*kEpdCols + c1], v10 = tab[r1*kEpdCols + c0], v11 = tab[r1*kEpdCols + c1];
+  float v00, v01, v10, v11;
+#if defined(__CUDA_ARCH__) && !defined(BBMCU_EPD_NO_STAGE)
+  const EpdStage& st = epd_stage();
+  if(st.r0 == r0 && st.r1 == r1)                               // uniform: the staged rows are this launch's rows
+  { v00 = st.rows[c0]; v01 = st.rows[c1]; v10 = st.rows[kEpdCols + c0]; v11 = st.rows[kEpdCols + c1]; }
+  else
+#endif
+  {
+#ifdef __CUDA_ARCH__
+    v00 = __ldg(tab + r0*kEpdCols + c0); v01 = __ldg(tab + r0*kEpdCols + c1); v10 = __ldg(tab + r1*kEpdCols + c0); v11 = __ldg(tab + r1*kEpdCols + c1);
+#else
+    v00 = tab[r0*kEpdCols + c0]; v01 = tab[r0*kEpdCols + c1]; v10 = tab[r1*kEpdCols + c0]; v11 = tab[r1*kEpdCols + c1];
+#endif
+  }
   float a = (float)std_lerp((double)v00, (double)v01, wc);
   float b = (float)std_lerp((double)v10, (double)v11, wc);
   if(d_ip) *d_ip = (ip >= 0.0 && ip <= (double)(kEpdRows - 1)) ? (b - a) : 0.0f;

@@ -16,6 +16,7 @@
 namespace bbmcu {
 
 constexpr int kVec = 4;
+template<class...> struct VoidOf { using type = void; };
 
 // ---- SoA access: 4 consecutive elements of one plane ---------------------------------------------
 struct Lanes { float v[kVec]; };
@@ -93,6 +94,7 @@ BBMCU_D GenInputs generate_inputs(uint64_t seed, uint64_t index)
 // ---- operators --------------------------------------------------------------------------------------
 template<class B> struct EvalOp
 {
+  using BsdfT = B;
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;     // eval never reads the sampling tables
   BsdfDesc bsdf; int component; const float* in; const float* out; float* rgb; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
@@ -107,6 +109,7 @@ template<class B> struct EvalOp
 
 template<class B> struct PdfOp
 {
+  using BsdfT = B;
   static constexpr bool kOneWaveWithTables = true;            // cheap body: pay the CDF prologue once per SM slot (bbmcu_launch.cuh)
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
@@ -122,6 +125,7 @@ template<class B> struct PdfOp
 
 template<class B> struct ReflectanceOp
 {
+  using BsdfT = B;
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false;
   BsdfDesc bsdf; int component; const float* out; float* rgb; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
@@ -136,6 +140,7 @@ template<class B> struct ReflectanceOp
 
 template<class B> struct SampleOp
 {
+  using BsdfT = B;
   static constexpr bool kOneWaveWithTables = true;
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
@@ -155,6 +160,7 @@ template<class B> struct SampleOp
 // inputs are written to `gen_out` / `gen_xi` when those are given.
 template<class B, bool GEN> struct SampleEvalPdfOpT
 {
+  using BsdfT = B;
   static constexpr bool kOneWaveWithTables = false;           // dominated by the model's eval, whose cost varies per element: keep many blocks for balance
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocksFused;     // (the hand-merged GGX kernel: 256 x 3 with 4736 blocks 94.6 G pairs/s, 256 x 4 94.1, 512 x 2 92.9, 128 x 8 93.1, 1024 x 1 91.3)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
@@ -214,6 +220,7 @@ template<class B> using SampleEvalPdfGenOp = SampleEvalPdfOpT<B, true>;      // 
 // `in` / `out` (optional) receive the generated directions - the parity protocol of SURVEY.md section 7.
 template<class B> struct EvalGridOp
 {
+  using BsdfT = B;
   static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocks;
   static constexpr bool kHasBsdf = true, kTables = false, kLinTab = true;
   BsdfDesc bsdf; int component; const float* lin_tab; uint32_t first; float* rgb; float* in; float* out; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
@@ -307,6 +314,8 @@ struct MerlLookupOp
   }
 };
 
+template<class Op, class = void> struct OpUsesEpd { static constexpr bool value = false; };
+template<class Op> struct OpUsesEpd<Op, typename VoidOf<typename Op::BsdfT>::type> { static constexpr bool value = UsesEpd<typename Op::BsdfT>::value; };
 template<class Op, class = void> struct UsesLinTab { static constexpr bool value = false; };
 template<class Op> struct UsesLinTab<Op, typename std::enable_if<Op::kLinTab>::type> { static constexpr bool value = true; };
 
@@ -317,6 +326,7 @@ __global__ void k_merl_lin_tab(float* tab);
 template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks) k_foreach4(const Op op, size_t groups)
 {
   const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if constexpr (OpUsesEpd<Op>::value) { epd_stage_rows(op.bsdf, threadIdx.x, blockDim.x); __syncthreads(); }       // G1 rows of this launch's p -> shared memory
   if constexpr (!Op::kHasBsdf) { for(size_t g = first; g < groups; g += stride) op.group(g * kVec); }
   else if constexpr (UsesLinTab<Op>::value)
   {

@@ -1,3 +1,5 @@
+// (batched losses evaluate many parameter sets per launch: the EPD G1 rows are not launch-uniform here - read the table, not a staged copy)
+#define BBMCU_EPD_NO_STAGE
 // Loss objects of the C ABI (include/bbmcu.h): the six metrics over the MERL or spherical linearizer,
 // batched over K parameter sets, with the analytic parameter gradient.
 // Mirrors include/bbm/sampledlossfunction.h:26-95 and the thin metric classes of include/loss/*.h.

@@ -1,3 +1,5 @@
+// (batched losses evaluate many parameter sets per launch: the EPD G1 rows are not launch-uniform here - read the table, not a staged copy)
+#define BBMCU_EPD_NO_STAGE
 // loss(+gradient) kernel instantiations, single lobe, model group 3
 #include "bbmcu_losskernel.cuh"
 namespace bbmcu {
