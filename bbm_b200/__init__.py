@@ -378,22 +378,27 @@ class Context:
         return t
 
     # ---- losses ------------------------------------------------------------------------------------
-    def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False):
-        return Loss(self, metric, reference, grid, component, unit, first, count, materialise)
+    def loss(self, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False, interleaved=None):
+        return Loss(self, metric, reference, grid, component, unit, first, count, materialise, interleaved)
 
 
 class Loss:
     """a bbm::sampledlossfunction (include/bbm/sampledlossfunction.h:26-95) with one of the six error
     functors of include/loss/*.h.  `reference` is a Bsdf, a (3, 1458000) measured MERL table, or a LIST of such tables
     (a batch of materials evaluated in one launch, see eval_multi).  By default the kernels generate the linearizer's
-    directions from the sample index; materialise=True keeps them as planes in device memory instead (same bits)."""
+    directions from the sample index; materialise=True keeps them as planes in device memory instead (same bits).
+    The shard this object owns: samples [first, first + count) (count 0 = all), or - interleaved=(rank, world) - every
+    world-th block of 1024 samples starting at block `rank`: shards of equal cost (BBMCU_LOSS_SHARD_INTERLEAVED)."""
 
-    def __init__(self, ctx, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False):
+    def __init__(self, ctx, metric, reference, grid=None, component=ALL, unit=RADIANCE, first=0, count=0, materialise=False, interleaved=None):
         self.ctx = ctx
         self._h = C.c_void_p()
         m = METRICS.index(metric) if isinstance(metric, str) else int(metric)
         self._keep = reference
         flags = 1 if materialise else 0
+        if interleaved is not None:
+            first, count = int(interleaved[0]), int(interleaved[1])
+            flags |= 2
         if isinstance(reference, Bsdf):
             ref_b, tabs, M = reference._h, None, 1
         else:

@@ -43,6 +43,7 @@ struct bbmcu_loss
   uint64_t N = 0;            // samples of the whole linearizer
   uint64_t first = 0;        // this shard
   size_t count = 0;
+  int il_world = 0, il_rank = 0;   // BBMCU_LOSS_SHARD_INTERLEAVED: blocks il_rank, il_rank + il_world, ... of kTileSamples samples
   int n_materials = 1;       // reference operands sharing this linearizer (bbmcu_loss_create_ex: a batch of measured tables)
   bool fused = true;         // directions generated inside the kernels (no d_in / d_out planes kept)
   const float* d_lin_tab = nullptr;   // the device's separable merl_linearizer table (owned by the library, per device), or d_sph_tab
@@ -242,7 +243,7 @@ template<class T> void grow(T*& p, size_t& cap, size_t need)
 void fill_sample_source(const bbmcu_loss* L, LossArgs& a)
 {
   a.lin_mode = !L->fused ? LIN_MATERIALISED : (L->merl_grid ? LIN_MERL_TABLES : LIN_SPHERICAL);
-  a.lin_tab = L->d_lin_tab; a.first = L->first; a.grid = L->grid;
+  a.lin_tab = L->d_lin_tab; a.first = L->first; a.grid = L->grid; a.il_world = L->il_world; a.il_rank = L->il_rank;
   a.in = L->d_in; a.out = L->d_out; a.ref = L->d_ref; a.ref_stride = 3*L->count; a.n = L->count;
   a.k_per_material = 1; a.n_materials = 1;
 }
@@ -270,9 +271,24 @@ int bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid*
     L->n_materials = n_materials;
     L->fused = !(flags & BBMCU_LOSS_MATERIALISE_DIRECTIONS);
     if(grid) { L->grid = to_device_grid(*grid); L->N = L->grid.size(); } else L->N = kMerlBins;
-    if(first > L->N) throw std::out_of_range("BBM: loss shard starts beyond the linearizer size");
-    if(count == 0) count = L->N - first;
-    if(first + count > L->N) throw std::out_of_range("BBM: loss shard exceeds the linearizer size");
+    if(flags & BBMCU_LOSS_SHARD_INTERLEAVED)
+    {
+      // (first, count) = (rank, world): every world-th block of kTileSamples consecutive samples
+      if(count < 1 || count > 65536 || first >= count) throw std::invalid_argument("BBM: interleaved loss shard needs first = rank < count = world");
+      const uint64_t blocks = (L->N + kTileSamples - 1) / kTileSamples, world = count, rank = first;
+      const uint64_t mine = rank < blocks ? (blocks - rank + world - 1) / world : 0;
+      uint64_t n_il = mine * kTileSamples;
+      if(mine && (rank + (mine - 1)*world) == blocks - 1) n_il -= blocks*kTileSamples - L->N;       // the grid's last, partial block is this shard's last
+      if(world > 1) { L->il_world = (int)world; L->il_rank = (int)rank; }
+      first = 0; count = n_il;
+      if(world == 1) count = L->N;
+    }
+    else
+    {
+      if(first > L->N) throw std::out_of_range("BBM: loss shard starts beyond the linearizer size");
+      if(count == 0) count = L->N - first;
+      if(first + count > L->N) throw std::out_of_range("BBM: loss shard exceeds the linearizer size");
+    }
     L->first = first; L->count = (size_t)count;
     const size_t n = L->count;
     if(L->merl_grid) L->d_lin_tab = merl_lin_table_device(ctx->device);
@@ -297,8 +313,22 @@ int bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid*
     // 1. the linearizer's directions for this shard: needed here to tabulate the reference operand; kept only in
     //    materialised mode (the fused kernels regenerate the same bits from the bin index)
     const bool al = true;                     // cudaMalloc'ed planes; launch_foreach4 checks the plane stride
-    if(L->merl_grid) { MerlDirsOp op; op.first = (uint32_t)first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
-    else { SphericalDirsOp op; op.grid = L->grid; op.first = first; op.in = L->d_in; op.out = L->d_out; op.n = n; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, n); }
+    // (an interleaved shard is generated block by block into planes that are n floats apart)
+    const size_t piece = L->il_world > 1 ? (size_t)kTileSamples : n;
+    const size_t saved_ld = ctx->ld;
+    ctx->ld = n;
+    try
+    {
+      for(size_t off = 0; off < n; off += piece)
+      {
+        const size_t len = std::min(piece, n - off);
+        const uint64_t lin = L->il_world > 1 ? ((uint64_t)(off / kTileSamples) * (uint64_t)L->il_world + (uint64_t)L->il_rank) * kTileSamples : first;
+        if(L->merl_grid) { MerlDirsOp op; op.first = (uint32_t)lin; op.in = L->d_in + off; op.out = L->d_out + off; op.n = len; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, len); }
+        else { SphericalDirsOp op; op.grid = L->grid; op.first = lin; op.in = L->d_in + off; op.out = L->d_out + off; op.n = len; op.aligned = al; launch_foreach4(ctx, ctx->stream, op, len); }
+      }
+    }
+    catch(...) { ctx->ld = saved_ld; throw; }
+    ctx->ld = saved_ld;
     // 2. the reference operand tabulated at those directions (it never changes during a fit)
     if(reference_bsdf)
     {

@@ -26,7 +26,8 @@ struct LossArgs
   // the materialised planes hold (same functions), so a pass reads only the 12 B per sample of measured data.
   int lin_mode;
   const float* lin_tab;
-  uint64_t first;         // linearizer index of the shard's sample 0
+  uint64_t first;         // linearizer index of the shard's sample 0 (contiguous shards)
+  int il_world, il_rank;  // il_world > 1: the shard is blocks il_rank, il_rank + il_world, ... of kTileSamples consecutive samples
   SphericalGrid grid;
   const float* in;        // 3 planes of n (LIN_MATERIALISED)
   const float* out;       // 3 planes of n
@@ -51,11 +52,22 @@ struct LossArgs
 constexpr int kInlineAttrFloats = 256;
 BBMCU_D float loss_attr(const LossArgs& a, size_t idx) { return a.inline_count ? a.inline_attrs[idx] : a.attrs[idx]; }
 
+constexpr int kLossThreads = 256;
+constexpr int kTileSPT = 4;
+constexpr int kTileKChunk = 8;
+constexpr int kTileSamples = kTileSPT * kLossThreads;
+
+// linearizer index of sample i of the shard
+BBMCU_D uint64_t loss_lin_index(const LossArgs& a, size_t i)
+{
+  if(a.il_world > 1) { const size_t t = i / kTileSamples; return ((uint64_t)t * (uint64_t)a.il_world + (uint64_t)a.il_rank) * kTileSamples + (uint64_t)(i - t*kTileSamples); }
+  return a.first + i;
+}
 // sample i of the shard: direction pair (generated or loaded) - s_lin is the shared-memory copy of a.lin_tab
 BBMCU_D void loss_dirs(const LossArgs& a, const float* s_lin, size_t i, f3& in, f3& out)
 {
-  if(a.lin_mode == LIN_MERL_TABLES) merl_dirs_tab(s_lin, (uint32_t)(a.first + i), in, out);
-  else if(a.lin_mode == LIN_SPHERICAL) spherical_dirs_tab(a.grid, a.lin_tab, a.first + i, in, out);
+  if(a.lin_mode == LIN_MERL_TABLES) merl_dirs_tab(s_lin, (uint32_t)loss_lin_index(a, i), in, out);
+  else if(a.lin_mode == LIN_SPHERICAL) spherical_dirs_tab(a.grid, a.lin_tab, loss_lin_index(a, i), in, out);
   else
   {
 #ifdef __CUDA_ARCH__
@@ -75,8 +87,6 @@ __device__ __forceinline__ void loss_stage_lin(const LossArgs& a, float* s_lin)
 }
 #endif
 
-constexpr int kLossThreads = 256;
-
 // LossT::sample(attrs, metric, component, in, out, ref, grad[P], want_grad) -> e   (LossSingle / LossPair)
 // ---- sample-stationary variant: the launch shape for batched passes --------------------------------
 // A block owns a tile of kTileSPT * 256 samples, loads them ONCE into registers and loops over its range of parameter
@@ -86,10 +96,6 @@ constexpr int kLossThreads = 256;
 // over the thread's kTileSPT samples, warp-shuffled in float (128 terms), and enter FP64 at the cross-warp step; block
 // partials are written per (parameter set, tile) and added in fixed order by k_loss_finish: deterministic, and a
 // parameter set's result does not depend on which other sets share the launch.
-constexpr int kTileSPT = 4;
-constexpr int kTileKChunk = 8;
-constexpr int kTileSamples = kTileSPT * kLossThreads;
-
 // Warp reduction of C values per lane with a halving butterfly: at each offset a lane keeps one half of its values
 // and ships the other half to its partner, so C values cost CP/2 + CP/4 + ... + 1 (+ the remaining plain steps)
 // shuffles instead of 5 C.  Afterwards the lane with (lane & rest) == 0 holds the full sum of value `idx`.

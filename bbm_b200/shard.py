@@ -13,6 +13,15 @@ def shard_range(n, rank, world):
     return first, max(0, min(per, n - first))
 
 
+def interleaved_indices(n, rank, world, block=1024):
+    """linearizer indices of the shard BBMCU_LOSS_SHARD_INTERLEAVED gives `rank`: blocks rank, rank + world, ... of `block`
+    consecutive samples, in the shard's own order (bbmcu_loss_terms order).  Equal work per shard where contiguous ranges are not."""
+    blocks = (n + block - 1) // block
+    mine = np.arange(rank, blocks, world, dtype=np.int64)
+    idx = (mine[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < n]
+
+
 def partition_by_cost(costs, world):
     """longest-processing-time-first assignment of independent jobs to ranks; returns a list of index lists"""
     order = np.argsort(-np.asarray(costs, np.float64), kind="stable")

@@ -394,12 +394,11 @@ def main():
     # ---- loss + gradient passes (BASELINE configs[2]), sample axis sharded over ranks --------------------
     loss_info = None
     if not args.no_loss:
-        N = bb.MERL_BINS
-        per = (N + world - 1) // world
-        first = rank * per
-        count = max(0, min(per, N - first))
+        # the sample axis is dealt to the ranks in blocks of 1024 samples (rank, rank + world, ...): contiguous eighths of
+        # the MERL grid are unequal work (the first has no pair below the horizon), interleaved shards are equal
+        shard = dict(interleaved=(rank, world))
         fitted, truth = bb.Bsdf(FITTED), bb.Bsdf(TRUTH)
-        L = ctx.loss("nganL2", truth, None, first=first, count=count)
+        L = ctx.loss("nganL2", truth, None, **shard)
         P = len(fitted.parameter_values())
         rng = np.random.default_rng(7)
         params = fitted.parameter_values()[None] * (1 + 0.1 * rng.random((LOSS_K, P)))
@@ -421,7 +420,7 @@ def main():
         L_peer, peer_error = None, None
         if world > 1:
             try:
-                L_peer = ctx.loss("nganL2", truth, None, first=first, count=count)
+                L_peer = ctx.loss("nganL2", truth, None, **shard)
                 L_peer.connect_peers(LOSS_K * (1 + P))
             except Exception as e:                                   # noqa: BLE001 - reported in the JSON line
                 L_peer, peer_error = None, str(e)[:200]
@@ -466,7 +465,7 @@ def main():
             rk = torch.zeros((kk, 1 + P), device=dev, dtype=torch.float64)
             by_k[str(kk)] = kk / (timed(lambda: L.eval_device(fitted, pk, rk), 20) * 1e-3)       # this rank's shard only, no collective
         # the same pass reading MATERIALISED direction planes (36 B per sample instead of 12): what round 1 shipped
-        Lm = ctx.loss("nganL2", truth, None, first=first, count=count, materialise=True)
+        Lm = ctx.loss("nganL2", truth, None, materialise=True, **shard)
         mat_ms = timed(lambda: Lm.eval_device(fitted, params, res), nl)
         del Lm
         if world == 1:

@@ -182,8 +182,13 @@ BBMCU_API int  bbmcu_loss_create(bbmcu_ctx* ctx, int metric, const bbmcu_spheric
  * through a 900-float separable table staged in shared memory; spherical_linearizer(idx) directly): a pass then reads only
  * the 12 B per sample of tabulated reference data and a loss object costs 17.5 MB per material instead of 52.5 MB.  The
  * generated directions are bit-identical to bbmcu_merl_dirs / bbmcu_spherical_dirs.  BBMCU_LOSS_MATERIALISE_DIRECTIONS
- * keeps the direction planes in device memory and reads them instead (36 B per sample; same results bit for bit). */
-enum { BBMCU_LOSS_MATERIALISE_DIRECTIONS = 1 };
+ * keeps the direction planes in device memory and reads them instead (36 B per sample; same results bit for bit).
+ * BBMCU_LOSS_SHARD_INTERLEAVED changes what (first, count) mean: first = rank, count = world, and the shard is every
+ * world-th BLOCK of 1024 consecutive samples (blocks rank, rank + world, ...).  Samples of the MERL grid differ in cost by
+ * region (pairs below the horizon leave the model early; the first eighth of the index range has none), so contiguous
+ * eighths are unequal work and the slowest shard sets the pace of a multi-GPU step; interleaved shards are equal.
+ * bbmcu_loss_terms then returns the shard's samples in its own (block-interleaved) order. */
+enum { BBMCU_LOSS_MATERIALISE_DIRECTIONS = 1, BBMCU_LOSS_SHARD_INTERLEAVED = 2 };
 BBMCU_API int  bbmcu_loss_create_ex(bbmcu_ctx* ctx, int metric, const bbmcu_spherical_grid* grid, int component, int unit,
                           const bbmcu_bsdf* reference_bsdf, const float* const* reference_merl_rgb, int n_materials,
                           uint64_t first, uint64_t count, unsigned flags, bbmcu_loss** out);

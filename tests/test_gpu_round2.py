@@ -255,3 +255,33 @@ def test_gpu_gradient_vs_finite_differences_of_double_reference(ctx, ref, refd, 
         check_gradient_case(ref, refd, metric, fitted, truth, float(loss[0]), grad[0])
         done += 1
     assert done == len(GRAD_FAMILIES)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("materialise", [False, True])
+def test_interleaved_loss_shards_sum_to_the_whole(ctx, materialise):
+    """BBMCU_LOSS_SHARD_INTERLEAVED: blocks of 1024 samples dealt round-robin to the shards.  The shards' sums add up to the
+    unsharded loss and gradient, their per-sample terms are the unsharded terms at bbm_b200.shard.interleaved_indices, and
+    the fused and materialised modes agree bit for bit."""
+    import bbm_b200 as bb
+    from bbm_b200.shard import interleaved_indices
+    truth = bb.Bsdf("Aggregate(Lambertian([0.2, 0.1, 0.05]), CookTorrance([0.3, 0.3, 0.3], 0.2, 1.5))")
+    fitted = bb.Bsdf("Aggregate(Lambertian(), CookTorrance())")
+    rng = np.random.default_rng(3)
+    params = fitted.parameter_values()[None] * (1 + 0.1 * rng.random((5, 8)))
+    whole = ctx.loss("nganL2", truth, None, materialise=materialise)
+    lw, gw = whole(fitted, params, grad=True)
+    tw = whole.terms(fitted)
+    for world in (3, 8):
+        ls, gs, total = 0.0, 0.0, 0
+        for r in range(world):
+            L = ctx.loss("nganL2", truth, None, materialise=materialise, interleaved=(r, world))
+            idx = interleaved_indices(bb.MERL_BINS, r, world)
+            assert L.shard_count() == len(idx)
+            l, g = L(fitted, params, grad=True)
+            ls, gs, total = ls + l, gs + g, total + len(idx)
+            assert np.array_equal(L.terms(fitted).view(np.uint32), tw[idx].view(np.uint32))
+        assert total == bb.MERL_BINS
+        assert np.allclose(ls, lw, rtol=1e-13, atol=0) and np.allclose(gs, gw, rtol=1e-11, atol=1e-14)
+    with pytest.raises(bb.BbmError):
+        ctx.loss("nganL2", truth, None, interleaved=(3, 3))

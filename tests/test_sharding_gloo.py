@@ -68,3 +68,19 @@ def test_shard_ranges_cover_exactly():
     parts = partition_by_cost([5, 1, 1, 1, 4, 4], 2)
     assert sorted(sum(parts, [])) == list(range(6))
     assert abs(sum([5, 1, 1, 1, 4, 4][j] for j in parts[0]) - 8) <= 1
+
+
+def test_interleaved_shards_cover_exactly_and_are_balanced():
+    """the index map of BBMCU_LOSS_SHARD_INTERLEAVED (bbm_b200.shard.interleaved_indices mirrors bbmcu_loss.cu): shards are
+    disjoint, cover [0, n), keep blocks of 1024 consecutive samples, and differ in size by at most one block"""
+    from bbm_b200.shard import interleaved_indices
+    for n in (1, 1023, 1024, 1025, 5000, 1458000):
+        for world in (1, 2, 3, 8):
+            parts = [interleaved_indices(n, r, world) for r in range(world)]
+            allidx = np.concatenate(parts)
+            assert len(allidx) == n and np.array_equal(np.sort(allidx), np.arange(n))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1024
+            for r, p in enumerate(parts):
+                if len(p):
+                    assert p[0] == r * 1024 and np.all(np.diff(p)[np.arange(len(p) - 1) % 1024 != 1023] == 1)

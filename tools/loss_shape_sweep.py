@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def worker(K):
+def worker(K, interleaved=False):
     import numpy as np
     import torch
     import bbm_b200 as bb
@@ -32,7 +32,9 @@ def worker(K):
         res = torch.zeros((k, 1 + P), device=dev, dtype=torch.float64)
         for div in (1, 2, 4, 8):
             count = (bb.MERL_BINS + div - 1) // div
-            L = ctx.loss("nganL2", truth, None, first=0, count=count)
+            # contiguous: the first 1/div of the grid (the most expensive contiguous shard: no pair below the horizon);
+            # interleaved: blocks 0, div, 2 div, ... of 1024 samples (BBMCU_LOSS_SHARD_INTERLEAVED: what bench.py uses)
+            L = ctx.loss("nganL2", truth, None, interleaved=(0, div)) if interleaved else ctx.loss("nganL2", truth, None, first=0, count=count)
             for _ in range(3):
                 L.eval_device(fitted, params, res)
             ctx.synchronize()
@@ -54,14 +56,15 @@ def main():
     ap.add_argument("--K", default="16,256")
     ap.add_argument("--out", default=None)
     ap.add_argument("--worker", action="store_true")
+    ap.add_argument("--interleaved", action="store_true", help="shards dealt in blocks of 1024 samples instead of contiguous ranges")
     a = ap.parse_args()
     K = [int(x) for x in a.K.split(",")]
     if a.worker:
-        return worker(K)
+        return worker(K, a.interleaved)
     table = {}
     for f in a.fills.split(","):
         env = dict(os.environ, BBMCU_LOSS_BLOCKS_PER_SM=f)
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", "--K", a.K], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", "--K", a.K] + (["--interleaved"] if a.interleaved else []), env=env, capture_output=True, text=True)
         if r.returncode != 0:
             print(r.stderr[-2000:])
             sys.exit(1)
