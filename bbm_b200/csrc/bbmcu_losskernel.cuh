@@ -290,7 +290,8 @@ template<class LossT> static void launch_loss_static(cudaStream_t s, const LossA
   // block walking over several tiles (K = 1 passes and many-material launches: the table / attribute staging is then paid
   // once per block)
   const size_t slots = (size_t)a.sm_count * (size_t)per_sm[wg];
-  const size_t target = slots * (kpb >= 8 ? 8 : 2), other = (size_t)ksplit * a.n_materials;
+  static const int small_rounds = [] { const char* e = std::getenv("BBMCU_LOSS_SMALLK_ROUNDS"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 2; }();   // tuning
+  const size_t target = slots * (kpb >= 8 ? 8 : (size_t)small_rounds), other = (size_t)ksplit * a.n_materials;
   unsigned gx = tiles;
   if((size_t)tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
   if(gx > tiles) gx = tiles;

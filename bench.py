@@ -591,6 +591,22 @@ def main():
             epd_info["cpu_reference"] = {"eval_G_evals_per_s_all_threads": (1 << 18) / te / 1e9, "cores": cores, "fit_steps_per_s_one_thread": len(trace) / tf,
                                          "fit_steps_timed": int(len(trace)), "how": "oracle/_ref: bsdf_ptr eval on 2^18 grid directions; unmodified bbm::compass, 10 steps"}
 
+    # ---- checkBsdf's sample loops and the HP renormalisation table as device kernels (rank 0's GPU) -----------------
+    tools_info = None
+    if not args.no_extras and rank == 0:
+        from bbm_b200 import check as bcheck
+        ggx = bb.Bsdf("GGX()")
+        ns = 1 << 26
+        bcheck.pdf_integral(ctx, ggx, 1 << 20, 1, False, "philox", 1)                      # warm-up
+        t0 = time.perf_counter(); val, _ = bcheck.pdf_integral(ctx, ggx, ns, 4, False, "philox", 2); t_int = time.perf_counter() - t0
+        t0 = time.perf_counter(); rp = bcheck.pdf(ctx, ggx, ns, False, True, "philox", 3); t_pdf = time.perf_counter() - t0
+        t0 = time.perf_counter(); tab = ctx.hp_precompute_normalization(); t_hp = time.perf_counter() - t0
+        tools_info = {"checkBsdf": {"bsdf": "GGX()", "rng": "philox (drawn in the kernel, 0 bytes in)", "samples_per_estimate": ns,
+                                    "pdfInt_4_trials_s": t_int, "pdfInt_G_samples_per_s": 4 * ns / t_int / 1e9, "pdfInt_values": [float(v) for v in val],
+                                    "pdf_test_s": t_pdf, "pdf_test_G_samples_per_s": ns / t_pdf / 1e9, "pdf_test_negative": list(rp["negative"]), "pdf_test_mismatch": [float(v) for v in rp["mismatch"]]},
+                      "hp_normalization": {"entries": int(tab.size), "seconds": t_hp, "quadrature_terms": 5.67e9}}
+        del tab
+
     # ---- configs[4]: many materials per launch, and the fit sweep ---------------------------------------------------------------------------
     multi_info, sweep_info = None, None
     if not args.no_extras and not args.no_loss:
@@ -669,7 +685,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(n), "peak_source": peak_src,
                              "kernel": "k_foreach4<SampleEvalPdfOpT<BsdfSingle<GGX>, false>>", "algorithmic_bytes_per_launch": BYTES_PER_PAIR * n},
                 "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches, "clocks": clk, "loss_grad": loss_info, "eval_merl_grid": eval_info,
-                "epd": epd_info, "loss_multi": multi_info, "sweep": sweep_info}
+                "epd": epd_info, "loss_multi": multi_info, "sweep": sweep_info, "tools": tools_info}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

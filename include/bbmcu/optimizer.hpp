@@ -90,10 +90,26 @@ public:
     if(is_converged()) return 0.0f;
     const size_t P = _param.size();
     _probes.assign(2 * P * P, 0.0);
+    // the reference tests ALL parameters of a probe against the box (compass.h:117-121), not only the one it moved: a
+    // start point outside the box in another coordinate rejects every probe
+    bool base_inside = true;
+    for(size_t i = 0; i < P; ++i)
+    {
+      const float v = (float)_param[i];
+      if(!_lower.empty() && !(v >= (float)_lower[i])) base_inside = false;
+      if(!_upper.empty() && !(v <= (float)_upper[i])) base_inside = false;
+    }
     std::vector<char> ok(2 * P, 1);
     for(size_t k = 0; k < 2 * P; ++k)
     {
       const size_t j = k / 2;
+      if(!base_inside)
+      {
+        // with the other coordinates outside, only a probe whose own coordinate is the single offender can be inside
+        bool others = true;
+        for(size_t i = 0; i < P; ++i) if(i != j) { const float v = (float)_param[i]; if((!_lower.empty() && !(v >= (float)_lower[i])) || (!_upper.empty() && !(v <= (float)_upper[i]))) others = false; }
+        if(!others) ok[k] = 0;
+      }
       std::copy(_param.begin(), _param.end(), _probes.begin() + k * P);
       float v = (float)_param[j] + ((k & 1) ? -_step : _step);
       _probes[k * P + j] = (double)v;

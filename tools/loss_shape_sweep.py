@@ -56,6 +56,7 @@ def main():
     ap.add_argument("--K", default="16,256")
     ap.add_argument("--out", default=None)
     ap.add_argument("--worker", action="store_true")
+    ap.add_argument("--small-rounds", action="store_true", help="sweep BBMCU_LOSS_SMALLK_ROUNDS (rounds of resident blocks for launches with < 8 sets per block) with --fills values")
     ap.add_argument("--interleaved", action="store_true", help="shards dealt in blocks of 1024 samples instead of contiguous ranges")
     a = ap.parse_args()
     K = [int(x) for x in a.K.split(",")]
@@ -64,6 +65,8 @@ def main():
     table = {}
     for f in a.fills.split(","):
         env = dict(os.environ, BBMCU_LOSS_BLOCKS_PER_SM=f)
+        if a.small_rounds:
+            env = dict(os.environ, BBMCU_LOSS_SMALLK_ROUNDS=f)      # --small-rounds: the swept value is the small-K round count instead
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--worker", "--K", a.K] + (["--interleaved"] if a.interleaved else []), env=env, capture_output=True, text=True)
         if r.returncode != 0:
             print(r.stderr[-2000:])
