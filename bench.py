@@ -396,6 +396,7 @@ def main():
     if not args.no_loss:
         # the sample axis is dealt to the ranks in blocks of 1024 samples (rank, rank + world, ...): contiguous eighths of
         # the MERL grid are unequal work (the first has no pair below the horizon), interleaved shards are equal
+        N = bb.MERL_BINS
         shard = dict(interleaved=(rank, world))
         fitted, truth = bb.Bsdf(FITTED), bb.Bsdf(TRUTH)
         L = ctx.loss("nganL2", truth, None, **shard)
