@@ -130,6 +130,9 @@ class ClockSampler:
 
     def __enter__(self):
         self.t.start()
+        t0 = time.perf_counter()                    # the first NVML query of a process can take longer than the region it is meant
+        while not self.sm and time.perf_counter() - t0 < 3.0:   # to sample: let it complete before the region starts
+            time.sleep(0.001)
         return self
 
     def __exit__(self, *a):
