@@ -98,7 +98,16 @@ const float* merl_device_table(const bbmcu_host::MerlData& m, int device)
 
 namespace {
 
-struct ArrayArg { const void* ptr; int planes; bool input; };    // 4-byte elements, SoA planes; an OUTPUT pointer may be null (not wanted)
+// 4-byte elements, SoA planes; an OUTPUT pointer may be null (not wanted).  How a host output travels back over PCIe:
+//   XFER_PLAIN    as it is (4 bytes per element)
+//   XFER_BYTES    one-plane int32 output with values in [0, 255] (bsdf_flag): narrowed to one byte per element on the device,
+//                 copied into the pinned ring and widened into the caller's array by host threads (1 byte over the link, not 4)
+//   XFER_COPY_OF / XFER_MASKED_BY  not transferred at all: equal to another output of the same call (`src`), or to it where a
+//                 third output (`mask`: the flag) is non-zero and 0 elsewhere - the host threads write it from those
+// (the fused pass returns sample.pdf next to pdf(sample.direction, out), which most models define as the same number:
+// 36 -> 29 bytes per pair down the link, the side the pass is bound by)
+enum : int { XFER_PLAIN = 0, XFER_BYTES, XFER_COPY_OF, XFER_MASKED_BY };
+struct ArrayArg { const void* ptr; int planes; bool input; int xfer = XFER_PLAIN; int src = -1; int mask = -1; };
 
 enum class Mem { Device, Pinned, Pageable };
 Mem classify(const void* p)
@@ -143,6 +152,25 @@ void host_copy_rows(char* dst, size_t dst_pitch, const char* src, size_t src_pit
   for(auto& th : pool) th.join();
 }
 
+__global__ void k_narrow_to_bytes(const int32_t* __restrict__ in, unsigned char* __restrict__ out, size_t n)
+{
+  for(size_t i = ((size_t)blockIdx.x*blockDim.x + threadIdx.x)*4; i < n; i += (size_t)gridDim.x*blockDim.x*4)
+  {
+    if(i + 4 <= n) { const int4 v = *reinterpret_cast<const int4*>(in + i); *reinterpret_cast<uchar4*>(out + i) = make_uchar4((unsigned char)v.x, (unsigned char)v.y, (unsigned char)v.z, (unsigned char)v.w); }
+    else for(size_t k = i; k < n; ++k) out[k] = (unsigned char)in[k];
+  }
+}
+
+// f(begin, end) over [0, n) on `threads` host threads
+template<class F> void host_parallel(size_t n, int threads, F&& f)
+{
+  if(n < (size_t(1) << 18) || threads <= 1) { f((size_t)0, n); return; }
+  std::vector<std::thread> pool;
+  const size_t per = ((n + threads - 1) / threads + 63) & ~size_t(63);
+  for(int t=0; t < threads; ++t) { const size_t b = (size_t)t*per; if(b >= n) break; const size_t e = std::min(n, b + per); pool.emplace_back([=] { f(b, e); }); }
+  for(auto& th : pool) th.join();
+}
+
 // Host-pointer path: chunks of the batch flow through kSlots device staging buffers, each chunk's H2D copies, kernel and
 // D2H copies on its own stream so copies of one chunk overlap the kernel and the copies of its neighbours.  Pinned /
 // registered caller memory is DMA'd in place; PAGEABLE caller memory goes through a pinned staging ring filled and
@@ -158,14 +186,15 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
   const size_t user_ld = ctx->user_ld ? ctx->user_ld : n;      // the caller's plane stride
   if(user_ld < n) throw std::invalid_argument("BBM: plane stride smaller than the batch");
   size_t need = 0;
-  bool any_pageable = false;
+  bool any_pageable = false;                                    // per-chunk host work: pageable memory, narrowed or derived outputs
   std::vector<size_t> off(args.size());
   for(size_t a=0; a < args.size(); ++a)
   {
     off[a] = need;
     if(!args[a].ptr) continue;
     need += ((size_t)args[a].planes * ld * 4 + 255) & ~size_t(255);
-    any_pageable |= (kind[a] == Mem::Pageable);
+    if(args[a].xfer == XFER_BYTES) need += (ld + 255) & ~size_t(255);             // the narrowed copy behind the int32 plane
+    any_pageable |= (kind[a] == Mem::Pageable) || (args[a].xfer != XFER_PLAIN);
   }
   if(need > ctx->slot_bytes)
   {
@@ -189,9 +218,31 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
     if(!pending[s].busy) return;
     BBMCU_CUDA(cudaStreamSynchronize(ctx->slot_stream[s]));
     pending[s].busy = false;
+    const size_t c0 = pending[s].c0, cn = pending[s].cn;
     for(size_t a=0; a < args.size(); ++a)
-      if(args[a].ptr && !args[a].input && kind[a] == Mem::Pageable)
-        host_copy_rows((char*)args[a].ptr + pending[s].c0*4, user_ld*4, (const char*)ctx->pin_buf[s] + off[a], ld*4, pending[s].cn*4, args[a].planes, threads);
+      if(args[a].ptr && !args[a].input && args[a].xfer == XFER_PLAIN && kind[a] == Mem::Pageable)
+        host_copy_rows((char*)args[a].ptr + c0*4, user_ld*4, (const char*)ctx->pin_buf[s] + off[a], ld*4, cn*4, args[a].planes, threads);
+    // narrowed outputs: bytes in the ring -> the caller's int32 plane
+    for(size_t a=0; a < args.size(); ++a)
+      if(args[a].ptr && args[a].xfer == XFER_BYTES)
+      {
+        const unsigned char* src = (const unsigned char*)ctx->pin_buf[s] + off[a];
+        int32_t* dst = (int32_t*)args[a].ptr + c0;
+        host_parallel(cn, threads, [=](size_t b, size_t e) { for(size_t i = b; i < e; ++i) dst[i] = (int32_t)src[i]; });
+      }
+    // derived outputs, from what has just arrived of their sources (the caller's own plane, or the ring if that is pageable and not yet copied... it is: see above)
+    for(size_t a=0; a < args.size(); ++a)
+      if(args[a].ptr && (args[a].xfer == XFER_COPY_OF || args[a].xfer == XFER_MASKED_BY))
+      {
+        const float* src = (const float*)args[args[a].src].ptr + c0;
+        float* dst = (float*)args[a].ptr + c0;
+        if(args[a].xfer == XFER_COPY_OF) host_parallel(cn, threads, [=](size_t b, size_t e) { std::memcpy(dst + b, src + b, (e - b)*sizeof(float)); });
+        else
+        {
+          const unsigned char* m = (const unsigned char*)ctx->pin_buf[s] + off[args[a].mask];     // the flag bytes of this chunk
+          host_parallel(cn, threads, [=](size_t b, size_t e) { for(size_t i = b; i < e; ++i) dst[i] = m[i] ? src[i] : 0.0f; });
+        }
+      }
   };
   const size_t saved_ld = ctx->ld;
   ctx->ld = ld;
@@ -218,10 +269,21 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
         }
         else BBMCU_CUDA(cudaMemcpy2DAsync(dptr[a], ld*4, src, user_ld*4, cn*4, args[a].planes, cudaMemcpyHostToDevice, st));
       }
+      // a derived output is still computed by the kernel when its staging pointer is given; it is not: null = not stored
+      for(size_t a=0; a < args.size(); ++a) if(args[a].ptr && (args[a].xfer == XFER_COPY_OF || args[a].xfer == XFER_MASKED_BY)) dptr[a] = nullptr;
       launch(st, dptr, cn);
       for(size_t a=0; a < args.size(); ++a)
       {
         if(!args[a].ptr || args[a].input) continue;
+        if(args[a].xfer == XFER_COPY_OF || args[a].xfer == XFER_MASKED_BY) continue;
+        if(args[a].xfer == XFER_BYTES)
+        {
+          unsigned char* bytes = (unsigned char*)dptr[a] + (((size_t)args[a].planes * ld * 4 + 255) & ~size_t(255));      // behind the int32 plane
+          k_narrow_to_bytes<<<(unsigned)std::min<size_t>(1184, (cn/4 + 255)/256 + 1), 256, 0, st>>>((const int32_t*)dptr[a], bytes, cn);
+          BBMCU_CUDA(cudaGetLastError());
+          BBMCU_CUDA(cudaMemcpyAsync((char*)ctx->pin_buf[s] + off[a], bytes, cn, cudaMemcpyDeviceToHost, st));
+          continue;
+        }
         if(kind[a] == Mem::Pageable) BBMCU_CUDA(cudaMemcpy2DAsync((char*)ctx->pin_buf[s] + off[a], ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
         else BBMCU_CUDA(cudaMemcpy2DAsync((char*)args[a].ptr + c0*4, user_ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
       }
@@ -256,6 +318,36 @@ void run_any(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, Launch
     ctx->ld = saved_ld;
   }
   else run_hosted(ctx, n, args, kind, launch);
+}
+
+// What the fused pass returns twice: sample.pdf against pdf(sample.direction, out).
+//   an aggregate:                         sample.pdf IS that pdf (aggregatebsdf.h:119-126 and :183; SampleEvalPdfOpT copies it)
+//   the hand-merged GGX kernel:           the same number (0 when the sample is invalid)
+//   models with kSamplePdfIsPdf:          pdf where the sample's flag is not None, else 0
+// For those the host-pointer path does not send sample.pdf over the link: host threads write it from pdf (and the flag).
+// The flag itself travels as one byte per element.  BBMCU_HOST_TRANSFER_PLAIN=1 (tests) sends every plane as it is.
+enum : int { SPDF_INDEPENDENT = 0, SPDF_IS_PDF, SPDF_IS_PDF_WHERE_FLAGGED };
+int sample_pdf_rule(const BsdfDesc& d)
+{
+  if(d.aggregate) return SPDF_IS_PDF;
+  if(d.n_lobes != 1) return SPDF_INDEPENDENT;
+  int rule = SPDF_INDEPENDENT;
+  dispatch_model_host(d.model[0], [&](auto* m) {
+    using M = typename std::remove_pointer<decltype(m)>::type;
+    if(HandFused<M>::value) rule = SPDF_IS_PDF;
+    else if(SamplePdfIsPdf<M>::value) rule = SPDF_IS_PDF_WHERE_FLAGGED;
+  });
+  return rule;
+}
+void compress_fused_outputs(const BsdfDesc& d, std::vector<ArrayArg>& args, int i_spdf, int i_flag, int i_pdf)
+{
+  static const bool plain = [] { const char* e = std::getenv("BBMCU_HOST_TRANSFER_PLAIN"); return e && e[0] == '1'; }();
+  if(plain) return;
+  if(args[i_flag].ptr) args[i_flag].xfer = XFER_BYTES;
+  if(!args[i_spdf].ptr || !args[i_pdf].ptr) return;
+  const int rule = sample_pdf_rule(d);
+  if(rule == SPDF_IS_PDF) { args[i_spdf].xfer = XFER_COPY_OF; args[i_spdf].src = i_pdf; }
+  else if(rule == SPDF_IS_PDF_WHERE_FLAGGED && args[i_flag].ptr) { args[i_spdf].xfer = XFER_MASKED_BY; args[i_spdf].src = i_pdf; args[i_spdf].mask = i_flag; }
 }
 
 void check_flags(int component, int unit)
@@ -457,8 +549,9 @@ int bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component,
     if(!ctx) throw std::invalid_argument("BBM: null context");
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     BsdfDesc d = make_desc(bsdf->b, ctx->device);
-    run_any(ctx, n, {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}},
-            [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+    std::vector<ArrayArg> args = {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}};
+    compress_fused_outputs(d, args, 3, 4, 6);
+    run_any(ctx, n, args, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       launch_sample_eval_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn); });
   });
 }
@@ -474,8 +567,9 @@ int bbmcu_sample_eval_pdf_generated(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int 
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     BsdfDesc d = make_desc(bsdf->b, ctx->device);
     size_t done = 0;                                     // chunks arrive in order: the running element offset
-    run_any(ctx, n, {{gen_out, 3, false}, {gen_xi, 2, false}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}},
-            [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+    std::vector<ArrayArg> args = {{gen_out, 3, false}, {gen_xi, 2, false}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}};
+    compress_fused_outputs(d, args, 3, 4, 6);
+    run_any(ctx, n, args, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
       GenArgs g; g.gen = 1; g.seed = seed; g.first = first + done; g.out = (float*)p[0]; g.xi = (float*)p[1];
       launch_sample_eval_pdf(ctx, s, d, component, nullptr, nullptr, (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn, g);
       done += cn; });

@@ -285,3 +285,37 @@ def test_interleaved_loss_shards_sum_to_the_whole(ctx, materialise):
         assert np.allclose(ls, lw, rtol=1e-13, atol=0) and np.allclose(gs, gw, rtol=1e-11, atol=1e-14)
     with pytest.raises(bb.BbmError):
         ctx.loss("nganL2", truth, None, interleaved=(3, 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("s", ["GGX()", "Phong()", "CookTorrance()", "Lambertian()", "Aggregate(Lambertian(), GGX())", "Aggregate(Lambertian(), Phong(), GGX())", "He()"])
+def test_host_path_with_narrowed_and_derived_outputs_equals_device_path(ctx, s):
+    """host pointers: the flag plane travels as one byte per element and - for models whose sample.pdf is pdf(sample.direction,
+    out) - sample.pdf does not travel at all (host threads write both planes).  Every output equals the device-pointer
+    call's, bit for bit, for pinned and for pageable caller memory, also when some outputs are not asked for."""
+    import torch
+    import bbm_b200 as bb
+    n = (1 << 22) + 4097                                     # three chunks, the last one ragged and not a multiple of 4
+    rng = np.random.default_rng(11)
+    z = rng.random(n, dtype=np.float32); ph = rng.random(n, dtype=np.float32) * np.float32(2 * np.pi)
+    out = np.stack([np.sqrt(1 - z * z) * np.cos(ph), np.sqrt(1 - z * z) * np.sin(ph), z]).astype(np.float32)
+    xi = rng.random((2, n), dtype=np.float32)
+    xi[0, :5] = [-0.5, 1.5, 0.0, 1.0, 0.5]                   # invalid random numbers: flag None, sample.pdf 0
+    b = bb.Bsdf(s)
+    dev = torch.device("cuda", 0)
+    res = ctx.sample_eval_pdf(b, torch.from_numpy(out).to(dev), torch.from_numpy(xi).to(dev))
+    ctx.synchronize()                                        # the library's own stream: finish before torch reads the tensors
+    want = [t.cpu().numpy() for t in res]
+    got = ctx.sample_eval_pdf(b, out, xi)                    # pageable numpy memory
+    for name, g, w in zip(("dir", "sample_pdf", "flag", "rgb", "pdf"), got, want):
+        assert np.array_equal(g.view(np.uint32), w.view(np.uint32)), (s, name, "pageable")
+    pin = lambda a: torch.from_numpy(a).pin_memory()        # noqa: E731
+    outs = (torch.empty((3, n)).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty((3, n)).pin_memory(), torch.empty(n).pin_memory())
+    ctx.sample_eval_pdf(b, pin(out), pin(xi), outputs=outs)
+    for name, g, w in zip(("dir", "sample_pdf", "flag", "rgb", "pdf"), outs, want):
+        assert np.array_equal(g.numpy().view(np.uint32), w.view(np.uint32)), (s, name, "pinned")
+    # sample.pdf without pdf (nothing to derive it from) and without the flag
+    d2, sp2, f2, rgb2, p2 = ctx.sample_eval_pdf(b, out, xi, want=("sample_pdf",))
+    assert np.array_equal(sp2.view(np.uint32), want[1].view(np.uint32)) and d2 is None and p2 is None
+    d3, sp3, f3, rgb3, p3 = ctx.sample_eval_pdf(b, out, xi, want=("sample_pdf", "pdf"))
+    assert np.array_equal(sp3.view(np.uint32), want[1].view(np.uint32)) and np.array_equal(p3.view(np.uint32), want[4].view(np.uint32))
