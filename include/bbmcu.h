@@ -21,7 +21,11 @@
  *    bbmcu_host_register) is DMA'd in place; pageable memory goes through an internal pinned ring
  *    filled and drained by a few host threads.  The caller owns every buffer.
  *  - OUTPUT pointers of the batched calls may be NULL where documented: that plane is neither
- *    stored by the kernel nor copied back.
+ *    stored by the kernel nor copied back.  Host outputs of the fused pass that are cheap functions of
+ *    others do not cross PCIe as they are: the flag plane travels as one byte per element, and
+ *    sample_pdf - where the model defines it as pdf(sample.direction, out) - is written on the host
+ *    from the pdf plane.  The caller's buffers receive the same bits either way
+ *    (BBMCU_HOST_TRANSFER_PLAIN=1 in the environment sends every plane as it is).
  *  - planes of one argument are n floats apart unless bbmcu_set_plane_stride says otherwise.
  *  - there is no CPU fallback: without a usable CUDA device bbmcu_init fails.
  *  - one context per host thread per device; calls on one context are serialised on its stream.
