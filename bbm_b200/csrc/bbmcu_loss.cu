@@ -8,6 +8,7 @@
 
 #include "bbmcu_launch.cuh"
 #include "bbmcu_losskernel.cuh"
+#include "bbmcu_losscompact.cuh"
 
 using namespace bbmcu;
 
@@ -477,7 +478,11 @@ int bbmcu_loss_eval_multi_ex(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double
       else if(shape.n_lobes == 2 && shape.aggregate && m0 == M_Lambertian)
       {
         const int m1 = shape.model[1];
-        done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)Kper) ||
+        // the compact kernel (bbmcu_losscompact.cuh) where the specular lobe has one and both components are asked for
+        const char* nc = std::getenv("BBMCU_LOSS_NO_COMPACT");     // read per call: tests compare the two kernels in one process
+        const bool no_compact = nc && *nc && *nc != '0';
+        if(!no_compact && a.component == FLAG_ALL) done = launch_loss_pair_compact(m1, ctx->stream, a, (unsigned)Kper);
+        if(!done) done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)Kper) ||
                launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)Kper);
       }
       if(!done) bind_device_tables();

@@ -1,0 +1,326 @@
+// Compact batched loss(+gradient) pass for Aggregate(Lambertian, microfacet lobe) - the shape of BASELINE configs[2]
+// ("Ngan-style fit of Cook-Torrance") and of the Cook-Torrance entries of the reference's fits/*.fit.
+//
+// The generic tile kernel (bbmcu_losskernel.cuh) pushes dual numbers through the model templates once per (sample,
+// parameter set): 186 instructions per sample and set for the Cook-Torrance aggregate, of which the model's mathematics
+// is about a third.  Here the work is split by what it depends on (include/bsdfmodel/cooktorrance.h:29-34,
+// include/ndf/beckmann.h:60-75, include/maskingshadowing/vgroove.h:41-46, include/bbm/fresnel_cook.h:47-55,
+// include/loss/cosine_weighted_l2.h:25-34, cosine_weighted_log.h:32-43):
+//   * per SAMPLE, once per tile (directions only): the Beckmann exponent's numerator T = tan^2(theta_h), the V-groove term
+//     with every parameter-free factor folded in (G / (N z_i z_o cos^4 theta_h)), the Fresnel cosine, the metric's weights
+//     and the measured value already multiplied by the cosine (or its logarithm): 9 floats - so a thread keeps 8
+//     samples in registers instead of 4 and the warp reduction is paid half as often per sample;
+//   * per PARAMETER SET, once per block (parameters only): 1/alpha^2, the normalisation of D, the coefficients of
+//     d log D / d alpha, eta^2 - 1, albedo / pi - computed by one thread per set while the block stages its sets in shared
+//     memory;
+//   * per (sample, set): one exp2, the Fresnel term with its closed-form derivative, three channel errors, nine
+//     accumulations.
+// Factors common to a whole gradient column (2, 1/pi) are applied once per block partial.
+// Samples below the horizon (neither lobe contributes: the term does not depend on the parameters) are summed once per
+// tile into a constant instead of being evaluated per set.
+// Results agree with the generic kernel to float rounding (tests/test_loss_compact_hostsim.py on the host,
+// tests/test_gpu_round2.py::test_compact_loss_equals_generic_tile_kernel on the device); BBMCU_LOSS_NO_COMPACT=1 keeps
+// the generic kernel.
+#pragma once
+#include "bbmcu_lossop.cuh"
+#ifdef __CUDACC__
+#include "bbmcu_losskernel.cuh"
+#endif
+
+namespace bbmcu {
+
+BBMCU_D float c_ex2(float x)
+{
+#ifdef __CUDA_ARCH__
+  float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return exp2f(x);
+#endif
+}
+
+// ---- Fresnel policies: NS floats per parameter set, one float per sample, value + derivative -------------------------
+// fresnel::cook (fresnel_cook.h:47-55): g = sqrt(eta^2 + c^2 - 1), p = (g - c)/(g + c), q = (c(g + c) - 1)/(c(g - c) + 1),
+// F = p^2 (1 + q^2) / 2;  dp/dg = 2c/(g + c)^2, dq/dg = 2c(1 - c^2)/(c(g - c) + 1)^2, dg/deta = eta/g
+struct CFCook
+{
+  static constexpr int NS = 2, NP = 1;
+  BBMCU_D static void set(const float* a, float* d) { d[0] = a[0]*a[0] - 1.0f; d[1] = a[0]; }
+  BBMCU_D static float inv(float c) { return c; }
+  template<bool WG> BBMCU_D static void eval(const float* d, float c, float& Fv, float (&dF)[NP])
+  {
+    const float g2r = fmaf(c, c, d[0]);
+    const float g2 = fmaxf(g2r, 1e-30f);                       // total internal reflection (eta < 1): g = 0, F = 1
+    const float rs = q_rsqrt(g2), g = g2*rs;
+    const float A = g - c, B = g + c;
+    const float n2 = fmaf(c, B, -1.0f), d2 = fmaf(c, A, 1.0f);
+    const float R = q_rcp(B*d2);
+    const float iB = d2*R, id2 = B*R;
+    const float p = A*iB, q = n2*id2;
+    const float t = fmaf(q, q, 1.0f);
+    const float pt = p*t;
+    const float Fraw = 0.5f*p*pt;
+    Fv = fmaxf(Fraw, 0.0f);
+    if(WG)
+    {
+      const float c2 = c + c;
+      const float dp = c2*(iB*iB), dq = (c2*fmaf(-c, c, 1.0f))*(id2*id2);
+      const float dFdg = fmaf(pt, dp, (p*p)*(q*dq));
+      const float ers = (g2r > 0.0f) ? d[1]*rs : 0.0f;
+      dF[0] = dFdg*ers;
+    }
+  }
+};
+// fresnel::schlick of a reflectance at normal incidence (fresnel_schlick.h:48-51): R0 + (1 - R0) (1 - c)^5
+struct CFSchlick
+{
+  static constexpr int NS = 1, NP = 1;
+  BBMCU_D static void set(const float* a, float* d) { d[0] = a[0]; }
+  BBMCU_D static float inv(float c) { return (float)schlick_w(c); }
+  template<bool WG> BBMCU_D static void eval(const float* d, float w, float& Fv, float (&dF)[NP])
+  {
+    Fv = fmaf(-d[0], w, d[0]) + w;
+    if(WG) dF[0] = 1.0f - w;
+  }
+};
+
+// ---- D G policies: NS floats per set, NI floats per sample ------------------------------------------------------------
+// isotropic Beckmann (beckmann.h:60-75) times the V-groove term (vgroove.h:41-46), which has no parameter:
+//   D G / (N z_i z_o) = exp(-T / alpha^2) / (alpha^2 [pi]) * [G / (N z_i z_o cos^4 theta_h)],   T = tan^2 theta_h
+//   d log D / d alpha = 2 T / alpha^3 - 2 / alpha
+template<bool NORMALIZE> struct CDGBeckmannVGroove
+{
+  static constexpr int NS = 4, NP = 1, NI = 2;
+  BBMCU_D static void set(const float* a, float* d)
+  {
+    const float al = a[0], ia2 = 1.0f/(al*al);
+    d[0] = -1.44269504088896340736f*ia2; d[1] = NORMALIZE ? kInvPi*ia2 : ia2; d[2] = -2.0f/al; d[3] = 2.0f*ia2/al;
+  }
+  // caller guarantees in.z > 0, out.z > 0, inh > 0, outh > 0;  k = 1 / (N z_i z_o)
+  BBMCU_D static void inv(f3 in, f3 out, f3 h, float inh, float outh, float k, float* I)
+  {
+    const float c2 = h.z*h.z;
+    I[0] = (h.x*h.x + h.y*h.y)/c2;
+    const float gi = q_div(2.0f*h.z*in.z, inh), go = q_div(2.0f*h.z*out.z, outh);
+    const float G = fminf(1.0f, fminf(gi, go));
+    I[1] = fminf(G*k/(c2*c2), 3.0e38f);
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& DG, float (&dDG)[NP])
+  {
+    DG = (c_ex2(I[0]*d[0])*I[1])*d[1];
+    if(WG) dDG[0] = DG*fmaf(I[0], d[3], d[2]);
+  }
+};
+
+// ---- Aggregate(Lambertian, M), M = Microfacet<NDF, G, F, NORM, true> described by the two policies ------------------
+// fit parameters in attribute order: albedo rgb, scale rgb, NDF parameters, Fresnel parameters
+template<class M, class DG, class CF> struct CompactPair
+{
+  using Model = M;
+  static constexpr int NRAW = 3 + M::NA;                       // attribute floats of a parameter set
+  static constexpr int P = 6 + DG::NP + CF::NP, C = 1 + P;
+  static constexpr int OFF_DG = 6, OFF_F = 6 + DG::NS, NSET = (6 + DG::NS + CF::NS + 3) & ~3;
+  static_assert(NRAW == 6 + DG::NP + CF::NP && M::SCALE == 0, "every attribute is a fit parameter; leading scale");
+  struct Sample { float I[DG::NI]; float fc, cm, w, wc, r[3]; };
+
+  BBMCU_D static void set(const float* raw, float* d)
+  {
+#pragma unroll
+    for(int i=0; i < NSET; ++i) d[i] = 0.0f;
+    d[0] = raw[0]*kInvPi; d[1] = raw[1]*kInvPi; d[2] = raw[2]*kInvPi;
+    d[3] = raw[3]; d[4] = raw[4]; d[5] = raw[5];
+    DG::set(raw + 3 + M::OFF_NDF, d + OFF_DG);
+    CF::set(raw + 3 + M::OFF_F, d + OFF_F);
+  }
+  // factor of column j of the block partial: the per-sample sums leave out 2 (d e / d v) and 1/pi (d v / d albedo)
+  BBMCU_HD static double col_scale(int j) { return j == 0 ? 1.0 : (j <= 3 ? 2.0/kPiD : 2.0); }
+
+  template<bool LOG> BBMCU_D static Sample make_sample(int metric, f3 in, f3 out, const Spec<float>& ref, bool live, float& e_const)
+  {
+    Sample s;
+#pragma unroll
+    for(int i=0; i < DG::NI; ++i) s.I[i] = 0.0f;
+    s.fc = CF::inv(0.5f); s.cm = 0.0f; s.w = 0.0f; s.wc = 0.0f; s.r[0] = s.r[1] = s.r[2] = 0.0f;
+    if(!live) return s;
+    const float cm = fmaxf(in.z, 0.0f), w = metric_weight(metric, in, out);
+    if(!((in.z >= 0.0f) && (out.z >= 0.0f)))
+    {
+      // below the horizon: both lobes are zero (lambertian.h:38-44, microfacet.h:74-81), the term is a constant
+      e_const += loss_term_g(metric, cm, w, Spec<float>(0.0f), ref, nullptr);
+      return s;
+    }
+    if((in.z > 0.0f) && (out.z > 0.0f))
+    {
+      const f3 h = halfway(in, out);
+      const float inh = dot(in, h), outh = dot(out, h);
+      if((inh > 0.0f) && (outh > 0.0f))
+      {
+        DG::inv(in, out, h, inh, outh, q_rcp((float)M::norm() * (in.z*out.z)), s.I);
+        s.fc = CF::inv(0.5f*(inh + outh));
+      }
+    }
+    s.cm = cm; s.w = w; s.wc = w*cm;
+    if(LOG) { s.r[0] = logf(1.0f + ref.r*cm); s.r[1] = logf(1.0f + ref.g*cm); s.r[2] = logf(1.0f + ref.b*cm); }
+    else    { s.r[0] = ref.r*cm; s.r[1] = ref.g*cm; s.r[2] = ref.b*cm; }
+    return s;
+  }
+
+  template<bool WG, bool LOG> BBMCU_D static void accumulate(const float* d, const Sample& s, float* acc)
+  {
+    float DGv, dDG[DG::NP], Fv, dF[CF::NP];
+    DG::template eval<WG>(d + OFF_DG, s.I, DGv, dDG);
+    CF::template eval<WG>(d + OFF_F, s.fc, Fv, dF);
+    const float u = DGv*Fv;
+    const float v0 = fmaf(d[3], u, d[0]), v1 = fmaf(d[4], u, d[1]), v2 = fmaf(d[5], u, d[2]);
+    float t0, t1, t2, k0, k1, k2;
+    if(LOG)
+    {
+      const float a0 = fmaf(v0, s.cm, 1.0f), a1 = fmaf(v1, s.cm, 1.0f), a2 = fmaf(v2, s.cm, 1.0f);
+      t0 = logf(a0) - s.r[0]; t1 = logf(a1) - s.r[1]; t2 = logf(a2) - s.r[2];
+      if(WG) { k0 = s.wc*q_rcp(a0); k1 = s.wc*q_rcp(a1); k2 = s.wc*q_rcp(a2); }
+    }
+    else
+    {
+      t0 = fmaf(v0, s.cm, -s.r[0]); t1 = fmaf(v1, s.cm, -s.r[1]); t2 = fmaf(v2, s.cm, -s.r[2]);
+      if(WG) { k0 = k1 = k2 = s.wc; }
+    }
+    acc[0] = fmaf(fmaf(t2, t2, fmaf(t1, t1, t0*t0)), s.w, acc[0]);
+    if(WG)
+    {
+      const float e0 = t0*k0, e1 = t1*k1, e2 = t2*k2;        // (d e / d v) / 2
+      acc[1] += e0; acc[2] += e1; acc[3] += e2;
+      acc[4] = fmaf(e0, u, acc[4]); acc[5] = fmaf(e1, u, acc[5]); acc[6] = fmaf(e2, u, acc[6]);
+      const float sdv = fmaf(e2, d[5], fmaf(e1, d[4], e0*d[3]));
+#pragma unroll
+      for(int j=0; j < DG::NP; ++j) acc[7 + j] = fmaf(sdv, dDG[j]*Fv, acc[7 + j]);
+#pragma unroll
+      for(int j=0; j < CF::NP; ++j) acc[7 + DG::NP + j] = fmaf(sdv, DGv*dF[j], acc[7 + DG::NP + j]);
+    }
+  }
+};
+
+// which specular lobes have a compact pair kernel
+template<class M> struct CompactOf { static constexpr bool value = false; };
+template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>>
+{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>, CDGBeckmannVGroove<NRM>, CFCook>; };
+template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>>
+{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>, CDGBeckmannVGroove<NRM>, CFSchlick>; };
+
+constexpr int kCThreads = 128, kCSPT = 8;
+
+#ifdef __CUDACC__
+static_assert(kCThreads*kCSPT == kTileSamples, "same tiles (and block partial rows) as the generic tile kernel");
+template<class CL, bool WG, bool LOG>
+__global__ void __launch_bounds__(kCThreads, 4) k_loss_tile_compact(const LossArgs a, int K, int k_per_block, int n_tiles)
+{
+  constexpr int C = WG ? CL::C : 1;
+  constexpr int NW = kCThreads/32;
+  extern __shared__ __align__(16) float s_set[];                // (k1 - k0) x NSET
+  __shared__ float s_red[kTileKChunk][NW][C];
+  __shared__ float s_lin[kMerlLinTabFloats];
+  const int mat = blockIdx.z;
+  const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
+  const size_t kbase = (size_t)mat * K;
+  for(int k = threadIdx.x; k < k1 - k0; k += blockDim.x)
+  {
+    float raw[CL::NRAW];
+#pragma unroll
+    for(int j=0; j < CL::NRAW; ++j) raw[j] = loss_attr(a, (kbase + k0 + k)*a.attr_stride + j);
+    float d[CL::NSET];
+    CL::set(raw, d);
+#pragma unroll
+    for(int j=0; j < CL::NSET; ++j) s_set[k*CL::NSET + j] = d[j];
+  }
+  loss_stage_lin(a, s_lin);
+  __syncthreads();
+  const float* refp = a.ref + (size_t)mat * a.ref_stride;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for(int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+  {
+    typename CL::Sample smp[kCSPT];
+    float e_const = 0.0f;
+#pragma unroll
+    for(int s=0; s < kCSPT; ++s)
+    {
+      const size_t i = (size_t)tile*kTileSamples + (size_t)s*kCThreads + threadIdx.x;
+      const bool live = i < a.n;
+      const size_t ii = live ? i : 0;
+      f3 in, out;
+      loss_dirs(a, s_lin, ii, in, out);
+      const Spec<float> ref(__ldg(refp + ii), __ldg(refp + a.n + ii), __ldg(refp + 2*a.n + ii));
+      smp[s] = CL::template make_sample<LOG>(a.metric, in, out, ref, live, e_const);
+    }
+    for(int kc = k0; kc < k1; kc += kTileKChunk)
+    {
+      const int nkk = min(kTileKChunk, k1 - kc);
+      for(int kk=0; kk < nkk; ++kk)
+      {
+        float d[CL::NSET];
+        const float4* sp = reinterpret_cast<const float4*>(s_set + (size_t)(kc + kk - k0)*CL::NSET);
+#pragma unroll
+        for(int j=0; j < CL::NSET/4; ++j) { const float4 q = sp[j]; d[4*j] = q.x; d[4*j + 1] = q.y; d[4*j + 2] = q.z; d[4*j + 3] = q.w; }
+        float acc[CL::C];
+        acc[0] = e_const;
+#pragma unroll
+        for(int j=1; j < CL::C; ++j) acc[j] = 0.0f;
+#pragma unroll
+        for(int s=0; s < kCSPT; ++s) CL::template accumulate<WG, LOG>(d, smp[s], acc);
+        float red[C];
+#pragma unroll
+        for(int j=0; j < C; ++j) red[j] = acc[j];
+        int ridx; float rval; bool rwriter;
+        warp_reduce_multi<C>(red, lane, ridx, rval, rwriter);
+        if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
+      }
+      __syncthreads();
+      for(int t = threadIdx.x; t < nkk*(1 + a.P); t += blockDim.x)
+      {
+        const int kk = t / (1 + a.P), j = t % (1 + a.P);
+        double v = 0.0;
+        if(j < C)
+        {
+#pragma unroll
+          for(int w=0; w < NW; ++w) v += (double)s_red[kk][w][j];
+          v *= CL::col_scale(j);
+        }
+        a.partial[((kbase + kc + kk)*(1 + a.P) + j)*n_tiles + tile] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template<class CL> static void launch_loss_compact_static(cudaStream_t s, const LossArgs& a, unsigned K)
+{
+  const bool log_metric = a.metric > METRIC_BIERON_L2;
+  const int wg = a.want_grad ? 1 : 0, lg = log_metric ? 1 : 0;
+  static int per_sm[2][2] = {{0, 0}, {0, 0}};
+  if(per_sm[wg][lg] == 0)
+  {
+    int v = 0;
+    cudaError_t e = wg ? (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, true>, kCThreads, 24*1024)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, false>, kCThreads, 24*1024))
+                       : (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, true>, kCThreads, 24*1024)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, false>, kCThreads, 24*1024));
+    per_sm[wg][lg] = (e == cudaSuccess && v > 0) ? v : 4;
+  }
+  unsigned tiles, ksplit; int kpb;
+  // per-set / per-tile instruction weights of this kernel (profiles/r02_s27_ncu_loss_tile_compact_ct.txt)
+  loss_tile_shape(a.n, (size_t)K*a.n_materials, K, CL::NSET, a.sm_count, per_sm[wg][lg], tiles, ksplit, kpb, 24*1024, 75.0, 330.0);
+  const size_t smem = (size_t)kpb*CL::NSET*sizeof(float);
+  const size_t slots = (size_t)a.sm_count * (size_t)per_sm[wg][lg];
+  const size_t target = slots * (kpb >= 8 ? 8 : 2), other = (size_t)ksplit * a.n_materials;
+  unsigned gx = tiles;
+  if((size_t)tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
+  if(gx > tiles) gx = tiles;
+  const dim3 grid(gx, ksplit, (unsigned)a.n_materials);
+  if(wg) { if(lg) k_loss_tile_compact<CL, true, true><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
+           else   k_loss_tile_compact<CL, true, false><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles); }
+  else   { if(lg) k_loss_tile_compact<CL, false, true><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
+           else   k_loss_tile_compact<CL, false, false><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles); }
+}
+
+// Aggregate(Lambertian, model) through the compact kernel; false if `model` has none (bbmcu_loss_pair_compact.cu)
+bool launch_loss_pair_compact(int model, cudaStream_t, const LossArgs&, unsigned K);
+#endif
+
+} // namespace bbmcu

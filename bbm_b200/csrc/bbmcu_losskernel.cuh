@@ -228,11 +228,12 @@ __global__ void __launch_bounds__(kLossThreads) k_loss_tile(const LossArgs a, in
 // the one that minimises that product - e.g. a 1/8 shard (178 tiles) at K = 256 takes 8 ranges of 32 sets (1424 blocks, 5
 // rounds of 296) rather than 14 of 19 (9 rounds): 347 -> 322 us (tools/loss_shape_sweep.py).  BBMCU_LOSS_BLOCKS_PER_SM (tuning)
 // restores the fixed blocks-per-SM target.
-inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm_count, int blocks_per_sm, unsigned& tiles, unsigned& ksplit, int& k_per_block)
+inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm_count, int blocks_per_sm, unsigned& tiles, unsigned& ksplit, int& k_per_block,
+                            size_t smem_budget = 40*1024, double w_set = 185.0, double w_tile = 215.0)
 {
   tiles = (unsigned)((n + kTileSamples - 1) / kTileSamples);
   if(tiles < 1) tiles = 1;
-  const size_t smem_k = (size_t)(40*1024) / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the static shared-memory budget
+  const size_t smem_k = smem_budget / ((size_t)n_attrs*sizeof(float));          // parameter sets that fit the shared-memory budget
   size_t split_fit = (K + smem_k - 1) / (smem_k ? smem_k : 1);
   if(split_fit < 1) split_fit = 1;
   static const int fill = [] { const char* e = std::getenv("BBMCU_LOSS_BLOCKS_PER_SM"); int v = e ? std::atoi(e) : 0; return v > 0 ? v : 0; }();
@@ -246,8 +247,7 @@ inline void loss_tile_shape(size_t n, size_t Ktot, size_t K, int n_attrs, int sm
   else
   {
     // relative cost of one parameter set and of the per-tile work of a sample (instructions, loss + gradient of the
-    // Cook-Torrance aggregate: profiles/r02_s3_ncu_loss_tile_ct_fused_linearizer.txt)
-    const double w_set = 185.0, w_tile = 215.0;
+    // Cook-Torrance aggregate: profiles/r02_s3_ncu_loss_tile_ct_fused_linearizer.txt) are the defaults of w_set, w_tile
     const size_t slots = (size_t)sm_count * (size_t)(blocks_per_sm > 0 ? blocks_per_sm : 2);
     // two passes: the cheapest shape, then the finest split within 2 % of it (equal on paper, but short blocks even out
     // the run-time differences between blocks: full grid at K = 256, 1 range 2276 us, 2 ranges 2218, 4 ranges 2200)

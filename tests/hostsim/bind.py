@@ -114,3 +114,16 @@ class HostSim:
         self._chk(self.lib.hostsim_loss(bsdf.encode(), metric, component, self._p(i), self._p(o), self._p(r), C.c_size_t(n), C.c_double(1.0 / n),
                                         C.byref(loss), self._p(grad) if want_grad else None, self._p(terms)))
         return loss.value, grad[:nparams], terms
+
+    def loss_compact(self, bsdf, metric, inn, out, ref, want_grad=True, nparams=0):
+        """the compact pair loss (bbmcu_losscompact.cuh) on the host; None if the BSDF has no compact kernel"""
+        i, o, r = soa(inn), soa(out), soa(ref)
+        n = i.shape[1]
+        loss = C.c_double(0)
+        grad = np.zeros(max(nparams, 1), np.float64)
+        rc = self.lib.hostsim_loss_compact(bsdf.encode(), metric, self._p(i), self._p(o), self._p(r), C.c_size_t(n), C.c_double(1.0 / n),
+                                           C.byref(loss), self._p(grad) if want_grad else None)
+        if rc == 2:
+            return None
+        self._chk(rc)
+        return loss.value, grad[:nparams]

@@ -10,6 +10,7 @@
 #include "bbmcu_desc.hpp"
 #include "bbmcu_kernels.cuh"
 #include "bbmcu_lossop.cuh"
+#include "bbmcu_losscompact.cuh"
 #include "bbmcu_hpnorm.cuh"
 
 using namespace bbmcu;
@@ -141,3 +142,48 @@ int hostsim_loss(const char* bsdf, int metric, int component, const float* in, c
   )
 }
 } // extern "C"
+
+// the compact pair loss (bbmcu_losscompact.cuh) of ONE parameter set over explicit samples: per-set constants, per-sample
+// invariants and the accumulation exactly as k_loss_tile_compact runs them (8 samples per float accumulator, the
+// below-horizon constant, column factors), summed in double.  Returns 2 if the BSDF has no compact kernel.
+template<class CL, bool LOG> static void loss_compact_host(const BsdfDesc& d, int metric, const float* in, const float* out, const float* ref, size_t n, double inv_n, double* loss, double* grad)
+{
+  float set[CL::NSET];
+  CL::set(d.attrs, set);
+  std::vector<double> tot(CL::C, 0.0);
+  for(size_t i0=0; i0 < n; i0 += kCSPT)
+  {
+    float acc[CL::C]; float e_const = 0.0f;
+    typename CL::Sample smp[kCSPT];
+    for(int s=0; s < kCSPT; ++s)
+    {
+      const size_t i = i0 + s; const bool live = i < n; const size_t ii = live ? i : 0;
+      smp[s] = CL::template make_sample<LOG>(metric, make_f3(in[ii], in[n+ii], in[2*n+ii]), make_f3(out[ii], out[n+ii], out[2*n+ii]), Spec<float>(ref[ii], ref[n+ii], ref[2*n+ii]), live, e_const);
+    }
+    acc[0] = e_const; for(int j=1; j < CL::C; ++j) acc[j] = 0.0f;
+    for(int s=0; s < kCSPT; ++s) { if(grad) CL::template accumulate<true, LOG>(set, smp[s], acc); else CL::template accumulate<false, LOG>(set, smp[s], acc); }
+    for(int j=0; j < CL::C; ++j) tot[j] += (double)acc[j];
+  }
+  *loss = tot[0] * inv_n;
+  if(grad) for(int j=0; j < CL::P; ++j) grad[j] = tot[1+j] * CL::col_scale(1+j) * inv_n;
+}
+extern "C" int hostsim_loss_compact(const char* bsdf, int metric, const float* in, const float* out, const float* ref, size_t n, double inv_n, double* loss, double* grad)
+{
+  try {
+    auto b = bbmcu_host::parse_bsdf(bsdf);
+    BsdfDesc d = make_desc(b);
+    if(!(d.n_lobes == 2 && d.aggregate && d.model[0] == M_Lambertian)) return 2;
+    bool done = false;
+    dispatch_model(d.model[1], [&](auto* tag) {
+      using M = typename std::remove_pointer<decltype(tag)>::type;
+      if constexpr (CompactOf<M>::value)
+      {
+        using CL = typename CompactOf<M>::type;
+        if(metric > METRIC_BIERON_L2) loss_compact_host<CL, true>(d, metric, in, out, ref, n, inv_n, loss, grad);
+        else loss_compact_host<CL, false>(d, metric, in, out, ref, n, inv_n, loss, grad);
+        done = true;
+      }
+    });
+    return done ? 0 : 2;
+  } catch(const std::exception& e) { g_err = e.what(); return 1; }
+}

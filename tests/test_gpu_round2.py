@@ -319,3 +319,42 @@ def test_host_path_with_narrowed_and_derived_outputs_equals_device_path(ctx, s):
     assert np.array_equal(sp2.view(np.uint32), want[1].view(np.uint32)) and d2 is None and p2 is None
     d3, sp3, f3, rgb3, p3 = ctx.sample_eval_pdf(b, out, xi, want=("sample_pdf", "pdf"))
     assert np.array_equal(sp3.view(np.uint32), want[1].view(np.uint32)) and np.array_equal(p3.view(np.uint32), want[4].view(np.uint32))
+
+
+# ---- compact pair loss kernel (bbmcu_losscompact.cuh) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["nganL2", "lowL2", "bieronL2", "lowLog", "bieronLog", "standardLog"])
+def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
+    """Aggregate(Lambertian, Cook-Torrance family) runs the compact kernel (per-sample invariants, per-set constants, closed-form
+    jacobian); BBMCU_LOSS_NO_COMPACT=1 keeps the generic dual-number tile kernel.  Both on the full MERL grid, a shard of it
+    and a spherical grid, with and without gradient, K = 1 / 7 / 40 parameter sets: equal to float rounding of the terms."""
+    import bbm_b200 as bb
+    truth = bb.Bsdf(TRUTH)
+    rng = np.random.default_rng(11)
+    for fitted in ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.1, 1.6))",
+                   "Aggregate(Lambertian(), LowCookTorrance())", "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganCookTorrance([0.4, 0.5, 0.6], 0.1, 0.2))"):
+        fb = bb.Bsdf(fitted)
+        p0 = fb.parameter_values()
+        for grid, first, count in ((None, 0, 0), (None, 400_001, 300_007), (bb.spherical_grid((31, 16), (5, 9)), 0, 0)):
+            L = ctx.loss(metric, truth, grid, first=first, count=count)
+            for K in (1, 7, 40):
+                params = p0[None] * (1 + 0.05 * rng.random((K, len(p0))))
+                lc, gc = L(fb, params, grad=True)
+                vc = L(fb, params)
+                os.environ["BBMCU_LOSS_NO_COMPACT"] = "1"
+                try:
+                    lg, gg = L(fb, params, grad=True)
+                    vg = L(fb, params)
+                finally:
+                    del os.environ["BBMCU_LOSS_NO_COMPACT"]
+                assert np.all(np.abs(lc - lg) <= 2e-5 * np.abs(lg)), (fitted, metric, K, lc, lg)
+                assert np.all(np.abs(vc - lg) <= 2e-5 * np.abs(lg)) and np.all(np.abs(vg - lg) <= 2e-5 * np.abs(lg))
+                tol = 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=1, keepdims=True)
+                assert np.all(np.abs(gc - gg) <= tol), (fitted, metric, K, np.abs(gc - gg).max(), gc[0], gg[0])
+    # a parameter set's result does not depend on what else shares the launch (block partials per (set, tile), fixed order)
+    L = ctx.loss(metric, truth, None)
+    fb = bb.Bsdf("Aggregate(Lambertian(), CookTorrance())")
+    p0 = fb.parameter_values()
+    params = p0[None] * (1 + 0.05 * rng.random((33, len(p0))))
+    la, ga = L(fb, params, grad=True)
+    lb, gb = L(fb, params[5:6], grad=True)
+    assert np.array_equal(la[5:6].view(np.uint64), lb.view(np.uint64)) and np.array_equal(ga[5:6].view(np.uint64), gb.view(np.uint64))
