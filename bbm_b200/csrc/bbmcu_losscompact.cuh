@@ -134,20 +134,25 @@ template<class M, class DG, class CF> struct CompactPair
   // factor of column j of the block partial: the per-sample sums leave out 2 (d e / d v) and 1/pi (d v / d albedo)
   BBMCU_HD static double col_scale(int j) { return j == 0 ? 1.0 : (j <= 3 ? 2.0/kPiD : 2.0); }
 
-  template<bool LOG> BBMCU_D static Sample make_sample(int metric, f3 in, f3 out, const Spec<float>& ref, bool live, float& e_const)
+  // direction-only part of a sample.  state: 0 regular, 1 padding (past the end of the shard), 2 below the horizon - both
+  // lobes are zero there (lambertian.h:38-44, microfacet.h:74-81), so the term does not depend on the parameters: the
+  // sample is neutral in the per-set loop (w = 0) and keeps (cos_i, weight) in I[0], I[1] for below_const()
+  BBMCU_D static Sample make_geom(int metric, f3 in, f3 out, bool live, int& state)
   {
     Sample s;
 #pragma unroll
     for(int i=0; i < DG::NI; ++i) s.I[i] = 0.0f;
     s.fc = CF::inv(0.5f); s.cm = 0.0f; s.w = 0.0f; s.wc = 0.0f; s.r[0] = s.r[1] = s.r[2] = 0.0f;
+    state = 1;
     if(!live) return s;
     const float cm = fmaxf(in.z, 0.0f), w = metric_weight(metric, in, out);
     if(!((in.z >= 0.0f) && (out.z >= 0.0f)))
     {
-      // below the horizon: both lobes are zero (lambertian.h:38-44, microfacet.h:74-81), the term is a constant
-      e_const += loss_term_g(metric, cm, w, Spec<float>(0.0f), ref, nullptr);
+      static_assert(DG::NI >= 2, "two floats to keep the cosine and the weight of a below-horizon sample");
+      s.I[0] = cm; s.I[1] = fminf(w, 3.0e38f); state = 2;
       return s;
     }
+    state = 0;
     if((in.z > 0.0f) && (out.z > 0.0f))
     {
       const f3 h = halfway(in, out);
@@ -159,10 +164,15 @@ template<class M, class DG, class CF> struct CompactPair
       }
     }
     s.cm = cm; s.w = w; s.wc = w*cm;
-    if(LOG) { s.r[0] = logf(1.0f + ref.r*cm); s.r[1] = logf(1.0f + ref.g*cm); s.r[2] = logf(1.0f + ref.b*cm); }
-    else    { s.r[0] = ref.r*cm; s.r[1] = ref.g*cm; s.r[2] = ref.b*cm; }
     return s;
   }
+  // the measured value of one material at the sample (regular samples only; the others keep zeros)
+  template<bool LOG> BBMCU_D static void set_ref(Sample& s, const Spec<float>& ref, bool regular)
+  {
+    if(LOG) { s.r[0] = regular ? logf(1.0f + ref.r*s.cm) : 0.0f; s.r[1] = regular ? logf(1.0f + ref.g*s.cm) : 0.0f; s.r[2] = regular ? logf(1.0f + ref.b*s.cm) : 0.0f; }
+    else    { s.r[0] = regular ? ref.r*s.cm : 0.0f; s.r[1] = regular ? ref.g*s.cm : 0.0f; s.r[2] = regular ? ref.b*s.cm : 0.0f; }
+  }
+  BBMCU_D static float below_const(int metric, const Sample& s, const Spec<float>& ref) { return loss_term_g(metric, s.I[0], s.I[1], Spec<float>(0.0f), ref, nullptr); }
 
   template<bool WG, bool LOG> BBMCU_D static void accumulate(const float* d, const Sample& s, float* acc)
   {
@@ -209,84 +219,155 @@ constexpr int kCThreads = 128, kCSPT = 8;
 
 #ifdef __CUDACC__
 static_assert(kCThreads*kCSPT == kTileSamples, "same tiles (and block partial rows) as the generic tile kernel");
+
+// Block (x, y, z): sample tiles x, x + gridDim.x, ...; parameter sets [y kpb, (y+1) kpb) of each material; materials
+// [z mpb, (z+1) mpb).  The direction-only part of a tile's samples is computed ONCE and serves every material of the block
+// (a multi-material launch reads 12 B per sample and material and nothing else: with one parameter set per material
+// this is a DRAM stream); per material the three measured planes are loaded and folded into the samples, then the
+// parameter sets of that material run.  Block partials per (material, set, tile), written in groups of kTileKChunk rows.
 template<class CL, bool WG, bool LOG>
-__global__ void __launch_bounds__(kCThreads, 4) k_loss_tile_compact(const LossArgs a, int K, int k_per_block, int n_tiles)
+__global__ void __launch_bounds__(kCThreads, 4) k_loss_tile_compact(const LossArgs a, int K, int k_per_block, int n_tiles, int m_per_block)
 {
   constexpr int C = WG ? CL::C : 1;
   constexpr int NW = kCThreads/32;
-  extern __shared__ __align__(16) float s_set[];                // (k1 - k0) x NSET
+  extern __shared__ __align__(16) float s_set[];                // (m1 - m0) x (k1 - k0) x NSET
   __shared__ float s_red[kTileKChunk][NW][C];
   __shared__ float s_lin[kMerlLinTabFloats];
-  const int mat = blockIdx.z;
-  const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block);
-  const size_t kbase = (size_t)mat * K;
-  for(int k = threadIdx.x; k < k1 - k0; k += blockDim.x)
+  const int m0 = blockIdx.z * m_per_block, m1 = min(a.n_materials, m0 + m_per_block);
+  const int k0 = blockIdx.y * k_per_block, k1 = min(K, k0 + k_per_block), nk = k1 - k0;
+  for(int idx = threadIdx.x; idx < (m1 - m0)*nk; idx += blockDim.x)
   {
+    const int mm = idx / nk, k = idx - mm*nk;
+    const size_t set = (size_t)(m0 + mm)*K + (size_t)(k0 + k);
     float raw[CL::NRAW];
 #pragma unroll
-    for(int j=0; j < CL::NRAW; ++j) raw[j] = loss_attr(a, (kbase + k0 + k)*a.attr_stride + j);
+    for(int j=0; j < CL::NRAW; ++j) raw[j] = loss_attr(a, set*a.attr_stride + j);
     float d[CL::NSET];
     CL::set(raw, d);
 #pragma unroll
-    for(int j=0; j < CL::NSET; ++j) s_set[k*CL::NSET + j] = d[j];
+    for(int j=0; j < CL::NSET; ++j) s_set[(size_t)idx*CL::NSET + j] = d[j];
   }
   loss_stage_lin(a, s_lin);
   __syncthreads();
-  const float* refp = a.ref + (size_t)mat * a.ref_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for(int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
   {
     typename CL::Sample smp[kCSPT];
-    float e_const = 0.0f;
+    unsigned regular = 0u, below = 0u;
 #pragma unroll
     for(int s=0; s < kCSPT; ++s)
     {
       const size_t i = (size_t)tile*kTileSamples + (size_t)s*kCThreads + threadIdx.x;
       const bool live = i < a.n;
-      const size_t ii = live ? i : 0;
       f3 in, out;
-      loss_dirs(a, s_lin, ii, in, out);
-      const Spec<float> ref(__ldg(refp + ii), __ldg(refp + a.n + ii), __ldg(refp + 2*a.n + ii));
-      smp[s] = CL::template make_sample<LOG>(a.metric, in, out, ref, live, e_const);
+      loss_dirs(a, s_lin, live ? i : 0, in, out);
+      int state;
+      smp[s] = CL::make_geom(a.metric, in, out, live, state);
+      regular |= (state == 0 ? 1u : 0u) << s; below |= (state == 2 ? 1u : 0u) << s;
     }
-    for(int kc = k0; kc < k1; kc += kTileKChunk)
-    {
-      const int nkk = min(kTileKChunk, k1 - kc);
-      for(int kk=0; kk < nkk; ++kk)
-      {
-        float d[CL::NSET];
-        const float4* sp = reinterpret_cast<const float4*>(s_set + (size_t)(kc + kk - k0)*CL::NSET);
-#pragma unroll
-        for(int j=0; j < CL::NSET/4; ++j) { const float4 q = sp[j]; d[4*j] = q.x; d[4*j + 1] = q.y; d[4*j + 2] = q.z; d[4*j + 3] = q.w; }
-        float acc[CL::C];
-        acc[0] = e_const;
-#pragma unroll
-        for(int j=1; j < CL::C; ++j) acc[j] = 0.0f;
-#pragma unroll
-        for(int s=0; s < kCSPT; ++s) CL::template accumulate<WG, LOG>(d, smp[s], acc);
-        float red[C];
-#pragma unroll
-        for(int j=0; j < C; ++j) red[j] = acc[j];
-        int ridx; float rval; bool rwriter;
-        warp_reduce_multi<C>(red, lane, ridx, rval, rwriter);
-        if(rwriter && ridx < C) s_red[kk][warp][ridx] = rval;
-      }
+    // rows of s_red waiting to be written: (material, set) pairs seq0, seq0 + 1, ... of this block's m-major sequence
+    int pending = 0, seq0 = 0;
+    const float4* sp = reinterpret_cast<const float4*>(s_set);
+    auto flush = [&]() {
       __syncthreads();
-      for(int t = threadIdx.x; t < nkk*(1 + a.P); t += blockDim.x)
+      for(int t = threadIdx.x; t < pending*(1 + a.P); t += blockDim.x)
       {
-        const int kk = t / (1 + a.P), j = t % (1 + a.P);
+        const int q = t / (1 + a.P), j = t - q*(1 + a.P);
+        const int seq = seq0 + q, mm = seq / nk, kk = seq - mm*nk;
+        const size_t row = (size_t)(m0 + mm)*K + (size_t)(k0 + kk);
         double v = 0.0;
         if(j < C)
         {
 #pragma unroll
-          for(int w=0; w < NW; ++w) v += (double)s_red[kk][w][j];
+          for(int w=0; w < NW; ++w) v += (double)s_red[q][w][j];
           v *= CL::col_scale(j);
         }
-        a.partial[((kbase + kc + kk)*(1 + a.P) + j)*n_tiles + tile] = v;
+        a.partial[(row*(1 + a.P) + j)*n_tiles + tile] = v;
       }
       __syncthreads();
+      seq0 += pending; pending = 0;
+    };
+    for(int mat = m0; mat < m1; ++mat)
+    {
+      const float* refp = a.ref + (size_t)mat * a.ref_stride;
+      float e_const = 0.0f;
+      // the three measured planes of this material, loaded straight into the registers they end up in
+#pragma unroll
+      for(int s=0; s < kCSPT; ++s)
+      {
+        const size_t i = (size_t)tile*kTileSamples + (size_t)s*kCThreads + threadIdx.x;
+        const size_t ii = i < a.n ? i : 0;
+        smp[s].r[0] = __ldg(refp + ii); smp[s].r[1] = __ldg(refp + a.n + ii); smp[s].r[2] = __ldg(refp + 2*a.n + ii);
+      }
+      if(below)
+      {
+#pragma unroll
+        for(int s=0; s < kCSPT; ++s) if((below >> s) & 1u) e_const += CL::below_const(a.metric, smp[s], Spec<float>(smp[s].r[0], smp[s].r[1], smp[s].r[2]));
+      }
+#pragma unroll
+      for(int s=0; s < kCSPT; ++s) CL::template set_ref<LOG>(smp[s], Spec<float>(smp[s].r[0], smp[s].r[1], smp[s].r[2]), (regular >> s) & 1u);
+      // parameter sets of this material in chunks of up to kTileKChunk rows of s_red; the rows are written out when the
+      // next chunk would not fit (nk >= kTileKChunk: after every chunk; a few sets per material: several materials share a flush)
+      for(int kc=0; kc < nk; kc += kTileKChunk)
+      {
+        const int nkk = min(kTileKChunk, nk - kc);
+        float (*red_rows)[NW][C] = s_red + pending;
+        for(int kk=0; kk < nkk; ++kk)
+        {
+          float d[CL::NSET];
+#pragma unroll
+          for(int j=0; j < CL::NSET/4; ++j) { const float4 q = sp[j]; d[4*j] = q.x; d[4*j + 1] = q.y; d[4*j + 2] = q.z; d[4*j + 3] = q.w; }
+          sp += CL::NSET/4;                                     // the block's sets lie in the order they are visited
+          float acc[CL::C];
+          acc[0] = e_const;
+#pragma unroll
+          for(int j=1; j < CL::C; ++j) acc[j] = 0.0f;
+#pragma unroll
+          for(int s=0; s < kCSPT; ++s) CL::template accumulate<WG, LOG>(d, smp[s], acc);
+          float red[C];
+#pragma unroll
+          for(int j=0; j < C; ++j) red[j] = acc[j];
+          int ridx; float rval; bool rwriter;
+          warp_reduce_multi<C>(red, lane, ridx, rval, rwriter);
+          if(rwriter && ridx < C) red_rows[kk][warp][ridx] = rval;
+        }
+        pending += nkk;
+        if(pending + min(kTileKChunk, nk) > kTileKChunk) flush();
+      }
     }
+    if(pending) flush();
   }
+}
+
+// launch shape: tiles x k-splits x material groups.  A block costs its tile's direction-only work once, per material the
+// reference planes, per (material, set) one evaluation; blocks are equal and `slots` of them are resident at a time, so
+// the launch takes ceil(blocks / slots) block durations: the (k-split, material-split) pair that minimises the product,
+// then the finest pair within 2 % of it (weights: instructions per sample from profiles/r02_s29_ncu_loss_tile_compact_ct.txt)
+struct CompactShape { unsigned tiles, ksplit, msplit; int kpb, mpb; };
+inline CompactShape loss_compact_shape(size_t n, size_t K, size_t M, int nset, size_t slots)
+{
+  static thread_local struct { size_t n, K, M, slots; int nset; CompactShape s; bool valid; } memo = {0, 0, 0, 0, 0, {}, false};
+  if(memo.valid && memo.n == n && memo.K == K && memo.M == M && memo.slots == slots && memo.nset == nset) return memo.s;
+  CompactShape r;
+  r.tiles = (unsigned)std::max<size_t>(1, (n + kTileSamples - 1) / kTileSamples);
+  const size_t max_sets = std::max<size_t>(1, (size_t)(24*1024) / ((size_t)nset*sizeof(float)));      // (material, set) pairs a block can stage
+  const double w_set = 80.0, w_mat = 30.0, w_tile = 330.0;
+  auto cost_of = [&](size_t ks, size_t ms, bool& valid) {
+    const size_t kpb = (K + ks - 1) / ks, mpb = (M + ms - 1) / ms;
+    valid = ((K + kpb - 1) / kpb == ks) && ((M + mpb - 1) / mpb == ms) && kpb*mpb <= max_sets;
+    const size_t blocks = (size_t)r.tiles * ks * ms, rounds = (blocks + slots - 1) / slots;
+    return (double)rounds * (w_tile + (double)mpb * (w_mat + (double)kpb * w_set));
+  };
+  double best = 0.0; size_t bks = K, bms = M;
+  for(size_t ms = 1; ms <= M; ++ms)
+    for(size_t ks = 1; ks <= K && ks <= 256; ++ks) { bool v; const double c = cost_of(ks, ms, v); if(v && (best == 0.0 || c < best)) best = c; }
+  size_t fine = 0;
+  for(size_t ms = 1; ms <= M; ++ms)
+    for(size_t ks = 1; ks <= K && ks <= 256; ++ks) { bool v; const double c = cost_of(ks, ms, v); if(v && c <= best*1.02 && ks*ms >= fine) { fine = ks*ms; bks = ks; bms = ms; } }
+  r.kpb = (int)((K + bks - 1) / bks); r.mpb = (int)((M + bms - 1) / bms);
+  r.ksplit = (unsigned)((K + r.kpb - 1) / r.kpb); r.msplit = (unsigned)((M + r.mpb - 1) / r.mpb);
+  memo = {n, K, M, slots, nset, r, true};
+  return r;
 }
 
 template<class CL> static void launch_loss_compact_static(cudaStream_t s, const LossArgs& a, unsigned K)
@@ -303,20 +384,20 @@ template<class CL> static void launch_loss_compact_static(cudaStream_t s, const 
                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, false>, kCThreads, 24*1024));
     per_sm[wg][lg] = (e == cudaSuccess && v > 0) ? v : 4;
   }
-  unsigned tiles, ksplit; int kpb;
-  // per-set / per-tile instruction weights of this kernel (profiles/r02_s27_ncu_loss_tile_compact_ct.txt)
-  loss_tile_shape(a.n, (size_t)K*a.n_materials, K, CL::NSET, a.sm_count, per_sm[wg][lg], tiles, ksplit, kpb, 24*1024, 75.0, 330.0);
-  const size_t smem = (size_t)kpb*CL::NSET*sizeof(float);
   const size_t slots = (size_t)a.sm_count * (size_t)per_sm[wg][lg];
-  const size_t target = slots * (kpb >= 8 ? 8 : 2), other = (size_t)ksplit * a.n_materials;
-  unsigned gx = tiles;
-  if((size_t)tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
-  if(gx > tiles) gx = tiles;
-  const dim3 grid(gx, ksplit, (unsigned)a.n_materials);
-  if(wg) { if(lg) k_loss_tile_compact<CL, true, true><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
-           else   k_loss_tile_compact<CL, true, false><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles); }
-  else   { if(lg) k_loss_tile_compact<CL, false, true><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles);
-           else   k_loss_tile_compact<CL, false, false><<<grid, kCThreads, smem, s>>>(a, (int)K, kpb, (int)tiles); }
+  const CompactShape sh = loss_compact_shape(a.n, K, (size_t)a.n_materials, CL::NSET, slots);
+  const size_t smem = (size_t)sh.kpb*sh.mpb*CL::NSET*sizeof(float);
+  // blocks along the tile axis: all tiles unless that makes more than 8 rounds of resident blocks - then each block walks
+  // over several tiles and the staging of its parameter sets is paid once
+  const size_t other = (size_t)sh.ksplit * sh.msplit, target = slots * 8;
+  unsigned gx = sh.tiles;
+  if((size_t)sh.tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
+  if(gx > sh.tiles) gx = sh.tiles;
+  const dim3 grid(gx, sh.ksplit, sh.msplit);
+  if(wg) { if(lg) k_loss_tile_compact<CL, true, true><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
+           else   k_loss_tile_compact<CL, true, false><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
+  else   { if(lg) k_loss_tile_compact<CL, false, true><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
+           else   k_loss_tile_compact<CL, false, false><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
 }
 
 // Aggregate(Lambertian, model) through the compact kernel; false if `model` has none (bbmcu_loss_pair_compact.cu)

@@ -475,6 +475,12 @@ def main():
         Lm = ctx.loss("nganL2", truth, None, materialise=True, **shard)
         mat_ms = timed(lambda: Lm.eval_device(fitted, params, res), nl)
         del Lm
+        # the same pass through the generic dual-number tile kernel (what every model without a compact kernel runs)
+        os.environ["BBMCU_LOSS_NO_COMPACT"] = "1"
+        try:
+            gen_ms = timed(lambda: L.eval_device(fitted, params, res), nl)
+        finally:
+            del os.environ["BBMCU_LOSS_NO_COMPACT"]
         if world == 1:
             collective = None
         elif L_peer is not None:
@@ -483,7 +489,9 @@ def main():
             collective = "nccl all_reduce of K x (1+P) doubles (peer windows unavailable: %s)" % peer_error
         loss_info = {"value": passes, "passes_per_s_by_K_no_collective": by_k, "unit": "loss+grad passes/s", "K": LOSS_K, "P": P, "samples_per_pass": N, "ms_per_step": step_ms,
                      "scaling": "strong", "metric": "nganL2", "fitted": FITTED, "collective": collective, "linearizer": "fused into the kernel (12 B per sample)",
+                     "kernel": "compact pair kernel (bbmcu_losscompact.cuh): per-sample invariants, per-set constants, closed-form jacobian",
                      "passes_per_s_with_materialised_directions_no_collective": LOSS_K / (mat_ms * 1e-3),
+                     "passes_per_s_generic_tile_kernel_no_collective": LOSS_K / (gen_ms * 1e-3),
                      "passes_per_s_with_nccl_all_reduce": (LOSS_K / (nccl_ms * 1e-3)) if nccl_ms else None,
                      "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / (world * peak),
                      "frac_note": "whole-job passes/s x 12 B x N / (n_gpus x measured HBM peak); the grid is L2-resident, the kernel is issue-bound",

@@ -158,7 +158,11 @@ template<class CL, bool LOG> static void loss_compact_host(const BsdfDesc& d, in
     for(int s=0; s < kCSPT; ++s)
     {
       const size_t i = i0 + s; const bool live = i < n; const size_t ii = live ? i : 0;
-      smp[s] = CL::template make_sample<LOG>(metric, make_f3(in[ii], in[n+ii], in[2*n+ii]), make_f3(out[ii], out[n+ii], out[2*n+ii]), Spec<float>(ref[ii], ref[n+ii], ref[2*n+ii]), live, e_const);
+      int state;
+      smp[s] = CL::make_geom(metric, make_f3(in[ii], in[n+ii], in[2*n+ii]), make_f3(out[ii], out[n+ii], out[2*n+ii]), live, state);
+      const Spec<float> r(ref[ii], ref[n+ii], ref[2*n+ii]);
+      if(state == 2) e_const += CL::below_const(metric, smp[s], r);
+      CL::template set_ref<LOG>(smp[s], r, state == 0);
     }
     acc[0] = e_const; for(int j=1; j < CL::C; ++j) acc[j] = 0.0f;
     for(int s=0; s < kCSPT; ++s) { if(grad) CL::template accumulate<true, LOG>(set, smp[s], acc); else CL::template accumulate<false, LOG>(set, smp[s], acc); }

@@ -358,3 +358,19 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
     la, ga = L(fb, params, grad=True)
     lb, gb = L(fb, params[5:6], grad=True)
     assert np.array_equal(la[5:6].view(np.uint64), lb.view(np.uint64)) and np.array_equal(ga[5:6].view(np.uint64), gb.view(np.uint64))
+    # several materials per block (the direction-only part of a tile serves all of them): against the generic kernel
+    if metric in ("nganL2", "bieronLog"):
+        mats = ["Aggregate(Lambertian([%g, 0.1, 0.05]), CookTorrance([0.3, 0.3, %g], %g, 1.5))" % (0.1 + 0.05 * m, 0.1 + 0.1 * m, 0.05 + 0.04 * m) for m in range(5)]
+        tables = _synthetic_tables(ctx, mats)
+        Lm = ctx.loss(metric, tables, None, first=200_000, count=150_001)
+        for K in (1, 3):
+            pm = p0[None, None] * (1 + 0.05 * rng.random((len(mats), K, len(p0))))
+            lc, gc = Lm.eval_multi(fb, pm, grad=True)
+            vc = Lm.eval_multi(fb, pm)
+            os.environ["BBMCU_LOSS_NO_COMPACT"] = "1"
+            try:
+                lg, gg = Lm.eval_multi(fb, pm, grad=True)
+            finally:
+                del os.environ["BBMCU_LOSS_NO_COMPACT"]
+            assert np.all(np.abs(lc - lg) <= 2e-5 * np.abs(lg)) and np.all(np.abs(vc - lg) <= 2e-5 * np.abs(lg)), (metric, K)
+            assert np.all(np.abs(gc - gg) <= 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=2, keepdims=True)), (metric, K)
