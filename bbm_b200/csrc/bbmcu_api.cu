@@ -7,6 +7,9 @@
 #include <mutex>
 #include <thread>
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <emmintrin.h>
 
 #include "bbmcu_launch.cuh"
 
@@ -106,8 +109,12 @@ namespace {
 //                 third output (`mask`: the flag) is non-zero and 0 elsewhere - the host threads write it from those
 // (the fused pass returns sample.pdf next to pdf(sample.direction, out), which most models define as the same number:
 // 36 -> 29 bytes per pair down the link, the side the pass is bound by)
-enum : int { XFER_PLAIN = 0, XFER_BYTES, XFER_COPY_OF, XFER_MASKED_BY };
-struct ArrayArg { const void* ptr; int planes; bool input; int xfer = XFER_PLAIN; int src = -1; int mask = -1; };
+//   XFER_GRAY_SCALED  a three-plane output whose planes are one device plane u times three launch constants (eval of a
+//                 single scaled lobe whose unscaled value is gray): the kernel writes u, u crosses the link (4 bytes per
+//                 element, not 12) into the pinned ring and host threads write u * scale[c] into the caller's planes - the
+//                 IEEE single multiplications the device kernel does, so the same bits
+enum : int { XFER_PLAIN = 0, XFER_BYTES, XFER_COPY_OF, XFER_MASKED_BY, XFER_GRAY_SCALED };
+struct ArrayArg { const void* ptr; int planes; bool input; int xfer = XFER_PLAIN; int src = -1; int mask = -1; float scale[3] = {0.0f, 0.0f, 0.0f}; };
 
 enum class Mem { Device, Pinned, Pageable };
 Mem classify(const void* p)
@@ -161,14 +168,106 @@ __global__ void k_narrow_to_bytes(const int32_t* __restrict__ in, unsigned char*
   }
 }
 
-// f(begin, end) over [0, n) on `threads` host threads
+// A few persistent host threads for the per-chunk work of the host-pointer path (created on first use; creating threads
+// per call cost more than the work of a chunk).  run(n, f) calls f(begin, end) on disjoint ranges covering [0, n).
+class HostPool
+{
+  std::vector<std::thread> workers;
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::function<void(size_t, size_t)> fn;
+  size_t n = 0, per = 0;
+  int pending = 0;
+  uint64_t generation = 0;
+  bool stop = false;
+  void loop(int id)
+  {
+    uint64_t seen = 0;
+    for(;;)
+    {
+      std::unique_lock<std::mutex> lk(m);
+      cv_work.wait(lk, [&] { return stop || generation != seen; });
+      if(stop) return;
+      seen = generation;
+      const size_t b = (size_t)id*per, e = std::min(n, b + per);
+      lk.unlock();
+      if(b < e) fn(b, e);
+      lk.lock();
+      if(--pending == 0) cv_done.notify_one();
+    }
+  }
+public:
+  explicit HostPool(int threads) { for(int i=0; i < threads; ++i) workers.emplace_back([this, i] { loop(i); }); }
+  ~HostPool() { { std::lock_guard<std::mutex> lk(m); stop = true; } cv_work.notify_all(); for(auto& t : workers) t.join(); }
+  int size() const { return (int)workers.size(); }
+  void run(size_t count, std::function<void(size_t, size_t)> f)
+  {
+    std::unique_lock<std::mutex> lk(m);
+    fn = std::move(f); n = count;
+    per = ((count + workers.size() - 1) / workers.size() + 63) & ~size_t(63);
+    pending = (int)workers.size(); ++generation;
+    cv_work.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+};
+std::mutex g_pool_mutex;                                        // one call at a time uses the pool
+HostPool& host_pool()
+{
+  static HostPool pool((int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2)));
+  return pool;
+}
+// f(begin, end) over [0, n) on the pool's threads (small n: on the caller)
 template<class F> void host_parallel(size_t n, int threads, F&& f)
 {
   if(n < (size_t(1) << 18) || threads <= 1) { f((size_t)0, n); return; }
-  std::vector<std::thread> pool;
-  const size_t per = ((n + threads - 1) / threads + 63) & ~size_t(63);
-  for(int t=0; t < threads; ++t) { const size_t b = (size_t)t*per; if(b >= n) break; const size_t e = std::min(n, b + per); pool.emplace_back([=] { f(b, e); }); }
-  for(auto& th : pool) th.join();
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  host_pool().run(n, std::function<void(size_t, size_t)>(f));
+}
+
+// Streaming (non-temporal) forms of the per-chunk host loops: the destinations are whole output planes that are not
+// read again here, so the stores bypass the cache instead of reading every line for ownership first.
+inline bool aligned16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+void widen_bytes(int32_t* dst, const unsigned char* src, size_t b, size_t e)
+{
+  size_t i = b;
+  while(i < e && !aligned16p(dst + i)) { dst[i] = (int32_t)src[i]; ++i; }
+  const __m128i z = _mm_setzero_si128();
+  for(; i + 16 <= e; i += 16)
+  {
+    const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+    const __m128i lo = _mm_unpacklo_epi8(x, z), hi = _mm_unpackhi_epi8(x, z);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i),      _mm_unpacklo_epi16(lo, z));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4),  _mm_unpackhi_epi16(lo, z));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 8),  _mm_unpacklo_epi16(hi, z));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 12), _mm_unpackhi_epi16(hi, z));
+  }
+  for(; i < e; ++i) dst[i] = (int32_t)src[i];
+  _mm_sfence();
+}
+void stream_copy(float* dst, const float* src, size_t b, size_t e)
+{
+  size_t i = b;
+  while(i < e && !aligned16p(dst + i)) { dst[i] = src[i]; ++i; }
+  for(; i + 4 <= e; i += 4) _mm_stream_ps(dst + i, _mm_loadu_ps(src + i));
+  for(; i < e; ++i) dst[i] = src[i];
+  _mm_sfence();
+}
+// d_c[i] = u[i] * s_c: IEEE single products, scalar or packed (the same operation, the same bits as the device's FMUL)
+void stream_scaled3(float* d0, float* d1, float* d2, const float* u, float s0, float s1, float s2, size_t b, size_t e)
+{
+  size_t i = b;
+  if(aligned16p(d0) && aligned16p(d1) && aligned16p(d2))
+  {
+    while(i < e && (i & 3)) { const float v = u[i]; d0[i] = v*s0; d1[i] = v*s1; d2[i] = v*s2; ++i; }
+    const __m128 v0 = _mm_set1_ps(s0), v1 = _mm_set1_ps(s1), v2 = _mm_set1_ps(s2);
+    for(; i + 4 <= e; i += 4)
+    {
+      const __m128 v = _mm_loadu_ps(u + i);
+      _mm_stream_ps(d0 + i, _mm_mul_ps(v, v0)); _mm_stream_ps(d1 + i, _mm_mul_ps(v, v1)); _mm_stream_ps(d2 + i, _mm_mul_ps(v, v2));
+    }
+  }
+  for(; i < e; ++i) { const float v = u[i]; d0[i] = v*s0; d1[i] = v*s1; d2[i] = v*s2; }
+  _mm_sfence();
 }
 
 // Host-pointer path: chunks of the batch flow through kSlots device staging buffers, each chunk's H2D copies, kernel and
@@ -228,7 +327,16 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
       {
         const unsigned char* src = (const unsigned char*)ctx->pin_buf[s] + off[a];
         int32_t* dst = (int32_t*)args[a].ptr + c0;
-        host_parallel(cn, threads, [=](size_t b, size_t e) { for(size_t i = b; i < e; ++i) dst[i] = (int32_t)src[i]; });
+        host_parallel(cn, threads, [=](size_t b, size_t e) { widen_bytes(dst, src, b, e); });
+      }
+    // scaled outputs: u in the ring -> u * scale[c] in the caller's three planes
+    for(size_t a=0; a < args.size(); ++a)
+      if(args[a].ptr && args[a].xfer == XFER_GRAY_SCALED)
+      {
+        const float* src = (const float*)((const char*)ctx->pin_buf[s] + off[a]);
+        float* d0 = (float*)args[a].ptr + c0; float* d1 = d0 + user_ld; float* d2 = d1 + user_ld;
+        const float s0 = args[a].scale[0], s1 = args[a].scale[1], s2 = args[a].scale[2];
+        host_parallel(cn, threads, [=](size_t b, size_t e) { stream_scaled3(d0, d1, d2, src, s0, s1, s2, b, e); });
       }
     // derived outputs, from what has just arrived of their sources (the caller's own plane, or the ring if that is pageable and not yet copied... it is: see above)
     for(size_t a=0; a < args.size(); ++a)
@@ -236,7 +344,7 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
       {
         const float* src = (const float*)args[args[a].src].ptr + c0;
         float* dst = (float*)args[a].ptr + c0;
-        if(args[a].xfer == XFER_COPY_OF) host_parallel(cn, threads, [=](size_t b, size_t e) { std::memcpy(dst + b, src + b, (e - b)*sizeof(float)); });
+        if(args[a].xfer == XFER_COPY_OF) host_parallel(cn, threads, [=](size_t b, size_t e) { stream_copy(dst, src, b, e); });
         else
         {
           const unsigned char* m = (const unsigned char*)ctx->pin_buf[s] + off[args[a].mask];     // the flag bytes of this chunk
@@ -284,6 +392,7 @@ void run_hosted(bbmcu_ctx* ctx, size_t n, const std::vector<ArrayArg>& args, con
           BBMCU_CUDA(cudaMemcpyAsync((char*)ctx->pin_buf[s] + off[a], bytes, cn, cudaMemcpyDeviceToHost, st));
           continue;
         }
+        if(args[a].xfer == XFER_GRAY_SCALED) { BBMCU_CUDA(cudaMemcpyAsync((char*)ctx->pin_buf[s] + off[a], dptr[a], cn*4, cudaMemcpyDeviceToHost, st)); continue; }
         if(kind[a] == Mem::Pageable) BBMCU_CUDA(cudaMemcpy2DAsync((char*)ctx->pin_buf[s] + off[a], ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
         else BBMCU_CUDA(cudaMemcpy2DAsync((char*)args[a].ptr + c0*4, user_ld*4, dptr[a], ld*4, cn*4, args[a].planes, cudaMemcpyDeviceToHost, st));
       }
@@ -339,10 +448,14 @@ int sample_pdf_rule(const BsdfDesc& d)
   });
   return rule;
 }
-void compress_fused_outputs(const BsdfDesc& d, std::vector<ArrayArg>& args, int i_spdf, int i_flag, int i_pdf)
+void compress_fused_outputs(const BsdfDesc& d, std::vector<ArrayArg>& args, int i_spdf, int i_flag, int i_pdf, int i_rgb = -1)
 {
   static const bool plain = [] { const char* e = std::getenv("BBMCU_HOST_TRANSFER_PLAIN"); return e && e[0] == '1'; }();
   if(plain) return;
+  // eval of a single hand-merged lobe = u * its leading RGB scale (attributes 0..2): send u.  Host pointers only - the
+  // caller of a device-pointer call reads the planes the kernel wrote.
+  if(i_rgb >= 0 && args[i_rgb].ptr && classify(args[i_rgb].ptr) != Mem::Device && launch_sample_eval_pdf_gray_capable(d))
+  { args[i_rgb].xfer = XFER_GRAY_SCALED; args[i_rgb].scale[0] = d.attrs[0]; args[i_rgb].scale[1] = d.attrs[1]; args[i_rgb].scale[2] = d.attrs[2]; }
   if(args[i_flag].ptr) args[i_flag].xfer = XFER_BYTES;
   if(!args[i_spdf].ptr || !args[i_pdf].ptr) return;
   const int rule = sample_pdf_rule(d);
@@ -550,8 +663,10 @@ int bbmcu_sample_eval_pdf(bbmcu_ctx* ctx, const bbmcu_bsdf* bsdf, int component,
     BBMCU_CUDA(cudaSetDevice(ctx->device));
     BsdfDesc d = make_desc(bsdf->b, ctx->device);
     std::vector<ArrayArg> args = {{out, 3, true}, {xi, 2, true}, {dir, 3, false}, {spdf, 1, false}, {flag, 1, false}, {rgb, 3, false}, {pdf, 1, false}};
-    compress_fused_outputs(d, args, 3, 4, 6);
+    compress_fused_outputs(d, args, 3, 4, 6, 5);
+    const bool gray = args[5].xfer == XFER_GRAY_SCALED;
     run_any(ctx, n, args, [&](cudaStream_t s, const std::vector<void*>& p, size_t cn) {
+      if(gray && launch_sample_eval_pdf_gray(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn)) return;
       launch_sample_eval_pdf(ctx, s, d, component, (const float*)p[0], (const float*)p[1], (float*)p[2], (float*)p[3], (int32_t*)p[4], (float*)p[5], (float*)p[6], cn); });
   });
 }

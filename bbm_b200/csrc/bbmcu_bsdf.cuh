@@ -191,6 +191,8 @@ struct BsdfSingle
   { if constexpr (kFusedSample) M::eval_pdf(in, out, b.attrs, component, e, p); }
   BBMCU_D static void sample_eval_pdf_merged(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag, Spec<float>& e, float& p)
   { if constexpr (kHandFused) M::sample_eval_pdf_merged(out, xi, b.attrs, component, dir, flag, e, p); }
+  BBMCU_D static void sample_eval_pdf_merged_u(const BsdfDesc& b, f3 out, f2 xi, int component, f3& dir, int& flag, float& u, float& p)
+  { if constexpr (kHandFused) M::sample_eval_pdf_merged_u(out, xi, b.attrs, component, dir, flag, u, p); }
   BBMCU_D static Spec<float> eval(const BsdfDesc& b, f3 in, f3 out, int component) { return M::template eval<float>(in, out, b.attrs, component); }
   BBMCU_D static Spec<float> reflectance(const BsdfDesc& b, f3 out, int component) { return M::reflectance(out, b.attrs, component); }
   BBMCU_D static float pdf(const BsdfDesc& b, f3 in, f3 out, int component) { return M::pdf(in, out, b.attrs, component); }

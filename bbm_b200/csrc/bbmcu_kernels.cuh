@@ -212,6 +212,29 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
   }
 };
 
+// The fused pass of a hand-merged single-lobe model with the value BEFORE its leading RGB scale: `gray` receives u (one
+// plane), eval = u * scale.  Used by the host-pointer path only (bbmcu_api.cu): 4 bytes per element cross the link instead
+// of 12 and host threads form the three products (same IEEE single multiplications as the device: same bits).
+template<class B> struct SampleEvalPdfGrayOp
+{
+  using BsdfT = B;
+  static constexpr bool kOneWaveWithTables = false;
+  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocksFused;
+  static constexpr bool kHasBsdf = true, kTables = B::kTables;
+  BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* gray; float* pdf; size_t n; bool aligned; size_t ld = 0;
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
+  {
+    Lanes3 b = load4x3(out, i, n, ld, aligned), d; Lanes u = load4(xi, i, n, aligned), v = load4(xi + ld, i, n, aligned), g, p; int f[kVec];
+#pragma unroll
+    for(int k=0; k < kVec; ++k) { f3 dd; B::sample_eval_pdf_merged_u(bsdf, b.get(k), make_f2(u.v[k], v.v[k]), component, dd, f[k], g.v[k], p.v[k]); d.set(k, dd); }
+    if(dir) store4x3(dir, i, n, ld, aligned, d);
+    if(spdf) store4(spdf, i, n, aligned, p);                  // p is already 0 when the sample is invalid
+    if(flag) store4i(flag, i, n, aligned, f);
+    if(gray) store4(gray, i, n, aligned, g);
+    if(pdf) store4(pdf, i, n, aligned, p);
+  }
+};
+
 template<class B> using SampleEvalPdfOp = SampleEvalPdfOpT<B, false>;
 template<class B> using SampleEvalPdfGenOp = SampleEvalPdfOpT<B, true>;      // inputs drawn in the kernel (0 B in)
 

@@ -115,6 +115,11 @@ void launch_reflectance(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component
 void launch_sample(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi, float* dir, float* pdf, int32_t* flag, size_t n);
 void launch_sample_eval_pdf(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
                             float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf, size_t n, const GenArgs& g = GenArgs());
+// the fused pass writing the value before the leading RGB scale (one plane) instead of rgb; false unless the BSDF is a single
+// hand-merged lobe (launch_sample_eval_pdf_gray_capable says so without launching)
+bool launch_sample_eval_pdf_gray_capable(const BsdfDesc&);
+bool launch_sample_eval_pdf_gray(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, const float* out, const float* xi,
+                                 float* dir, float* spdf, int32_t* flag, float* gray, float* pdf, size_t n);
 // eval over bins [first, first + n) of the MERL grid, directions generated in the kernel; in / out may be null
 void launch_eval_grid(bbmcu_ctx*, cudaStream_t, const BsdfDesc&, int component, uint32_t first, float* rgb, float* in, float* out, size_t n);
 // the device's separable merl_linearizer table (900 floats, built on first use, lives for the process)

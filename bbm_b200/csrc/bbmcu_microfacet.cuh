@@ -744,6 +744,15 @@ struct Microfacet
   // arithmetic runs on whatever the element holds (the *_raw operations neither trap nor loop on garbage).
   BBMCU_D static void sample_eval_pdf_merged(f3 out, f2 xi, const float* a, int component, f3& dir, int& flag, Spec<float>& e, float& p)
   {
+    float u;
+    sample_eval_pdf_merged_u(out, xi, a, component, dir, flag, u, p);
+    e = Spec<float>(u*a[0], u*a[1], u*a[2]);
+  }
+  // the same with the value before the leading RGB scale: eval = (u a[0], u a[1], u a[2]).  The host-pointer path sends u (4
+  // bytes per element instead of 12) and lets host threads form the three products - IEEE single multiplications on both
+  // sides, the same bits (bbmcu_api.cu, XFER_GRAY_SCALED)
+  BBMCU_D static void sample_eval_pdf_merged_u(f3 out, f2 xi, const float* a, int component, f3& dir, int& flag, float& u, float& p)
+  {
     static_assert(kHandFusedEvalPdf, "only the hand-merged model has this path");
     const bool ok_s = (component & FLAG_SPECULAR) && xi_valid(xi) && (out.z > 0.0f);
     const f3 m = NDF::sample_unchecked(out, xi, a + OFF_NDF);
@@ -764,11 +773,10 @@ struct Microfacet
     const float fa = A*d2*R, fb = n2*B*R;
     const float Fv = fmaxf(0.5f * (fa*fa) * fmaf(fb, fb, 1.0f), 0.0f);
     const float R4 = q_rcp(4.0f * in.z * out.z);
-    const float u = ok_e ? Dv * (gi*go) * Fv * R4 : 0.0f;
+    u = ok_e ? Dv * (gi*go) * Fv * R4 : 0.0f;
     const float pv = Dv * go * in.z * R4;
     dir = make_f3(ok_s ? in.x : 0.0f, ok_s ? in.y : 0.0f, ok_s ? in.z : 0.0f);
     flag = ok_s ? FLAG_SPECULAR : FLAG_NONE;
-    e = Spec<float>(u*a[0], u*a[1], u*a[2]);
     p = (ok_e && (pv > 0.0f)) ? pv : 0.0f;
   }
   // sample.pdf is pdf(sample.direction, out) (microfacet.h:138): fused sample -> eval -> pdf passes evaluate it once

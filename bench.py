@@ -371,9 +371,11 @@ def main():
         full_ms = wall(lambda: ctx.sample_eval_pdf(bsdf, a_out, a_xi, outputs=a_res), args.steps)
         e2e = {"value": world * n / (full_ms * 1e-3) / 1e9, "unit": "G pairs/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 36 * n,
                "ms_per_step": full_ms, "contract": "host (pinned) inputs, all five outputs delivered to the caller's host buffers", "numa": numa,
-               "d2h_bytes_over_pcie_per_step": 29 * n,
-               "d2h_note": "36 B per pair arrive in the caller's buffers; 29 B of them cross the link: the flag plane travels as one byte per element and sample.pdf - the "
-                           "same number as pdf for this model - is written by host threads from pdf (bbmcu_api.cu compress_fused_outputs; BBMCU_HOST_TRANSFER_PLAIN=1 sends all 36)"}
+               "d2h_bytes_over_pcie_per_step": 21 * n,
+               "d2h_note": "36 B per pair arrive in the caller's buffers; 21 B of them cross the link: the flag plane travels as one byte per element, sample.pdf - the "
+                           "same number as pdf for this model - is written by host threads from pdf, and eval = u x the lobe's RGB scale travels as u (4 B, not 12) with "
+                           "the three IEEE products formed by host threads (bbmcu_api.cu compress_fused_outputs; every byte equals the device path's, checked below; "
+                           "BBMCU_HOST_TRANSFER_PLAIN=1 sends all 36)"}
         # the host path returns exactly what the device path computed
         chk = slice(0, 1 << 16)
         for host_arr, dev_t in zip(a_res, outs):

@@ -288,10 +288,11 @@ def test_interleaved_loss_shards_sum_to_the_whole(ctx, materialise):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("s", ["GGX()", "Phong()", "CookTorrance()", "Lambertian()", "Aggregate(Lambertian(), GGX())", "Aggregate(Lambertian(), Phong(), GGX())", "He()"])
+@pytest.mark.parametrize("s", ["GGX()", "GGX([0.3, 0.6, 0.9], 0.15, 1.7)", "Phong()", "CookTorrance()", "Lambertian()", "Aggregate(Lambertian(), GGX())", "Aggregate(Lambertian(), Phong(), GGX())", "He()"])
 def test_host_path_with_narrowed_and_derived_outputs_equals_device_path(ctx, s):
     """host pointers: the flag plane travels as one byte per element and - for models whose sample.pdf is pdf(sample.direction,
-    out) - sample.pdf does not travel at all (host threads write both planes).  Every output equals the device-pointer
+    out) - sample.pdf does not travel at all (host threads write both planes); the eval of the hand-merged GGX lobe travels
+    as one plane before its RGB scale and host threads form the three products.  Every output equals the device-pointer
     call's, bit for bit, for pinned and for pageable caller memory, also when some outputs are not asked for."""
     import torch
     import bbm_b200 as bb
