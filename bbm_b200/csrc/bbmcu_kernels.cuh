@@ -47,6 +47,25 @@ BBMCU_D void store4i(int32_t* p, size_t i, size_t n, bool aligned, const int (&r
 #pragma unroll
   for(int k=0; k < kVec; ++k) if(i + k < n) p[i + k] = r[k];
 }
+// unconditional 16-byte accesses (the caller has established alignment and a full group)
+BBMCU_D Lanes load4_fast(const float* p)
+{
+  Lanes r;
+#ifdef __CUDA_ARCH__
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p)); r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+#else
+  for(int k=0; k < kVec; ++k) r.v[k] = p[k];
+#endif
+  return r;
+}
+BBMCU_D void store4_fast(float* p, const Lanes& r)
+{
+#ifdef __CUDA_ARCH__
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+#else
+  for(int k=0; k < kVec; ++k) p[k] = r.v[k];
+#endif
+}
 struct Lanes3 { Lanes x, y, z; BBMCU_D f3 get(int k) const { return make_f3(x.v[k], y.v[k], z.v[k]); } BBMCU_D void set(int k, f3 a) { x.v[k] = a.x; y.v[k] = a.y; z.v[k] = a.z; } };
 BBMCU_D Lanes3 load4x3(const float* p, size_t i, size_t n, size_t ld, bool aligned) { Lanes3 r; r.x = load4(p, i, n, aligned); r.y = load4(p + ld, i, n, aligned); r.z = load4(p + 2*ld, i, n, aligned); return r; }
 BBMCU_D void store4x3(float* p, size_t i, size_t n, size_t ld, bool aligned, const Lanes3& r) { store4(p, i, n, aligned, r.x); store4(p + ld, i, n, aligned, r.y); store4(p + 2*ld, i, n, aligned, r.z); }
@@ -162,11 +181,17 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
 {
   using BsdfT = B;
   static constexpr bool kOneWaveWithTables = false;           // dominated by the model's eval, whose cost varies per element: keep many blocks for balance
-  static constexpr int kBlock = 256, kMinBlocks = B::kMinBlocksFused;     // (the hand-merged GGX kernel: 256 x 3 with 4736 blocks 94.6 G pairs/s, 256 x 4 94.1, 512 x 2 92.9, 128 x 8 93.1, 1024 x 1 91.3)
+  static constexpr int kBlock = 256, kMinBlocks = (!GEN && B::kHandFused) ? 4 : B::kMinBlocksFused;     // (the hand-merged kernel with its fast path: 4 resident blocks = 64 registers, session 33; before it: 256 x 3 with 4736 blocks 94.6 G pairs/s at 62 registers, 256 x 3 with 4736 blocks 94.6 G pairs/s, 256 x 4 94.1, 512 x 2 92.9, 128 x 8 93.1, 1024 x 1 91.3)
   static constexpr bool kHasBsdf = true, kTables = B::kTables;
   BsdfDesc bsdf; int component; const float* out; const float* xi; float* dir; float* spdf; int32_t* flag; float* rgb; float* pdf; size_t n; bool aligned; size_t ld = 0;   // ld (0 = n): floats between the planes of one SoA argument (>= n)
   uint64_t gen_seed = 0, gen_first = 0; float* gen_out = nullptr; float* gen_xi = nullptr;       // GEN only
-  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const
+  // FAST: every plane of the call is 16-byte aligned, every output is wanted and the group is a full one - the kernel tests
+  // that once per launch (fast_ok) and runs the groups below n / 4 without per-plane tests and fall-back paths (the
+  // headline kernel spent ~25 of its 341 instructions per pair on them)
+  static constexpr bool kFastPath = !GEN && B::kHandFused;
+  BBMCU_D bool fast_ok() const { return aligned && dir && spdf && flag && rgb && pdf; }
+  BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const { group_t<false>(i, bsdf); }
+  template<bool FAST> BBMCU_D void group_t(size_t i, const BsdfDesc& bsdf) const
   {
     Lanes3 b, d, c; Lanes u, v, sp, p; int f[kVec];
     if constexpr (GEN)
@@ -176,6 +201,7 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
       if(gen_out) store4x3(gen_out, i, n, ld, aligned, b);
       if(gen_xi) { store4(gen_xi, i, n, aligned, u); store4(gen_xi + ld, i, n, aligned, v); }
     }
+    else if constexpr (FAST) { b.x = load4_fast(out + i); b.y = load4_fast(out + ld + i); b.z = load4_fast(out + 2*ld + i); u = load4_fast(xi + i); v = load4_fast(xi + ld + i); }
     else { b = load4x3(out, i, n, ld, aligned); u = load4(xi, i, n, aligned); v = load4(xi + ld, i, n, aligned); }
 #pragma unroll
     for(int k=0; k < kVec; ++k)
@@ -203,6 +229,15 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
         s = B::eval(bsdf, dd, o, component);
       }
       d.set(k, dd); c.set(k, make_f3(s.r, s.g, s.b));
+    }
+    if constexpr (FAST)
+    {
+      store4_fast(dir + i, d.x); store4_fast(dir + ld + i, d.y); store4_fast(dir + 2*ld + i, d.z);
+      store4_fast(spdf + i, sp);
+      *reinterpret_cast<int4*>(flag + i) = make_int4(f[0], f[1], f[2], f[3]);
+      store4_fast(rgb + i, c.x); store4_fast(rgb + ld + i, c.y); store4_fast(rgb + 2*ld + i, c.z);
+      store4_fast(pdf + i, p);
+      return;
     }
     if(dir) store4x3(dir, i, n, ld, aligned, d);
     if(spdf) store4(spdf, i, n, aligned, sp);
@@ -339,6 +374,8 @@ struct MerlLookupOp
 
 template<class Op, class = void> struct OpUsesEpd { static constexpr bool value = false; };
 template<class Op> struct OpUsesEpd<Op, typename VoidOf<typename Op::BsdfT>::type> { static constexpr bool value = UsesEpd<typename Op::BsdfT>::value; };
+template<class Op, class = void> struct OpFastPath { static constexpr bool value = false; };
+template<class Op> struct OpFastPath<Op, typename std::enable_if<Op::kFastPath>::type> { static constexpr bool value = true; };
 template<class Op, class = void> struct UsesLinTab { static constexpr bool value = false; };
 template<class Op> struct UsesLinTab<Op, typename std::enable_if<Op::kLinTab>::type> { static constexpr bool value = true; };
 
@@ -373,6 +410,16 @@ template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks)
         bsdf_tables_phase2(sb, threadIdx.x);
         __syncthreads();
         for(size_t g = first; g < groups; g += stride) op.group(g * kVec, sb);
+        return;
+      }
+    }
+    if constexpr (OpFastPath<Op>::value)
+    {
+      if(op.fast_ok())                           // uniform: full groups without per-plane tests, the ragged last group (if any) on the general path
+      {
+        const size_t full = op.n / kVec;
+        for(size_t g = first; g < full; g += stride) op.template group_t<true>(g * kVec, op.bsdf);
+        for(size_t g = full + first; g < groups; g += stride) op.group(g * kVec, op.bsdf);
         return;
       }
     }

@@ -16,6 +16,7 @@ bool launch_loss_pair_compact(int model, cudaStream_t s, const LossArgs& a, unsi
     case M_CookTorrance:     return try_compact<M_CookTorrance>(s, a, K);
     case M_LowCookTorrance:  return try_compact<M_LowCookTorrance>(s, a, K);
     case M_NganCookTorrance: return try_compact<M_NganCookTorrance>(s, a, K);
+    case M_GGX:              return try_compact<M_GGX>(s, a, K);
     default: return false;
   }
 }

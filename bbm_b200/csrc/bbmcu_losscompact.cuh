@@ -111,11 +111,40 @@ template<bool NORMALIZE> struct CDGBeckmannVGroove
   }
 };
 
+// isotropic GGX (ggx.h:60-75) times the uncorrelated Smith term of its own G1 (ggx.h:184-187):
+//   D = alpha^2 / (pi (q + alpha^2 (1 - q))^2),  q = h_x^2 + h_y^2;   G1(v) = 2 / (1 + s_v),  s_v = sqrt(1 + alpha^2 tan^2 theta_v)
+//   D G / (N z_i z_o) = alpha^2 [4 / (pi N z_i z_o)] / (den^2 (1 + s_i)(1 + s_o)),   den = q + alpha^2 (1 - q)
+//   d log (D G) / d alpha = 2/alpha - 4 alpha (1 - q) / den - alpha (t_i / (s_i (1 + s_i)) + t_o / (s_o (1 + s_o)))
+// three reciprocals serve the value and the derivative: 1/den, 1/(s_i (1 + s_i)), 1/(s_o (1 + s_o))
+struct CDGGgxSmith
+{
+  static constexpr int NS = 4, NP = 1, NI = 4;
+  BBMCU_D static void set(const float* a, float* d) { const float al = a[0]; d[0] = al*al; d[1] = al; d[2] = 2.0f/al; d[3] = 4.0f*al; }
+  // caller guarantees in.z > 0, out.z > 0, inh > 0, outh > 0;  k = 1 / (N z_i z_o)
+  BBMCU_D static void inv(f3 in, f3 out, f3 h, float, float, float k, float* I)
+  {
+    I[0] = h.x*h.x + h.y*h.y;
+    I[1] = fminf(sinTheta2(in)/(in.z*in.z), 1e30f);
+    I[2] = fminf(sinTheta2(out)/(out.z*out.z), 1e30f);
+    I[3] = fminf(4.0f*kInvPi*k, 3.0e38f);
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& DG, float (&dDG)[NP])
+  {
+    const float z2 = 1.0f - I[0];
+    const float den = fmaf(d[0], z2, I[0]);
+    const float si = q_sqrt(fmaf(d[0], I[1], 1.0f)), so = q_sqrt(fmaf(d[0], I[2], 1.0f));
+    const float r1 = q_rcp(den), r2 = q_rcp(fmaf(si, si, si)), r3 = q_rcp(fmaf(so, so, so));
+    DG = ((d[0]*I[3])*(r1*r1))*((r2*si)*(r3*so));
+    if(WG) dDG[0] = DG*(fmaf(-d[3]*z2, r1, d[2]) - d[1]*fmaf(I[1], r2, I[2]*r3));
+  }
+};
+
 // ---- Aggregate(Lambertian, M), M = Microfacet<NDF, G, F, NORM, true> described by the two policies ------------------
 // fit parameters in attribute order: albedo rgb, scale rgb, NDF parameters, Fresnel parameters
-template<class M, class DG, class CF> struct CompactPair
+template<class M, class DG, class CF, int SPT = 8> struct CompactPair
 {
   using Model = M;
+  static constexpr int kSPT = SPT, kThreads = 1024/SPT;        // samples per thread x threads = one tile of 1024 samples
   static constexpr int NRAW = 3 + M::NA;                       // attribute floats of a parameter set
   static constexpr int P = 6 + DG::NP + CF::NP, C = 1 + P;
   static constexpr int OFF_DG = 6, OFF_F = 6 + DG::NS, NSET = (6 + DG::NS + CF::NS + 3) & ~3;
@@ -215,10 +244,10 @@ template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>>
 { static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>, CDGBeckmannVGroove<NRM>, CFSchlick>; };
 
-constexpr int kCThreads = 128, kCSPT = 8;
+template<int NORM> struct CompactOf<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>>
+{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>, CDGGgxSmith, CFCook, 4>; };
 
 #ifdef __CUDACC__
-static_assert(kCThreads*kCSPT == kTileSamples, "same tiles (and block partial rows) as the generic tile kernel");
 
 // Block (x, y, z): sample tiles x, x + gridDim.x, ...; parameter sets [y kpb, (y+1) kpb) of each material; materials
 // [z mpb, (z+1) mpb).  The direction-only part of a tile's samples is computed ONCE and serves every material of the block
@@ -226,10 +255,11 @@ static_assert(kCThreads*kCSPT == kTileSamples, "same tiles (and block partial ro
 // this is a DRAM stream); per material the three measured planes are loaded and folded into the samples, then the
 // parameter sets of that material run.  Block partials per (material, set, tile), written in groups of kTileKChunk rows.
 template<class CL, bool WG, bool LOG>
-__global__ void __launch_bounds__(kCThreads, 4) k_loss_tile_compact(const LossArgs a, int K, int k_per_block, int n_tiles, int m_per_block)
+__global__ void __launch_bounds__(CL::kThreads, 512/CL::kThreads) k_loss_tile_compact(const LossArgs a, int K, int k_per_block, int n_tiles, int m_per_block)
 {
   constexpr int C = WG ? CL::C : 1;
-  constexpr int NW = kCThreads/32;
+  constexpr int NW = CL::kThreads/32, kCSPT = CL::kSPT, kCThreads = CL::kThreads;
+  static_assert(kCThreads*kCSPT == kTileSamples, "same tiles (and block partial rows) as the generic tile kernel");
   extern __shared__ __align__(16) float s_set[];                // (m1 - m0) x (k1 - k0) x NSET
   __shared__ float s_red[kTileKChunk][NW][C];
   __shared__ float s_lin[kMerlLinTabFloats];
@@ -378,10 +408,10 @@ template<class CL> static void launch_loss_compact_static(cudaStream_t s, const 
   if(per_sm[wg][lg] == 0)
   {
     int v = 0;
-    cudaError_t e = wg ? (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, true>, kCThreads, 24*1024)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, false>, kCThreads, 24*1024))
-                       : (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, true>, kCThreads, 24*1024)
-                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, false>, kCThreads, 24*1024));
+    cudaError_t e = wg ? (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, true>, CL::kThreads, 24*1024)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, true, false>, CL::kThreads, 24*1024))
+                       : (lg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, true>, CL::kThreads, 24*1024)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_loss_tile_compact<CL, false, false>, CL::kThreads, 24*1024));
     per_sm[wg][lg] = (e == cudaSuccess && v > 0) ? v : 4;
   }
   const size_t slots = (size_t)a.sm_count * (size_t)per_sm[wg][lg];
@@ -394,10 +424,10 @@ template<class CL> static void launch_loss_compact_static(cudaStream_t s, const 
   if((size_t)sh.tiles * other > target) gx = (unsigned)std::max<size_t>(1, (target + other - 1) / other);
   if(gx > sh.tiles) gx = sh.tiles;
   const dim3 grid(gx, sh.ksplit, sh.msplit);
-  if(wg) { if(lg) k_loss_tile_compact<CL, true, true><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
-           else   k_loss_tile_compact<CL, true, false><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
-  else   { if(lg) k_loss_tile_compact<CL, false, true><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
-           else   k_loss_tile_compact<CL, false, false><<<grid, kCThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
+  if(wg) { if(lg) k_loss_tile_compact<CL, true, true><<<grid, CL::kThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
+           else   k_loss_tile_compact<CL, true, false><<<grid, CL::kThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
+  else   { if(lg) k_loss_tile_compact<CL, false, true><<<grid, CL::kThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb);
+           else   k_loss_tile_compact<CL, false, false><<<grid, CL::kThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
 }
 
 // Aggregate(Lambertian, model) through the compact kernel; false if `model` has none (bbmcu_loss_pair_compact.cu)

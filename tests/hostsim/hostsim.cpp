@@ -151,6 +151,7 @@ template<class CL, bool LOG> static void loss_compact_host(const BsdfDesc& d, in
   float set[CL::NSET];
   CL::set(d.attrs, set);
   std::vector<double> tot(CL::C, 0.0);
+  constexpr int kCSPT = CL::kSPT;
   for(size_t i0=0; i0 < n; i0 += kCSPT)
   {
     float acc[CL::C]; float e_const = 0.0f;

@@ -11,6 +11,8 @@ CASES = [
     ("Aggregate(Lambertian([0.1, 0.1, 0.3]), CookTorrance([1.4, 1.5, 0.9], 0.03, 1.3))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), CookTorrance([1.0, 1.3, 1.1], 0.04, 1.25))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowCookTorrance([0.4, 0.5, 0.6], 0.3, 1.8))", "Aggregate(Lambertian([0.2, 0.2, 0.2]), LowCookTorrance([0.3, 0.6, 0.5], 0.25, 1.5))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganCookTorrance([0.4, 0.5, 0.6], 0.1, 0.2))", "Aggregate(Lambertian([0.2, 0.2, 0.2]), NganCookTorrance([0.3, 0.6, 0.5], 0.2, 0.1))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), GGX([0.4, 0.5, 0.6], 0.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), GGX([0.5, 0.4, 0.7], 0.15, 1.4))"),
+    ("Aggregate(Lambertian([0.1, 0.1, 0.3]), GGX([1.4, 1.5, 0.9], 0.02, 1.3))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), GGX([1.0, 1.3, 1.1], 0.03, 1.25))"),
     # total internal reflection inside the Fresnel term (eta < 1): g clamps to zero, F = 1
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.2, 0.9))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
 ]
@@ -43,7 +45,9 @@ def test_compact_loss_equals_generic_on_host(hostsim, case):
         got = hostsim.loss_compact(fitted, m, i, o, ref, nparams=P)
         assert got is not None, fitted
         assert abs(got[0] - want) <= 2e-5 * abs(want), (name, got[0], want)
-        tol = 5e-5 * np.abs(wg) + 1e-6 * np.abs(wg).max()
+        # eta < 1: d g / d eta = eta / g is singular where g = sqrt(eta^2 + c^2 - 1) -> 0, and the two kernels round g^2 differently
+        rel = 2e-3 if "1.6, 0.9" in fitted or ", 0.9))" in fitted else 5e-5
+        tol = rel * np.abs(wg) + 1e-6 * np.abs(wg).max()
         assert np.all(np.abs(got[1] - wg) <= tol), (name, got[1], wg)
         v = hostsim.loss_compact(fitted, m, i, o, ref, want_grad=False)
         assert abs(v[0] - want) <= 2e-5 * abs(want), name
@@ -52,5 +56,5 @@ def test_compact_loss_equals_generic_on_host(hostsim, case):
 def test_models_without_compact_kernel_report_so(hostsim):
     i, o = _samples(hostsim, 16, 1)
     ref = np.zeros((16, 3), np.float32)
-    assert hostsim.loss_compact("Aggregate(Lambertian([0.3, 0.2, 0.1]), GGX([0.4, 0.5, 0.6], 0.2, 1.6))", 0, i, o, ref) is None
+    assert hostsim.loss_compact("Aggregate(Lambertian([0.3, 0.2, 0.1]), Phong([0.4, 0.5, 0.6], 20))", 0, i, o, ref) is None
     assert hostsim.loss_compact("CookTorrance([0.4, 0.5, 0.6], 0.2, 1.6)", 0, i, o, ref) is None
