@@ -17,6 +17,8 @@ bool launch_loss_pair_compact(int model, cudaStream_t s, const LossArgs& a, unsi
     case M_LowCookTorrance:  return try_compact<M_LowCookTorrance>(s, a, K);
     case M_NganCookTorrance: return try_compact<M_NganCookTorrance>(s, a, K);
     case M_GGX:              return try_compact<M_GGX>(s, a, K);
+    case M_LowMicrofacet:    return try_compact<M_LowMicrofacet>(s, a, K);
+    case M_LowMicrofacetFit: return try_compact<M_LowMicrofacetFit>(s, a, K);
     default: return false;
   }
 }

@@ -38,6 +38,15 @@ BBMCU_D float c_ex2(float x)
 #endif
 }
 
+BBMCU_D float c_lg2(float x)
+{
+#ifdef __CUDA_ARCH__
+  float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+  return log2f(x);
+#endif
+}
+
 // ---- Fresnel policies: NS floats per parameter set, one float per sample, value + derivative -------------------------
 // fresnel::cook (fresnel_cook.h:47-55): g = sqrt(eta^2 + c^2 - 1), p = (g - c)/(g + c), q = (c(g + c) - 1)/(c(g - c) + 1),
 // F = p^2 (1 + q^2) / 2;  dp/dg = 2c/(g + c)^2, dq/dg = 2c(1 - c^2)/(c(g - c) + 1)^2, dg/deta = eta/g
@@ -136,6 +145,29 @@ struct CDGGgxSmith
     const float r1 = q_rcp(den), r2 = q_rcp(fmaf(si, si, si)), r3 = q_rcp(fmaf(so, so, so));
     DG = ((d[0]*I[3])*(r1*r1))*((r2*si)*(r3*so));
     if(WG) dDG[0] = DG*(fmaf(-d[3]*z2, r1, d[2]) - d[1]*fmaf(I[1], r2, I[2]*r3));
+  }
+};
+
+// Low et al. 2012 microfacet distribution (ndf/low.h:40-60), unnormalised, times the V-groove term:
+//   D = (1 + B x)^-C,  x = 1 - h_z;   d D / d B = -C D x / (1 + B x),   d D / d C = -D ln(1 + B x)
+// The reference calls the double pow; C is of order one (0.02 .. 2.7 in fits/low_lowmicrofacet_E2.fit), so the 2^-22 absolute
+// error of lg2.approx moves D by C ln 2 2^-22 < 1e-6 relative; x = 1 - h_z is exact in float for h_z >= 1/2.
+struct CDGLowVGroove
+{
+  static constexpr int NS = 2, NP = 2, NI = 2;
+  BBMCU_D static void set(const float* a, float* d) { d[0] = a[0]; d[1] = a[1]; }
+  BBMCU_D static void inv(f3 in, f3 out, f3 h, float inh, float outh, float k, float* I)
+  {
+    I[0] = 1.0f - h.z;
+    const float gi = q_div(2.0f*h.z*in.z, inh), go = q_div(2.0f*h.z*out.z, outh);
+    I[1] = fminf(fminf(1.0f, fminf(gi, go))*k, 3.0e38f);
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& DG, float (&dDG)[NP])
+  {
+    const float b = fmaf(d[0], I[0], 1.0f);
+    const float L = c_lg2(b);
+    DG = c_ex2(-d[1]*L)*I[1];
+    if(WG) { dDG[0] = -(d[1]*DG)*(I[0]*q_rcp(b)); dDG[1] = -DG*(L*0.69314718055994530942f); }
   }
 };
 
@@ -244,6 +276,8 @@ template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>>
 { static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>, CDGBeckmannVGroove<NRM>, CFSchlick>; };
 
+template<int NORM> struct CompactOf<Microfacet<NdfLow, GVGroove, FresnelCookIor, NORM, true>>
+{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfLow, GVGroove, FresnelCookIor, NORM, true>, CDGLowVGroove, CFCook>; };
 template<int NORM> struct CompactOf<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>>
 { static constexpr bool value = true; using type = CompactPair<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>, CDGGgxSmith, CFCook, 4>; };
 

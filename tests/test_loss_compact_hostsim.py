@@ -13,6 +13,8 @@ CASES = [
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganCookTorrance([0.4, 0.5, 0.6], 0.1, 0.2))", "Aggregate(Lambertian([0.2, 0.2, 0.2]), NganCookTorrance([0.3, 0.6, 0.5], 0.2, 0.1))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), GGX([0.4, 0.5, 0.6], 0.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), GGX([0.5, 0.4, 0.7], 0.15, 1.4))"),
     ("Aggregate(Lambertian([0.1, 0.1, 0.3]), GGX([1.4, 1.5, 0.9], 0.02, 1.3))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), GGX([1.0, 1.3, 1.1], 0.03, 1.25))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowMicrofacet([0.4, 0.5, 0.6], 300.0, 1.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowMicrofacet([0.5, 0.4, 0.7], 200.0, 1.5, 1.4))"),
+    ("Aggregate(Lambertian([0.1, 0.1, 0.3]), LowMicrofacetFit([51.7, 37.9, 27.4], 10482.1, 0.8167, 2.2365))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), LowMicrofacetFit([40.0, 30.0, 30.0], 20000.0, 0.9, 1.8))"),
     # total internal reflection inside the Fresnel term (eta < 1): g clamps to zero, F = 1
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.2, 0.9))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
 ]
