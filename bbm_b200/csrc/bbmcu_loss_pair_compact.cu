@@ -19,6 +19,11 @@ bool launch_loss_pair_compact(int model, cudaStream_t s, const LossArgs& a, unsi
     case M_GGX:              return try_compact<M_GGX>(s, a, K);
     case M_LowMicrofacet:    return try_compact<M_LowMicrofacet>(s, a, K);
     case M_LowMicrofacetFit: return try_compact<M_LowMicrofacetFit>(s, a, K);
+    case M_NganAshikhminShirley: return try_compact<M_NganAshikhminShirley>(s, a, K);
+    case M_LowAshikhminShirley:  return try_compact<M_LowAshikhminShirley>(s, a, K);
+    case M_Phong:            return try_compact<M_Phong>(s, a, K);
+    case M_NganBlinnPhong:   return try_compact<M_NganBlinnPhong>(s, a, K);
+    case M_NganLafortune:    return try_compact<M_NganLafortune>(s, a, K);
     default: return false;
   }
 }

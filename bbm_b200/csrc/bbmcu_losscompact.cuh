@@ -171,17 +171,159 @@ struct CDGLowVGroove
   }
 };
 
-// ---- Aggregate(Lambertian, M), M = Microfacet<NDF, G, F, NORM, true> described by the two policies ------------------
-// fit parameters in attribute order: albedo rgb, scale rgb, NDF parameters, Fresnel parameters
-template<class M, class DG, class CF, int SPT = 8> struct CompactPair
+// ---- lobe policies: a scaled lobe  scale_rgb * u(in, out; theta)  with a gray u -------------------------------------
+//   NS floats per parameter set (set), NI >= 2 floats per sample (inv; zero = a sample where the lobe vanishes), NP fit
+//   parameters after the scale, in attribute order;  eval<WG>(d, I, u, du[NP])
+// microfacet<NDF, G, F, N> (microfacet.h:74-102) from a D G policy and a Fresnel policy
+template<class M, class DG, class CF> struct LPMicrofacet
+{
+  static constexpr int NS = DG::NS + CF::NS, NP = DG::NP + CF::NP, NI = DG::NI + 1;
+  static_assert(M::SCALE == 0 && M::NA == 3 + NP, "leading scale, every other attribute a fit parameter");
+  BBMCU_D static void set(const float* a, float* d) { DG::set(a + (M::OFF_NDF - 3), d); CF::set(a + (M::OFF_F - 3), d + DG::NS); }
+  BBMCU_D static void zero(float* I)
+  {
+#pragma unroll
+    for(int i=0; i < DG::NI; ++i) I[i] = 0.0f;
+    I[DG::NI] = CF::inv(0.5f);
+  }
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    zero(I);
+    if(!((in.z > 0.0f) && (out.z > 0.0f))) return;
+    const f3 h = halfway(in, out);
+    const float inh = dot(in, h), outh = dot(out, h);
+    if(!((inh > 0.0f) && (outh > 0.0f))) return;
+    DG::inv(in, out, h, inh, outh, q_rcp((float)M::norm() * (in.z*out.z)), I);
+    I[DG::NI] = CF::inv(0.5f*(inh + outh));
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    float DGv, dDG[DG::NP], Fv, dF[CF::NP];
+    DG::template eval<WG>(d, I, DGv, dDG);
+    CF::template eval<WG>(d + DG::NS, I[DG::NI], Fv, dF);
+    u = DGv*Fv;
+    if(WG)
+    {
+#pragma unroll
+      for(int j=0; j < DG::NP; ++j) du[j] = dDG[j]*Fv;
+#pragma unroll
+      for(int j=0; j < CF::NP; ++j) du[DG::NP + j] = DGv*dF[j];
+    }
+  }
+};
+
+// isotropic Ashikhmin-Shirley lobe (ashikhminshirley.h:60-80; the NganAshikhminShirley / LowAshikhminShirley fits):
+//   u = F(h.in) (n + 1) / (8 pi) h_z^n / (h.in max(z_i, z_o));  attributes after the scale: Fresnel, n
+//   d u / d n = u (1 / (n + 1) + ln h_z)
+// per sample: log2 h_z (from the accurate logf: the exponent n log2 h_z reaches -126 before the power vanishes), 1 / (h.in max(z)),
+// the Fresnel cosine
+template<class M, class CF> struct LPAshikhminShirleyIso
+{
+  static constexpr int NS = CF::NS + 3, NP = CF::NP + 1, NI = 3;
+  static_assert(M::SCALE == 0 && M::NA == 3 + NP && M::OFF_N == 3 + CF::NP, "scale, Fresnel, exponent");
+  BBMCU_D static void set(const float* a, float* d) { CF::set(a, d); const float n = a[CF::NP]; d[CF::NS] = n; d[CF::NS + 1] = (n + 1.0f)/M::kEightPi; d[CF::NS + 2] = 1.0f/(n + 1.0f); }
+  BBMCU_D static void zero(float* I) { I[0] = 0.0f; I[1] = 0.0f; I[2] = CF::inv(0.5f); }
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    zero(I);
+    if(!((in.z > 0.0f) && (out.z > 0.0f))) return;
+    const f3 h = halfway(in, out);
+    const float hin = dot(h, in);
+    I[0] = fmaxf(logf(h.z)*1.44269504088896340736f, -1e4f);
+    I[1] = fminf(1.0f/(hin*fmaxf(in.z, out.z)), 3.0e38f);
+    I[2] = CF::inv(hin);
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    float Fv, dF[CF::NP];
+    CF::template eval<WG>(d, I[2], Fv, dF);
+    const float lobe = (d[CF::NS + 1]*c_ex2(d[CF::NS]*I[0]))*I[1];
+    u = Fv*lobe;
+    if(WG)
+    {
+#pragma unroll
+      for(int j=0; j < CF::NP; ++j) du[j] = dF[j]*lobe;
+      du[CF::NP] = u*fmaf(I[0], 0.69314718055994530942f, d[CF::NS + 2]);
+    }
+  }
+};
+
+// Phong / NganBlinnPhong (phong.h:43-60): u = (n + 2) / (2 pi) cos_alpha^n, cos_alpha = max(reflect_z(in).out, 0); d u / d n = u (1/(n + 2) + ln cos_alpha)
+template<class M> struct LPPhong
+{
+  static constexpr int NS = 3, NP = 1, NI = 2;
+  static_assert(M::SCALE == 0 && M::NA == 4, "scale, exponent");
+  BBMCU_D static void set(const float* a, float* d) { const float n = a[0]; d[0] = n; d[1] = (n + 2.0f)*(0.5f*kInvPi); d[2] = 1.0f/(n + 2.0f); }
+  BBMCU_D static void zero(float* I) { I[0] = -1e4f; I[1] = 0.0f; }
+  // the lobe lives on in.z >= 0, out.z >= 0 - the caller's domain
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    const float ca = fmaxf(dot(reflect_z(in), out), 0.0f);
+    I[0] = (ca > 0.0f) ? fmaxf(logf(ca)*1.44269504088896340736f, -1e4f) : -1e4f;
+    I[1] = 0.0f;
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    u = d[1]*c_ex2(d[0]*I[0]);
+    if(WG) du[0] = u*fmaf(I[0], 0.69314718055994530942f, d[2]);
+  }
+};
+
+// isotropic Lafortune lobe with Ngan's normalisation (lafortune.h:50-70, ngan.h:54-129):
+//   u = max(d, 0)^n nrm,  d = Cxy (x_i x_o + y_i y_o) + Cz z_i z_o,  nrm = (n + 2) / (2 pi max(Cz^2, Cxy^2)^(n/2))
+// nrm and its three parameter derivatives are per-set constants; d depends on both, so its logarithm (the accurate logf: n is
+// large for sharp lobes) is taken per sample and set
+template<class M> struct LPNganLafortune
+{
+  static constexpr int NS = 7, NP = 3, NI = 2;
+  static_assert(M::SCALE == 0 && M::NA == 6, "scale, Cxy, Cz, n");
+  BBMCU_D static void set(const float* a, float* d)
+  {
+    const float cxy = a[0], cz = a[1], n = a[2];
+    const float cz2 = cz*cz, cxy2 = cxy*cxy, m2 = fmaxf(cz2, cxy2);
+    const float nrm = (n + 2.0f)*(0.5f*kInvPi)/powf(m2, n*0.5f);
+    d[0] = cxy; d[1] = cz; d[2] = n; d[3] = nrm;
+    // m_max(cz2, cxy2) of the dual-number path keeps the first argument on a tie
+    d[4] = (cxy2 > cz2) ? -nrm*n*cxy/m2 : 0.0f;
+    d[5] = (cxy2 > cz2) ? 0.0f : -nrm*n*cz/m2;
+    d[6] = nrm*(1.0f/(n + 2.0f) - 0.5f*logf(m2));
+  }
+  BBMCU_D static void zero(float* I) { I[0] = 0.0f; I[1] = 0.0f; }
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    zero(I);
+    if(!((in.z > 0.0f) && (out.z > 0.0f))) return;
+    I[0] = in.x*out.x + in.y*out.y; I[1] = in.z*out.z;
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    const float dd = fmaf(d[0], I[0], d[1]*I[1]);
+    const bool on = dd > 0.0f;
+    const float ds = on ? dd : 1.0f;
+    const float ln = logf(ds);
+    const float pw = on ? c_ex2(d[2]*(ln*1.44269504088896340736f)) : 0.0f;
+    u = pw*d[3];
+    if(WG)
+    {
+      const float g = (d[2]*u)*q_rcp(ds);                        // d u / d d
+      du[0] = fmaf(g, I[0], pw*d[4]);
+      du[1] = fmaf(g, I[1], pw*d[5]);
+      du[2] = pw*fmaf(d[3], ln, d[6]);
+    }
+  }
+};
+
+// ---- Aggregate(Lambertian, M) with the specular lobe M described by a lobe policy ------------------------------------
+// fit parameters in attribute order: albedo rgb, scale rgb, the lobe's parameters
+template<class M, class LP, int SPT = 8> struct CompactPair
 {
   using Model = M;
   static constexpr int kSPT = SPT, kThreads = 1024/SPT;        // samples per thread x threads = one tile of 1024 samples
   static constexpr int NRAW = 3 + M::NA;                       // attribute floats of a parameter set
-  static constexpr int P = 6 + DG::NP + CF::NP, C = 1 + P;
-  static constexpr int OFF_DG = 6, OFF_F = 6 + DG::NS, NSET = (6 + DG::NS + CF::NS + 3) & ~3;
-  static_assert(NRAW == 6 + DG::NP + CF::NP && M::SCALE == 0, "every attribute is a fit parameter; leading scale");
-  struct Sample { float I[DG::NI]; float fc, cm, w, wc, r[3]; };
+  static constexpr int P = 6 + LP::NP, C = 1 + P;
+  static constexpr int OFF_LP = 6, NSET = (6 + LP::NS + 3) & ~3;
+  static_assert(NRAW == 6 + LP::NP && M::SCALE == 0, "every attribute is a fit parameter; leading scale");
+  struct Sample { float I[LP::NI]; float cm, w, wc, r[3]; };
 
   BBMCU_D static void set(const float* raw, float* d)
   {
@@ -189,41 +331,30 @@ template<class M, class DG, class CF, int SPT = 8> struct CompactPair
     for(int i=0; i < NSET; ++i) d[i] = 0.0f;
     d[0] = raw[0]*kInvPi; d[1] = raw[1]*kInvPi; d[2] = raw[2]*kInvPi;
     d[3] = raw[3]; d[4] = raw[4]; d[5] = raw[5];
-    DG::set(raw + 3 + M::OFF_NDF, d + OFF_DG);
-    CF::set(raw + 3 + M::OFF_F, d + OFF_F);
+    LP::set(raw + 6, d + OFF_LP);
   }
   // factor of column j of the block partial: the per-sample sums leave out 2 (d e / d v) and 1/pi (d v / d albedo)
   BBMCU_HD static double col_scale(int j) { return j == 0 ? 1.0 : (j <= 3 ? 2.0/kPiD : 2.0); }
 
   // direction-only part of a sample.  state: 0 regular, 1 padding (past the end of the shard), 2 below the horizon - both
   // lobes are zero there (lambertian.h:38-44, microfacet.h:74-81), so the term does not depend on the parameters: the
-  // sample is neutral in the per-set loop (w = 0) and keeps (cos_i, weight) in I[0], I[1] for below_const()
+  // sample is neutral in the per-set loop (cos_i and the measured value read as 0, the lobe at its zero) and keeps the
+  // weight in `w` and the true cos_i in `wc` for below_const()
   BBMCU_D static Sample make_geom(int metric, f3 in, f3 out, bool live, int& state)
   {
     Sample s;
-#pragma unroll
-    for(int i=0; i < DG::NI; ++i) s.I[i] = 0.0f;
-    s.fc = CF::inv(0.5f); s.cm = 0.0f; s.w = 0.0f; s.wc = 0.0f; s.r[0] = s.r[1] = s.r[2] = 0.0f;
+    LP::zero(s.I);
+    s.cm = 0.0f; s.w = 0.0f; s.wc = 0.0f; s.r[0] = s.r[1] = s.r[2] = 0.0f;
     state = 1;
     if(!live) return s;
     const float cm = fmaxf(in.z, 0.0f), w = metric_weight(metric, in, out);
     if(!((in.z >= 0.0f) && (out.z >= 0.0f)))
     {
-      static_assert(DG::NI >= 2, "two floats to keep the cosine and the weight of a below-horizon sample");
-      s.I[0] = cm; s.I[1] = fminf(w, 3.0e38f); state = 2;
+      s.w = fminf(w, 3.0e38f); s.wc = cm; state = 2;             // cm = 0 and r = 0 make every term of the per-set loop vanish
       return s;
     }
     state = 0;
-    if((in.z > 0.0f) && (out.z > 0.0f))
-    {
-      const f3 h = halfway(in, out);
-      const float inh = dot(in, h), outh = dot(out, h);
-      if((inh > 0.0f) && (outh > 0.0f))
-      {
-        DG::inv(in, out, h, inh, outh, q_rcp((float)M::norm() * (in.z*out.z)), s.I);
-        s.fc = CF::inv(0.5f*(inh + outh));
-      }
-    }
+    LP::inv(in, out, s.I);
     s.cm = cm; s.w = w; s.wc = w*cm;
     return s;
   }
@@ -233,14 +364,12 @@ template<class M, class DG, class CF, int SPT = 8> struct CompactPair
     if(LOG) { s.r[0] = regular ? logf(1.0f + ref.r*s.cm) : 0.0f; s.r[1] = regular ? logf(1.0f + ref.g*s.cm) : 0.0f; s.r[2] = regular ? logf(1.0f + ref.b*s.cm) : 0.0f; }
     else    { s.r[0] = regular ? ref.r*s.cm : 0.0f; s.r[1] = regular ? ref.g*s.cm : 0.0f; s.r[2] = regular ? ref.b*s.cm : 0.0f; }
   }
-  BBMCU_D static float below_const(int metric, const Sample& s, const Spec<float>& ref) { return loss_term_g(metric, s.I[0], s.I[1], Spec<float>(0.0f), ref, nullptr); }
+  BBMCU_D static float below_const(int metric, const Sample& s, const Spec<float>& ref) { return loss_term_g(metric, s.wc, s.w, Spec<float>(0.0f), ref, nullptr); }
 
   template<bool WG, bool LOG> BBMCU_D static void accumulate(const float* d, const Sample& s, float* acc)
   {
-    float DGv, dDG[DG::NP], Fv, dF[CF::NP];
-    DG::template eval<WG>(d + OFF_DG, s.I, DGv, dDG);
-    CF::template eval<WG>(d + OFF_F, s.fc, Fv, dF);
-    const float u = DGv*Fv;
+    float u, du[LP::NP];
+    LP::template eval<WG>(d + OFF_LP, s.I, u, du);
     const float v0 = fmaf(d[3], u, d[0]), v1 = fmaf(d[4], u, d[1]), v2 = fmaf(d[5], u, d[2]);
     float t0, t1, t2, k0, k1, k2;
     if(LOG)
@@ -262,9 +391,7 @@ template<class M, class DG, class CF, int SPT = 8> struct CompactPair
       acc[4] = fmaf(e0, u, acc[4]); acc[5] = fmaf(e1, u, acc[5]); acc[6] = fmaf(e2, u, acc[6]);
       const float sdv = fmaf(e2, d[5], fmaf(e1, d[4], e0*d[3]));
 #pragma unroll
-      for(int j=0; j < DG::NP; ++j) acc[7 + j] = fmaf(sdv, dDG[j]*Fv, acc[7 + j]);
-#pragma unroll
-      for(int j=0; j < CF::NP; ++j) acc[7 + DG::NP + j] = fmaf(sdv, DGv*dF[j], acc[7 + DG::NP + j]);
+      for(int j=0; j < LP::NP; ++j) acc[7 + j] = fmaf(sdv, du[j], acc[7 + j]);
     }
   }
 };
@@ -272,14 +399,21 @@ template<class M, class DG, class CF, int SPT = 8> struct CompactPair
 // which specular lobes have a compact pair kernel
 template<class M> struct CompactOf { static constexpr bool value = false; };
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>>
-{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>, CDGBeckmannVGroove<NRM>, CFCook>; };
+{ using M = Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>; static constexpr bool value = true; using type = CompactPair<M, LPMicrofacet<M, CDGBeckmannVGroove<NRM>, CFCook>>; };
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>>
-{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>, CDGBeckmannVGroove<NRM>, CFSchlick>; };
-
+{ using M = Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>; static constexpr bool value = true; using type = CompactPair<M, LPMicrofacet<M, CDGBeckmannVGroove<NRM>, CFSchlick>>; };
 template<int NORM> struct CompactOf<Microfacet<NdfLow, GVGroove, FresnelCookIor, NORM, true>>
-{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfLow, GVGroove, FresnelCookIor, NORM, true>, CDGLowVGroove, CFCook>; };
+{ using M = Microfacet<NdfLow, GVGroove, FresnelCookIor, NORM, true>; static constexpr bool value = true; using type = CompactPair<M, LPMicrofacet<M, CDGLowVGroove, CFCook>>; };
 template<int NORM> struct CompactOf<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>>
-{ static constexpr bool value = true; using type = CompactPair<Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>, CDGGgxSmith, CFCook, 4>; };
+{ using M = Microfacet<NdfGGX<false>, GUncorrelated, FresnelCookIor, NORM, true>; static constexpr bool value = true; using type = CompactPair<M, LPMicrofacet<M, CDGGgxSmith, CFCook>, 4>; };
+template<> struct CompactOf<AshikhminShirley<FresnelSchlickR0, false, true>>
+{ using M = AshikhminShirley<FresnelSchlickR0, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFSchlick>>; };
+template<> struct CompactOf<AshikhminShirley<FresnelCookIor, false, true>>
+{ using M = AshikhminShirley<FresnelCookIor, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFCook>>; };
+template<> struct CompactOf<Phong> { static constexpr bool value = true; using type = CompactPair<Phong, LPPhong<Phong>>; };
+template<> struct CompactOf<Lafortune<false, true>> { static constexpr bool value = true; using type = CompactPair<Lafortune<false, true>, LPNganLafortune<Lafortune<false, true>>>; };
+
+constexpr int kCThreads = 128, kCSPT = 8;     // the default shape (CompactPair<..., SPT = 8>)
 
 #ifdef __CUDACC__
 

@@ -325,7 +325,7 @@ def test_host_path_with_narrowed_and_derived_outputs_equals_device_path(ctx, s):
 # ---- compact pair loss kernel (bbmcu_losscompact.cuh) -----------------------------------------------------------------------------
 @pytest.mark.parametrize("metric", ["nganL2", "lowL2", "bieronL2", "lowLog", "bieronLog", "standardLog"])
 def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
-    """Aggregate(Lambertian, Cook-Torrance family / GGX / LowMicrofacet) runs the compact kernel (per-sample invariants, per-set constants, closed-form
+    """Aggregate(Lambertian, Cook-Torrance family / GGX / LowMicrofacet / isotropic Ashikhmin-Shirley / Phong / NganLafortune) runs the compact kernel (per-sample invariants, per-set constants, closed-form
     jacobian); BBMCU_LOSS_NO_COMPACT=1 keeps the generic dual-number tile kernel.  Both on the full MERL grid, a shard of it
     and a spherical grid, with and without gradient, K = 1 / 7 / 40 parameter sets: equal to float rounding of the terms."""
     import bbm_b200 as bb
@@ -334,7 +334,11 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
     for fitted in ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.1, 1.6))",
                    "Aggregate(Lambertian(), LowCookTorrance())", "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganCookTorrance([0.4, 0.5, 0.6], 0.1, 0.2))",
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), GGX([0.4, 0.5, 0.6], 0.1, 1.6))",
-                   "Aggregate(Lambertian([0.1, 0.1, 0.3]), LowMicrofacetFit([51.7, 37.9, 27.4], 10482.1, 0.8167, 2.2365))"):
+                   "Aggregate(Lambertian([0.1, 0.1, 0.3]), LowMicrofacetFit([51.7, 37.9, 27.4], 10482.1, 0.8167, 2.2365))",
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganAshikhminShirley([0.4, 0.5, 0.6], 0.1, 80.0))",
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowAshikhminShirley([0.4, 0.5, 0.6], 1.6, 2000.0))",
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganBlinnPhong([0.4, 0.5, 0.6], 60.0))",
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))"):
         fb = bb.Bsdf(fitted)
         p0 = fb.parameter_values()
         for grid, first, count in ((None, 0, 0), (None, 400_001, 300_007), (bb.spherical_grid((31, 16), (5, 9)), 0, 0)):

@@ -15,6 +15,12 @@ CASES = [
     ("Aggregate(Lambertian([0.1, 0.1, 0.3]), GGX([1.4, 1.5, 0.9], 0.02, 1.3))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), GGX([1.0, 1.3, 1.1], 0.03, 1.25))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowMicrofacet([0.4, 0.5, 0.6], 300.0, 1.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowMicrofacet([0.5, 0.4, 0.7], 200.0, 1.5, 1.4))"),
     ("Aggregate(Lambertian([0.1, 0.1, 0.3]), LowMicrofacetFit([51.7, 37.9, 27.4], 10482.1, 0.8167, 2.2365))", "Aggregate(Lambertian([0.12, 0.1, 0.25]), LowMicrofacetFit([40.0, 30.0, 30.0], 20000.0, 0.9, 1.8))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganAshikhminShirley([0.4, 0.5, 0.6], 0.1, 80.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganAshikhminShirley([0.5, 0.4, 0.7], 0.2, 120.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowAshikhminShirley([0.4, 0.5, 0.6], 1.6, 2000.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowAshikhminShirley([0.5, 0.4, 0.7], 1.4, 1500.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganBlinnPhong([0.4, 0.5, 0.6], 60.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), Phong([0.5, 0.4, 0.7], 90.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), Phong([0.4, 0.5, 0.6], 900.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), Phong([0.5, 0.4, 0.7], 700.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 60.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.55, 0.6, 150.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 100.0))"),
     # total internal reflection inside the Fresnel term (eta < 1): g clamps to zero, F = 1
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.2, 0.9))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
 ]
@@ -58,5 +64,5 @@ def test_compact_loss_equals_generic_on_host(hostsim, case):
 def test_models_without_compact_kernel_report_so(hostsim):
     i, o = _samples(hostsim, 16, 1)
     ref = np.zeros((16, 3), np.float32)
-    assert hostsim.loss_compact("Aggregate(Lambertian([0.3, 0.2, 0.1]), Phong([0.4, 0.5, 0.6], 20))", 0, i, o, ref) is None
+    assert hostsim.loss_compact("Aggregate(Lambertian([0.3, 0.2, 0.1]), Ward([0.4, 0.5, 0.6], [0.2, 0.3]))", 0, i, o, ref) is None
     assert hostsim.loss_compact("CookTorrance([0.4, 0.5, 0.6], 0.2, 1.6)", 0, i, o, ref) is None

@@ -22,8 +22,8 @@ ctx = bb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda:0"))
 truth = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), CookTorrance([0.3,0.3,0.3], 0.2, 1.5))")
 rows = []
-for model in args.models.split(","):
-    fitted = bb.Bsdf("Aggregate(Lambertian(), %s())" % model)
+for model in args.models.split(";" if ";" in args.models else ","):
+    fitted = bb.Bsdf("Aggregate(Lambertian(), %s)" % (model if "(" in model else model + "()"))
     p0 = fitted.parameter_values()
     for metric in ("nganL2", "standardLog"):
         L = ctx.loss(metric, truth, None, first=0, count=(bb.MERL_BINS + args.div - 1) // args.div)
@@ -31,7 +31,7 @@ for model in args.models.split(","):
             rng = np.random.default_rng(7)
             params = p0[None] * (1 + 0.1 * rng.random((K, len(p0))))
             res = torch.zeros((K, 1 + len(p0)), device="cuda:0", dtype=torch.float64)
-            row = {"model": model, "metric": metric, "K": K, "shard": "1/%d" % args.div}
+            row = {"model": model.split("(")[0], "metric": metric, "K": K, "shard": "1/%d" % args.div}
             for name, env in (("compact", None), ("generic", "1")):
                 if env:
                     os.environ["BBMCU_LOSS_NO_COMPACT"] = env
