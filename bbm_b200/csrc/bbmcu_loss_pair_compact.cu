@@ -24,6 +24,7 @@ bool launch_loss_pair_compact(int model, cudaStream_t s, const LossArgs& a, unsi
     case M_Phong:            return try_compact<M_Phong>(s, a, K);
     case M_NganBlinnPhong:   return try_compact<M_NganBlinnPhong>(s, a, K);
     case M_NganLafortune:    return try_compact<M_NganLafortune>(s, a, K);
+    case M_LowSmooth:        return try_compact<M_LowSmooth>(s, a, K);
     default: return false;
   }
 }

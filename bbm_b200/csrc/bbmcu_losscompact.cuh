@@ -313,6 +313,33 @@ template<class M> struct LPNganLafortune
   }
 };
 
+// Low et al. 2012 smooth-surface lobe (lowsmooth.h:50-70): u = S Q,  S = (1 + B Dp^2)^-C,  Q = fresnel::cook(eta, cos_D);
+// attributes after the scale A: B, C, eta.  Same exponent range as CDGLowVGroove (C of order one).
+template<class M> struct LPLowSmooth
+{
+  static constexpr int NS = 2 + CFCook::NS, NP = 3, NI = 2;
+  static_assert(M::SCALE == 0 && M::NA == 6, "scale, B, C, eta");
+  BBMCU_D static void set(const float* a, float* d) { d[0] = a[0]; d[1] = a[1]; CFCook::set(a + 2, d + 2); }
+  BBMCU_D static void zero(float* I) { I[0] = 0.0f; I[1] = 0.5f; }
+  // the lobe lives on in.z >= 0, out.z >= 0 - the caller's domain
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    const float sx = in.x + out.x, sy = in.y + out.y, dx = in.x - out.x, dy = in.y - out.y;
+    I[0] = sx*sx + sy*sy;
+    I[1] = (float)safe_sqrt_d(1.0 - 0.25*(double)(dx*dx + dy*dy));
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    const float b = fmaf(d[0], I[0], 1.0f);
+    const float L = c_lg2(b);
+    const float S = c_ex2(-d[1]*L);
+    float Q, dQ[1];
+    CFCook::template eval<WG>(d + 2, I[1], Q, dQ);
+    u = S*Q;
+    if(WG) { du[0] = -(d[1]*u)*(I[0]*q_rcp(b)); du[1] = -u*(L*0.69314718055994530942f); du[2] = S*dQ[0]; }
+  }
+};
+
 // ---- Aggregate(Lambertian, M) with the specular lobe M described by a lobe policy ------------------------------------
 // fit parameters in attribute order: albedo rgb, scale rgb, the lobe's parameters
 template<class M, class LP, int SPT = 8> struct CompactPair
@@ -410,6 +437,7 @@ template<> struct CompactOf<AshikhminShirley<FresnelSchlickR0, false, true>>
 { using M = AshikhminShirley<FresnelSchlickR0, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFSchlick>>; };
 template<> struct CompactOf<AshikhminShirley<FresnelCookIor, false, true>>
 { using M = AshikhminShirley<FresnelCookIor, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFCook>>; };
+template<> struct CompactOf<LowSmooth> { static constexpr bool value = true; using type = CompactPair<LowSmooth, LPLowSmooth<LowSmooth>>; };
 template<> struct CompactOf<Phong> { static constexpr bool value = true; using type = CompactPair<Phong, LPPhong<Phong>>; };
 template<> struct CompactOf<Lafortune<false, true>> { static constexpr bool value = true; using type = CompactPair<Lafortune<false, true>, LPNganLafortune<Lafortune<false, true>>>; };
 

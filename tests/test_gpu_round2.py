@@ -338,7 +338,8 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganAshikhminShirley([0.4, 0.5, 0.6], 0.1, 80.0))",
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowAshikhminShirley([0.4, 0.5, 0.6], 1.6, 2000.0))",
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganBlinnPhong([0.4, 0.5, 0.6], 60.0))",
-                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))"):
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))",
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))"):
         fb = bb.Bsdf(fitted)
         p0 = fb.parameter_values()
         for grid, first, count in ((None, 0, 0), (None, 400_001, 300_007), (bb.spherical_grid((31, 16), (5, 9)), 0, 0)):

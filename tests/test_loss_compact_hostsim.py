@@ -21,6 +21,7 @@ CASES = [
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), Phong([0.4, 0.5, 0.6], 900.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), Phong([0.5, 0.4, 0.7], 700.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 60.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.55, 0.6, 150.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 100.0))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowSmooth([50.0, 40.0, 70.0], 2000.0, 1.5, 1.4))"),
     # total internal reflection inside the Fresnel term (eta < 1): g clamps to zero, F = 1
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.2, 0.9))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
 ]
