@@ -25,6 +25,8 @@ bool launch_loss_pair_compact(int model, cudaStream_t s, const LossArgs& a, unsi
     case M_NganBlinnPhong:   return try_compact<M_NganBlinnPhong>(s, a, K);
     case M_NganLafortune:    return try_compact<M_NganLafortune>(s, a, K);
     case M_LowSmooth:        return try_compact<M_LowSmooth>(s, a, K);
+    case M_NganWard:         return try_compact<M_NganWard>(s, a, K);
+    case M_NganWardDuer:     return try_compact<M_NganWardDuer>(s, a, K);
     default: return false;
   }
 }

@@ -313,6 +313,35 @@ template<class M> struct LPNganLafortune
   }
 };
 
+// isotropic Ward lobes (ward.h:45-60, wardduer.h:55-70; the NganWard / NganWardDuer fits): with H = in + out (not normalised)
+//   u = exp(-T / alpha^2) / (4 pi alpha^2 w),  T = (H_x^2 + H_y^2) / H_z^2,  w = sqrt(z_i z_o) (Ward) or z_i z_o (Duer)
+//   d u / d alpha = u (2 T / alpha^3 - 2 / alpha)
+// At the horizon (z = 0) 1 / w is infinite and the reference returns Inf or NaN: nothing is clamped here, the
+// loss of a grid that touches the horizon is non-finite in both.
+template<class M, int VARIANT> struct LPWardIso
+{
+  static constexpr int NS = 4, NP = 1, NI = 2;
+  static_assert(M::SCALE == 0 && M::NA == 4 && VARIANT <= 1, "scale, roughness");
+  BBMCU_D static void set(const float* a, float* d)
+  {
+    const float al = a[0], ia2 = 1.0f/(al*al);
+    d[0] = -1.44269504088896340736f*ia2; d[1] = ia2; d[2] = -2.0f/al; d[3] = 2.0f*ia2/al;
+  }
+  BBMCU_D static void zero(float* I) { I[0] = 0.0f; I[1] = 0.0f; }
+  // the lobe lives on in.z >= 0, out.z >= 0 - the caller's domain
+  BBMCU_D static void inv(f3 in, f3 out, float* I)
+  {
+    const f3 H = in + out;
+    I[0] = (H.x*H.x + H.y*H.y)/(H.z*H.z);
+    I[1] = 1.0f/(M::kFourPi * (VARIANT == 0 ? sqrtf(in.z*out.z) : in.z*out.z));
+  }
+  template<bool WG> BBMCU_D static void eval(const float* d, const float* I, float& u, float (&du)[NP])
+  {
+    u = (c_ex2(I[0]*d[0])*I[1])*d[1];
+    if(WG) du[0] = u*fmaf(I[0], d[3], d[2]);
+  }
+};
+
 // Low et al. 2012 smooth-surface lobe (lowsmooth.h:50-70): u = S Q,  S = (1 + B Dp^2)^-C,  Q = fresnel::cook(eta, cos_D);
 // attributes after the scale A: B, C, eta.  Same exponent range as CDGLowVGroove (C of order one).
 template<class M> struct LPLowSmooth
@@ -437,6 +466,8 @@ template<> struct CompactOf<AshikhminShirley<FresnelSchlickR0, false, true>>
 { using M = AshikhminShirley<FresnelSchlickR0, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFSchlick>>; };
 template<> struct CompactOf<AshikhminShirley<FresnelCookIor, false, true>>
 { using M = AshikhminShirley<FresnelCookIor, false, true>; static constexpr bool value = true; using type = CompactPair<M, LPAshikhminShirleyIso<M, CFCook>>; };
+template<> struct CompactOf<Ward<false, 0>> { static constexpr bool value = true; using type = CompactPair<Ward<false, 0>, LPWardIso<Ward<false, 0>, 0>>; };
+template<> struct CompactOf<Ward<false, 1>> { static constexpr bool value = true; using type = CompactPair<Ward<false, 1>, LPWardIso<Ward<false, 1>, 1>>; };
 template<> struct CompactOf<LowSmooth> { static constexpr bool value = true; using type = CompactPair<LowSmooth, LPLowSmooth<LowSmooth>>; };
 template<> struct CompactOf<Phong> { static constexpr bool value = true; using type = CompactPair<Phong, LPPhong<Phong>>; };
 template<> struct CompactOf<Lafortune<false, true>> { static constexpr bool value = true; using type = CompactPair<Lafortune<false, true>, LPNganLafortune<Lafortune<false, true>>>; };

@@ -358,6 +358,25 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
                 assert np.all(np.abs(vc - lg) <= 2e-5 * np.abs(lg)) and np.all(np.abs(vg - lg) <= 2e-5 * np.abs(lg))
                 tol = 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=1, keepdims=True)
                 assert np.all(np.abs(gc - gg) <= tol), (fitted, metric, K, np.abs(gc - gg).max(), gc[0], gg[0])
+    # the isotropic Ward lobes: Inf / NaN at the horizon like the reference (non-finite loss over the MERL grid in both kernels);
+    # compared on a grid that stays off it
+    hp = float(np.float32(2) * np.float32(np.pi))
+    off_horizon = bb.spherical_grid((31, 12), (6, 9), start_in=(0, 0.05), start_out=(0, 0.05), end_in=(hp, 1.4), end_out=(hp, 1.4))
+    for fitted in ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWard([0.4, 0.5, 0.6], 0.2))", "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWardDuer([0.4, 0.5, 0.6], 0.05))"):
+        fb = bb.Bsdf(fitted)
+        p0 = fb.parameter_values()
+        params = p0[None] * (1 + 0.05 * rng.random((9, len(p0))))
+        assert not np.isfinite(ctx.loss(metric, truth, None)(fb, params)).any()
+        L = ctx.loss(metric, truth, off_horizon)
+        lc, gc = L(fb, params, grad=True)
+        os.environ["BBMCU_LOSS_NO_COMPACT"] = "1"
+        try:
+            lg, gg = L(fb, params, grad=True)
+            assert not np.isfinite(ctx.loss(metric, truth, None)(fb, params)).any()
+        finally:
+            del os.environ["BBMCU_LOSS_NO_COMPACT"]
+        assert np.all(np.abs(lc - lg) <= 2e-5 * np.abs(lg)), (fitted, metric, lc, lg)
+        assert np.all(np.abs(gc - gg) <= 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=1, keepdims=True)), (fitted, metric)
     # a parameter set's result does not depend on what else shares the launch (block partials per (set, tile), fixed order)
     L = ctx.loss(metric, truth, None)
     fb = bb.Bsdf("Aggregate(Lambertian(), CookTorrance())")

@@ -22,6 +22,9 @@ CASES = [
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 60.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.55, 0.6, 150.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 100.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowSmooth([50.0, 40.0, 70.0], 2000.0, 1.5, 1.4))"),
+    # Ward lobes are Inf / NaN at the horizon in the reference: their samples stay off it (NO_HORIZON below)
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWard([0.4, 0.5, 0.6], 0.2))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganWard([0.5, 0.4, 0.7], 0.15))"),
+    ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWardDuer([0.4, 0.5, 0.6], 0.05))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganWardDuer([0.5, 0.4, 0.7], 0.07))"),
     # total internal reflection inside the Fresnel term (eta < 1): g clamps to zero, F = 1
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), CookTorrance([0.4, 0.5, 0.6], 0.2, 0.9))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
 ]
@@ -48,6 +51,11 @@ def test_compact_loss_equals_generic_on_host(hostsim, case):
     P = len(bb.Bsdf(fitted).parameter_values())
     i, o = _samples(hostsim, 6000, case)
     assert (i[:, 2] < 0).any() and (o[:, 2] < 0).any() and (i[:, 2] == 0).any()      # the below-horizon constant and the clamped bins are exercised
+    if "Ward" in fitted:
+        keep = (np.abs(i[:, 2]) > 1e-3) & (np.abs(o[:, 2]) > 1e-3)
+        bad = hostsim.loss_compact(fitted, 0, i, o, hostsim.eval(truth, i, o), nparams=P)
+        assert not np.isfinite(bad[0]) and not np.isfinite(hostsim.loss(fitted, 0, i, o, hostsim.eval(truth, i, o), nparams=P)[0])     # non-finite in both at the horizon
+        i, o = i[keep], o[keep]
     ref = hostsim.eval(truth, i, o)
     for m, name in enumerate(METRICS):
         want, wg, _ = hostsim.loss(fitted, m, i, o, ref, nparams=P)

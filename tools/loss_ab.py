@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
 ap.add_argument("--div", type=int, default=1)
 ap.add_argument("--models", default="CookTorrance,NganCookTorrance")
+ap.add_argument("--grid", default="merl", help="merl, or offhorizon: a 31 x 12 x 6 x 9 spherical grid that stays off the horizon (Ward lobes)")
 args = ap.parse_args()
 ctx = bb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda:0"))
@@ -26,7 +27,11 @@ for model in args.models.split(";" if ";" in args.models else ","):
     fitted = bb.Bsdf("Aggregate(Lambertian(), %s)" % (model if "(" in model else model + "()"))
     p0 = fitted.parameter_values()
     for metric in ("nganL2", "standardLog"):
-        L = ctx.loss(metric, truth, None, first=0, count=(bb.MERL_BINS + args.div - 1) // args.div)
+        if args.grid == "merl":
+            L = ctx.loss(metric, truth, None, first=0, count=(bb.MERL_BINS + args.div - 1) // args.div)
+        else:
+            hp = float(np.float32(2) * np.float32(np.pi))
+            L = ctx.loss(metric, truth, bb.spherical_grid((62, 24), (24, 18), start_in=(0, 0.05), start_out=(0, 0.05), end_in=(hp, 1.4), end_out=(hp, 1.4)))
         for K in (1, 16, 256):
             rng = np.random.default_rng(7)
             params = p0[None] * (1 + 0.1 * rng.random((K, len(p0))))
