@@ -472,15 +472,17 @@ int bbmcu_loss_eval_multi_ex(bbmcu_loss* L, const bbmcu_bsdf* bsdf, const double
     if(n > 0)
     {
       const int m0 = shape.model[0];
-      if(shape.n_lobes == 1 && !shape.aggregate)
+      const char* nc = std::getenv("BBMCU_LOSS_NO_COMPACT");     // read per call: tests compare the two kernels in one process
+      const bool no_compact = nc && *nc && *nc != '0';
+      // the compact kernel (bbmcu_losscompact.cuh) where the lobe has one and both components are asked for
+      if(shape.n_lobes == 1 && !shape.aggregate && !no_compact && a.component == FLAG_ALL) done = launch_loss_single_compact(m0, ctx->stream, a, (unsigned)Kper);
+      if(done) {}
+      else if(shape.n_lobes == 1 && !shape.aggregate)
         done = launch_loss_single_g0(m0, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_single_g1(m0, ctx->stream, a, bx, (unsigned)Kper) ||
                launch_loss_single_g2(m0, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_single_g3(m0, ctx->stream, a, bx, (unsigned)Kper);
       else if(shape.n_lobes == 2 && shape.aggregate && m0 == M_Lambertian)
       {
         const int m1 = shape.model[1];
-        // the compact kernel (bbmcu_losscompact.cuh) where the specular lobe has one and both components are asked for
-        const char* nc = std::getenv("BBMCU_LOSS_NO_COMPACT");     // read per call: tests compare the two kernels in one process
-        const bool no_compact = nc && *nc && *nc != '0';
         if(!no_compact && a.component == FLAG_ALL) done = launch_loss_pair_compact(m1, ctx->stream, a, (unsigned)Kper);
         if(!done) done = launch_loss_pair_g0(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g1(m1, ctx->stream, a, bx, (unsigned)Kper) ||
                launch_loss_pair_g2(m1, ctx->stream, a, bx, (unsigned)Kper) || launch_loss_pair_g3(m1, ctx->stream, a, bx, (unsigned)Kper);

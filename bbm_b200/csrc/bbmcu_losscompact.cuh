@@ -369,28 +369,29 @@ template<class M> struct LPLowSmooth
   }
 };
 
-// ---- Aggregate(Lambertian, M) with the specular lobe M described by a lobe policy ------------------------------------
-// fit parameters in attribute order: albedo rgb, scale rgb, the lobe's parameters
-template<class M, class LP, int SPT = 8> struct CompactPair
+// ---- Aggregate(Lambertian, M) - or M alone (LAMB = false) - with the lobe M described by a lobe policy ----------------
+// fit parameters in attribute order: [albedo rgb,] scale rgb, the lobe's parameters
+template<class M, class LP, int SPT = 8, bool LAMB = true> struct CompactPair
 {
   using Model = M;
   static constexpr int kSPT = SPT, kThreads = 1024/SPT;        // samples per thread x threads = one tile of 1024 samples
-  static constexpr int NRAW = 3 + M::NA;                       // attribute floats of a parameter set
-  static constexpr int P = 6 + LP::NP, C = 1 + P;
+  static constexpr int L0 = LAMB ? 3 : 0;                      // attribute floats (and gradient columns) of the diffuse lobe
+  static constexpr int NRAW = L0 + M::NA;                      // attribute floats of a parameter set
+  static constexpr int P = L0 + 3 + LP::NP, C = 1 + P;
   static constexpr int OFF_LP = 6, NSET = (6 + LP::NS + 3) & ~3;
-  static_assert(NRAW == 6 + LP::NP && M::SCALE == 0, "every attribute is a fit parameter; leading scale");
+  static_assert(NRAW == L0 + 3 + LP::NP && M::SCALE == 0, "every attribute is a fit parameter; leading scale");
   struct Sample { float I[LP::NI]; float cm, w, wc, r[3]; };
 
   BBMCU_D static void set(const float* raw, float* d)
   {
 #pragma unroll
     for(int i=0; i < NSET; ++i) d[i] = 0.0f;
-    d[0] = raw[0]*kInvPi; d[1] = raw[1]*kInvPi; d[2] = raw[2]*kInvPi;
-    d[3] = raw[3]; d[4] = raw[4]; d[5] = raw[5];
-    LP::set(raw + 6, d + OFF_LP);
+    if(LAMB) { d[0] = raw[0]*kInvPi; d[1] = raw[1]*kInvPi; d[2] = raw[2]*kInvPi; }
+    d[3] = raw[L0]; d[4] = raw[L0 + 1]; d[5] = raw[L0 + 2];
+    LP::set(raw + L0 + 3, d + OFF_LP);
   }
   // factor of column j of the block partial: the per-sample sums leave out 2 (d e / d v) and 1/pi (d v / d albedo)
-  BBMCU_HD static double col_scale(int j) { return j == 0 ? 1.0 : (j <= 3 ? 2.0/kPiD : 2.0); }
+  BBMCU_HD static double col_scale(int j) { return j == 0 ? 1.0 : ((LAMB && j <= 3) ? 2.0/kPiD : 2.0); }
 
   // direction-only part of a sample.  state: 0 regular, 1 padding (past the end of the shard), 2 below the horizon - both
   // lobes are zero there (lambertian.h:38-44, microfacet.h:74-81), so the term does not depend on the parameters: the
@@ -443,17 +444,21 @@ template<class M, class LP, int SPT = 8> struct CompactPair
     if(WG)
     {
       const float e0 = t0*k0, e1 = t1*k1, e2 = t2*k2;        // (d e / d v) / 2
-      acc[1] += e0; acc[2] += e1; acc[3] += e2;
-      acc[4] = fmaf(e0, u, acc[4]); acc[5] = fmaf(e1, u, acc[5]); acc[6] = fmaf(e2, u, acc[6]);
+      if(LAMB) { acc[1] += e0; acc[2] += e1; acc[3] += e2; }
+      acc[L0 + 1] = fmaf(e0, u, acc[L0 + 1]); acc[L0 + 2] = fmaf(e1, u, acc[L0 + 2]); acc[L0 + 3] = fmaf(e2, u, acc[L0 + 3]);
       const float sdv = fmaf(e2, d[5], fmaf(e1, d[4], e0*d[3]));
 #pragma unroll
-      for(int j=0; j < LP::NP; ++j) acc[7 + j] = fmaf(sdv, du[j], acc[7 + j]);
+      for(int j=0; j < LP::NP; ++j) acc[L0 + 4 + j] = fmaf(sdv, du[j], acc[L0 + 4 + j]);
     }
   }
 };
 
-// which specular lobes have a compact pair kernel
+// which specular lobes have a compact kernel: CompactOf<M>::type for Aggregate(Lambertian, M), CompactSingleOf<M>::type for M alone
 template<class M> struct CompactOf { static constexpr bool value = false; };
+template<class CP> struct WithoutLambertian;
+template<class M, class LP, int SPT> struct WithoutLambertian<CompactPair<M, LP, SPT, true>> { using type = CompactPair<M, LP, SPT, false>; };
+template<class M, class = void> struct CompactSingleOf { static constexpr bool value = false; };
+template<class M> struct CompactSingleOf<M, typename std::enable_if<CompactOf<M>::value>::type> { static constexpr bool value = true; using type = typename WithoutLambertian<typename CompactOf<M>::type>::type; };
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>>
 { using M = Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelCookIor, NORM, true>; static constexpr bool value = true; using type = CompactPair<M, LPMicrofacet<M, CDGBeckmannVGroove<NRM>, CFCook>>; };
 template<bool NRM, int NORM> struct CompactOf<Microfacet<NdfBeckmann<false, NRM>, GVGroove, FresnelSchlickR0, NORM, true>>
@@ -657,8 +662,9 @@ template<class CL> static void launch_loss_compact_static(cudaStream_t s, const 
            else   k_loss_tile_compact<CL, false, false><<<grid, CL::kThreads, smem, s>>>(a, (int)K, sh.kpb, (int)sh.tiles, sh.mpb); }
 }
 
-// Aggregate(Lambertian, model) through the compact kernel; false if `model` has none (bbmcu_loss_pair_compact.cu)
+// Aggregate(Lambertian, model) - or the model alone - through the compact kernel; false if `model` has none (bbmcu_loss_pair_compact.cu)
 bool launch_loss_pair_compact(int model, cudaStream_t, const LossArgs&, unsigned K);
+bool launch_loss_single_compact(int model, cudaStream_t, const LossArgs&, unsigned K);
 #endif
 
 } // namespace bbmcu

@@ -477,6 +477,10 @@ def main():
         Lm = ctx.loss("nganL2", truth, None, materialise=True, **shard)
         mat_ms = timed(lambda: Lm.eval_device(fitted, params, res), nl)
         del Lm
+        # value only (what a derivative-free search such as bbm's compass asks for): this rank's shard, no collective
+        resv = torch.zeros((1, LOSS_K, 1 + P), device=dev, dtype=torch.float64)
+        val_ms = timed(lambda: L.eval_multi_device(fitted, params[None], resv, grad=False), nl)
+        del resv
         # the same pass through the generic dual-number tile kernel (what every model without a compact kernel runs)
         os.environ["BBMCU_LOSS_NO_COMPACT"] = "1"
         try:
@@ -494,6 +498,7 @@ def main():
                      "kernel": "compact pair kernel (bbmcu_losscompact.cuh): per-sample invariants, per-set constants, closed-form jacobian",
                      "passes_per_s_with_materialised_directions_no_collective": LOSS_K / (mat_ms * 1e-3),
                      "passes_per_s_generic_tile_kernel_no_collective": LOSS_K / (gen_ms * 1e-3),
+                     "value_only_passes_per_s_no_collective": LOSS_K / (val_ms * 1e-3),
                      "passes_per_s_with_nccl_all_reduce": (LOSS_K / (nccl_ms * 1e-3)) if nccl_ms else None,
                      "effective_gbs_at_12B_per_sample": passes * 12 * N / 1e9, "frac_of_hbm_roofline": passes * 12 * N / 1e9 / (world * peak),
                      "frac_note": "whole-job passes/s x 12 B x N / (n_gpus x measured HBM peak); the grid is L2-resident, the kernel is issue-bound",
@@ -660,7 +665,7 @@ def main():
                       "value_only_K1": {"passes_per_s": world * MD / (ms_v * 1e-3), "ms_per_launch": ms_v, "achieved_gbs_per_gpu": gbs(ms_v), "frac_of_hbm_roofline": gbs(ms_v) / peak},
                       "loss_grad_K1": {"passes_per_s": world * MD / (ms_g1 * 1e-3), "ms_per_launch": ms_g1, "achieved_gbs_per_gpu": gbs(ms_g1), "frac_of_hbm_roofline": gbs(ms_g1) / peak},
                       "loss_grad_K16": {"passes_per_s": world * MD * 16 / (ms_g * 1e-3), "ms_per_launch": ms_g},
-                      "note": "one launch = 64 materials x K parameter sets (grid z = material), 12 B x 1 458 000 per material read once per launch: "
+                      "note": "one launch = 64 materials x K parameter sets (a block's direction-only work serves all the materials of its group), 12 B x 1 458 000 per material read once per launch: "
                               "1.12 GB per GPU, far beyond the 126 MB L2 - the true-DRAM case of SURVEY 8(d); each rank holds its own 64 materials (weak scaling)"}
         del Lbig, res1, res16
         # (b) the fit sweep, split by material over the ranks; no collective

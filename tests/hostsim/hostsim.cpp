@@ -177,15 +177,18 @@ extern "C" int hostsim_loss_compact(const char* bsdf, int metric, const float* i
   try {
     auto b = bbmcu_host::parse_bsdf(bsdf);
     BsdfDesc d = make_desc(b);
-    if(!(d.n_lobes == 2 && d.aggregate && d.model[0] == M_Lambertian)) return 2;
+    const bool pair = d.n_lobes == 2 && d.aggregate && d.model[0] == M_Lambertian, single = d.n_lobes == 1 && !d.aggregate;
+    if(!pair && !single) return 2;
     bool done = false;
-    dispatch_model(d.model[1], [&](auto* tag) {
+    dispatch_model(d.model[pair ? 1 : 0], [&](auto* tag) {
       using M = typename std::remove_pointer<decltype(tag)>::type;
       if constexpr (CompactOf<M>::value)
       {
-        using CL = typename CompactOf<M>::type;
-        if(metric > METRIC_BIERON_L2) loss_compact_host<CL, true>(d, metric, in, out, ref, n, inv_n, loss, grad);
-        else loss_compact_host<CL, false>(d, metric, in, out, ref, n, inv_n, loss, grad);
+        using CP = typename CompactOf<M>::type;
+        using CS = typename CompactSingleOf<M>::type;
+        const bool lg = metric > METRIC_BIERON_L2;
+        if(pair) { if(lg) loss_compact_host<CP, true>(d, metric, in, out, ref, n, inv_n, loss, grad); else loss_compact_host<CP, false>(d, metric, in, out, ref, n, inv_n, loss, grad); }
+        else     { if(lg) loss_compact_host<CS, true>(d, metric, in, out, ref, n, inv_n, loss, grad); else loss_compact_host<CS, false>(d, metric, in, out, ref, n, inv_n, loss, grad); }
         done = true;
       }
     });

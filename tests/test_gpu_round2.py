@@ -339,7 +339,8 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowAshikhminShirley([0.4, 0.5, 0.6], 1.6, 2000.0))",
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganBlinnPhong([0.4, 0.5, 0.6], 60.0))",
                    "Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))",
-                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))"):
+                   "Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))",
+                   "CookTorrance([0.4, 0.5, 0.6], 0.1, 1.6)", "GGX([0.4, 0.5, 0.6], 0.1, 1.6)", "NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0)"):      # the lobe alone
         fb = bb.Bsdf(fitted)
         p0 = fb.parameter_values()
         for grid, first, count in ((None, 0, 0), (None, 400_001, 300_007), (bb.spherical_grid((31, 16), (5, 9)), 0, 0)):
@@ -356,7 +357,7 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
                     del os.environ["BBMCU_LOSS_NO_COMPACT"]
                 assert np.all(np.abs(lc - lg) <= 2e-5 * np.abs(lg)), (fitted, metric, K, lc, lg)
                 assert np.all(np.abs(vc - lg) <= 2e-5 * np.abs(lg)) and np.all(np.abs(vg - lg) <= 2e-5 * np.abs(lg))
-                tol = 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=1, keepdims=True)
+                tol = 1e-4 * np.abs(gg) + 1e-5 * np.abs(gg).max(axis=1, keepdims=True)      # (components that nearly cancel over 1.4 M float terms)
                 assert np.all(np.abs(gc - gg) <= tol), (fitted, metric, K, np.abs(gc - gg).max(), gc[0], gg[0])
     # the isotropic Ward lobes: Inf / NaN at the horizon like the reference (non-finite loss over the MERL grid in both kernels);
     # compared on a grid that stays off it

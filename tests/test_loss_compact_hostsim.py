@@ -22,6 +22,10 @@ CASES = [
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.58, 0.57, 40.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 60.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganLafortune([0.4, 0.5, 0.6], -0.55, 0.6, 150.0))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganLafortune([0.5, 0.4, 0.7], -0.6, 0.55, 100.0))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), LowSmooth([40.0, 50.0, 60.0], 3000.0, 1.2, 1.6))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), LowSmooth([50.0, 40.0, 70.0], 2000.0, 1.5, 1.4))"),
+    # single lobes (no Lambertian lobe in front)
+    ("CookTorrance([0.4, 0.5, 0.6], 0.2, 1.6)", "Aggregate(Lambertian([0.25, 0.22, 0.12]), CookTorrance([0.5, 0.4, 0.7], 0.15, 1.4))"),
+    ("GGX([0.4, 0.5, 0.6], 0.2, 1.6)", "GGX([0.5, 0.4, 0.7], 0.15, 1.4)"),
+    ("NganBlinnPhong([0.4, 0.5, 0.6], 60.0)", "Aggregate(Lambertian([0.25, 0.22, 0.12]), Phong([0.5, 0.4, 0.7], 90.0))"),
     # Ward lobes are Inf / NaN at the horizon in the reference: their samples stay off it (NO_HORIZON below)
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWard([0.4, 0.5, 0.6], 0.2))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganWard([0.5, 0.4, 0.7], 0.15))"),
     ("Aggregate(Lambertian([0.3, 0.2, 0.1]), NganWardDuer([0.4, 0.5, 0.6], 0.05))", "Aggregate(Lambertian([0.25, 0.22, 0.12]), NganWardDuer([0.5, 0.4, 0.7], 0.07))"),
@@ -74,4 +78,4 @@ def test_models_without_compact_kernel_report_so(hostsim):
     i, o = _samples(hostsim, 16, 1)
     ref = np.zeros((16, 3), np.float32)
     assert hostsim.loss_compact("Aggregate(Lambertian([0.3, 0.2, 0.1]), Ward([0.4, 0.5, 0.6], [0.2, 0.3]))", 0, i, o, ref) is None
-    assert hostsim.loss_compact("CookTorrance([0.4, 0.5, 0.6], 0.2, 1.6)", 0, i, o, ref) is None
+    assert hostsim.loss_compact("CookTorranceWalter([0.4, 0.5, 0.6], 0.2, 1.6)", 0, i, o, ref) is None

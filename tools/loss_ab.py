@@ -17,14 +17,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
 ap.add_argument("--div", type=int, default=1)
 ap.add_argument("--models", default="CookTorrance,NganCookTorrance")
+ap.add_argument("--single", action="store_true", help="the lobe alone instead of Aggregate(Lambertian(), lobe)")
 ap.add_argument("--grid", default="merl", help="merl, or offhorizon: a 31 x 12 x 6 x 9 spherical grid that stays off the horizon (Ward lobes)")
 args = ap.parse_args()
 ctx = bb.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda:0"))
 truth = bb.Bsdf("Aggregate(Lambertian([0.2,0.1,0.05]), CookTorrance([0.3,0.3,0.3], 0.2, 1.5))")
 rows = []
-for model in args.models.split(";" if ";" in args.models else ","):
-    fitted = bb.Bsdf("Aggregate(Lambertian(), %s)" % (model if "(" in model else model + "()"))
+for model in args.models.split(";" if (";" in args.models or "(" in args.models) else ","):
+    spec = model if "(" in model else model + "()"
+    fitted = bb.Bsdf(spec if args.single else "Aggregate(Lambertian(), %s)" % spec)
     p0 = fitted.parameter_values()
     for metric in ("nganL2", "standardLog"):
         if args.grid == "merl":
