@@ -213,7 +213,9 @@ public:
 std::mutex g_pool_mutex;                                        // one call at a time uses the pool
 HostPool& host_pool()
 {
-  static HostPool pool((int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2)));
+  // half the hardware threads, at most 16 (BBMCU_HOST_THREADS overrides: the loops are bound by the host's memory system)
+  static HostPool pool([] { const char* e = std::getenv("BBMCU_HOST_THREADS"); const int v = e ? std::atoi(e) : 0;
+                            return v > 0 ? std::min(v, 64) : (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / 2)); }());
   return pool;
 }
 // f(begin, end) over [0, n) on the pool's threads (small n: on the caller)

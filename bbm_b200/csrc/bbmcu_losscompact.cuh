@@ -626,6 +626,7 @@ inline CompactShape loss_compact_shape(size_t n, size_t K, size_t M, int nset, s
   size_t fine = 0;
   for(size_t ms = 1; ms <= M; ++ms)
     for(size_t ks = 1; ks <= K && ks <= 256; ++ks) { bool v; const double c = cost_of(ks, ms, v); if(v && c <= best*1.02 && ks*ms >= fine) { fine = ks*ms; bks = ks; bms = ms; } }
+  if(best == 0.0) { bms = M; bks = (K + max_sets - 1) / max_sets; }   // more sets than 256 ranges can stage (K > 256 x 512): as many ranges as it takes, one material per block
   r.kpb = (int)((K + bks - 1) / bks); r.mpb = (int)((M + bms - 1) / bms);
   r.ksplit = (unsigned)((K + r.kpb - 1) / r.kpb); r.msplit = (unsigned)((M + r.mpb - 1) / r.mpb);
   memo = {n, K, M, slots, nset, r, true};
