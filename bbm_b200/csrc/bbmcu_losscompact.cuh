@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(CL::kThreads, 512/CL::kThreads) k_loss_tile_co
 // launch shape: tiles x k-splits x material groups.  A block costs its tile's direction-only work once, per material the
 // reference planes, per (material, set) one evaluation; blocks are equal and `slots` of them are resident at a time, so
 // the launch takes ceil(blocks / slots) block durations: the (k-split, material-split) pair that minimises the product,
-// then the finest pair within 2 % of it (weights: instructions per sample from profiles/r02_s29_ncu_loss_tile_compact_ct.txt)
+// then the finest pair within 2 % of it (weights: instructions per sample from profiles/r02_s43_ncu_loss_tile_compact_ct.txt)
 struct CompactShape { unsigned tiles, ksplit, msplit; int kpb, mpb; };
 inline CompactShape loss_compact_shape(size_t n, size_t K, size_t M, int nset, size_t slots)
 {
