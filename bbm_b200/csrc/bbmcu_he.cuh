@@ -75,6 +75,10 @@ struct HeModel : NdfSamplerCdf<HeModel<V>>
   static constexpr int OFF_F = OFF_R + 2;
   static constexpr int NA = OFF_F + F::NA;
   static constexpr int NT = kHeCdfBins;                  // device-side CDF appended to the attribute block
+  // value-only batched losses take the all-float templates (bbmcu_lossop.cuh) - except Holzschuch's variant, whose ten-term series
+  // with the split exponent (one expf per term for the three channels) is already cheaper than three float exps per term
+  // (configs[4] sweep, seconds per rank: HeWestin 14.6 -> 7.0, NganHe 14.0 -> 4.8, He 8.1 -> 6.5, HeHolzschuch 7.4 -> 9.1)
+  static constexpr bool kQuickLossValue = (V != HE_VARIANT_HOLZSCHUCH);
 
   // ---- Eq. 24-25: mono-directional shadowing ---------------------------------------------------------
   template<class T, bool STRICT = false> BBMCU_D static T S1(f3 v, const T& rough, const T& tau)

@@ -75,12 +75,31 @@ template<class M> struct NonLinear { static constexpr int N = FitMap<M>::NFIT - 
 // that depends on the direction pair alone (half vector, dots).  The batched loss kernels compute it once per sample,
 // outside their loop over parameter sets.
 template<class...> struct VoidT { using type = void; };
+// models whose value-only loss passes evaluate the all-float form of their templates (Dual<0>) instead of eval<float> with the
+// reference's double spots: the He family, whose Taylor series (a double exp and float <-> double conversions per term and
+// channel) is two thirds of the configs[4] sweep.  Same value as the gradient kernels return (they carry it as the value part
+// of a dual number), within ~1e-5 of eval<float> per sample - the loss contract is 1e-4 on the total.
+template<class M, class = void> struct QuickLossValue { static constexpr bool value = false; };
+template<class M> struct QuickLossValue<M, typename std::enable_if<M::kQuickLossValue>::type> { static constexpr bool value = true; };
 template<class M, class = void> struct GeomOf
 {
   struct type {};
   BBMCU_D static type make(f3, f3) { return type(); }
   template<class T> BBMCU_D static Spec<T> eval_unscaled(const type&, f3 in, f3 out, const T* a, int component) { return M::template eval_unscaled<T>(in, out, a, component); }
-  BBMCU_D static Spec<float> eval(const type&, f3 in, f3 out, const float* a, int component) { return M::template eval<float>(in, out, a, component); }
+  BBMCU_D static Spec<float> eval(const type&, f3 in, f3 out, const float* a, int component)
+  {
+    if constexpr (QuickLossValue<M>::value)
+    {
+      Dual<0> ad[M::NA];
+#pragma unroll
+      for(int i=0; i < M::NA; ++i) ad[i] = Dual<0>(a[i]);
+      const Spec<Dual<0>> u = M::template eval_unscaled<Dual<0>>(in, out, ad, component);
+      Spec<float> r(u.r.v, u.g.v, u.b.v);
+      if(M::SCALE >= 0) r = r * load_spec(a + (M::SCALE >= 0 ? M::SCALE : 0));
+      return r;
+    }
+    else return M::template eval<float>(in, out, a, component);
+  }
 };
 template<class M> struct GeomOf<M, typename VoidT<typename M::Geom>::type>
 {

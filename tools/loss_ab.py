@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--out", default=None)
 ap.add_argument("--div", type=int, default=1)
 ap.add_argument("--models", default="CookTorrance,NganCookTorrance")
+ap.add_argument("--ks", default="1,16,256", help="parameter sets per launch")
+ap.add_argument("--reps", type=int, default=0, help="timed launches per measurement (0: 20, or 100 at K < 16)")
 ap.add_argument("--single", action="store_true", help="the lobe alone instead of Aggregate(Lambertian(), lobe)")
 ap.add_argument("--grid", default="merl", help="merl, or offhorizon: a 31 x 12 x 6 x 9 spherical grid that stays off the horizon (Ward lobes)")
 args = ap.parse_args()
@@ -34,7 +36,7 @@ for model in args.models.split(";" if (";" in args.models or "(" in args.models)
         else:
             hp = float(np.float32(2) * np.float32(np.pi))
             L = ctx.loss(metric, truth, bb.spherical_grid((62, 24), (24, 18), start_in=(0, 0.05), start_out=(0, 0.05), end_in=(hp, 1.4), end_out=(hp, 1.4)))
-        for K in (1, 16, 256):
+        for K in [int(k) for k in args.ks.split(",")]:
             rng = np.random.default_rng(7)
             params = p0[None] * (1 + 0.1 * rng.random((K, len(p0))))
             res = torch.zeros((K, 1 + len(p0)), device="cuda:0", dtype=torch.float64)
@@ -43,7 +45,7 @@ for model in args.models.split(";" if (";" in args.models or "(" in args.models)
                 if env:
                     os.environ["BBMCU_LOSS_NO_COMPACT"] = env
                 for grad in (True, False):
-                    reps = 20 if K >= 16 else 100
+                    reps = args.reps or (20 if K >= 16 else 100)
                     for _ in range(3):
                         L.eval_multi_device(fitted, params[None], res, grad=grad)
                     torch.cuda.synchronize()
