@@ -177,9 +177,17 @@ template<class M> struct LaunchMinBlocks<M, typename std::enable_if<(M::kLaunchM
 template<class M, class = void> struct LaunchMinBlocksFused { static constexpr int value = LaunchMinBlocks<M>::value; };
 template<class M> struct LaunchMinBlocksFused<M, typename std::enable_if<(M::kLaunchMinBlocksFused > 0)>::type> { static constexpr int value = M::kLaunchMinBlocksFused; };
 
+// models whose eval has parameter-only factors worth forming once per thread (M::precompute / M::eval_pre: Student-t)
+template<class M, class = void> struct ModelHasPre { static constexpr bool value = false; };
+template<class M> struct ModelHasPre<M, typename std::enable_if<M::kHasPre>::type> { static constexpr bool value = true; };
+
 template<class M>
 struct BsdfSingle
 {
+  static constexpr bool kHasPre = ModelHasPre<M>::value;
+  BBMCU_D static auto precompute(const BsdfDesc& b) { if constexpr (kHasPre) return M::precompute(b.attrs); else return 0; }
+  template<class PRE> BBMCU_D static Spec<float> eval_pre(const BsdfDesc& b, const PRE& q, f3 in, f3 out, int component)
+  { if constexpr (kHasPre) return M::eval_pre(in, out, b.attrs, component, q); else return M::template eval<float>(in, out, b.attrs, component); }
   static constexpr int kMinBlocks = LaunchMinBlocks<M>::value, kMinBlocksFused = LaunchMinBlocksFused<M>::value;
   static constexpr bool kAggregatePdfFromSample = false;
   static constexpr bool kTables = TableFloats<M>::N > 0;

@@ -124,6 +124,14 @@ template<class B> struct EvalOp
     for(int k=0; k < kVec; ++k) { Spec<float> s = B::eval(bsdf, a.get(k), b.get(k), component); r.set(k, make_f3(s.r, s.g, s.b)); }
     store4x3(rgb, i, n, ld, aligned, r);
   }
+  // the same with the model's parameter-only factors formed once per thread by the kernel (BsdfSingle<M>::precompute)
+  template<class PRE> BBMCU_D void group_pre(size_t i, const BsdfDesc& bsdf, const PRE& q) const
+  {
+    Lanes3 a = load4x3(in, i, n, ld, aligned), b = load4x3(out, i, n, ld, aligned), r;
+#pragma unroll
+    for(int k=0; k < kVec; ++k) { Spec<float> s = B::eval_pre(bsdf, q, a.get(k), b.get(k), component); r.set(k, make_f3(s.r, s.g, s.b)); }
+    store4x3(rgb, i, n, ld, aligned, r);
+  }
 };
 
 template<class B> struct PdfOp
@@ -376,6 +384,8 @@ template<class Op, class = void> struct OpUsesEpd { static constexpr bool value 
 template<class Op> struct OpUsesEpd<Op, typename VoidOf<typename Op::BsdfT>::type> { static constexpr bool value = UsesEpd<typename Op::BsdfT>::value; };
 template<class Op, class = void> struct OpFastPath { static constexpr bool value = false; };
 template<class Op> struct OpFastPath<Op, typename std::enable_if<Op::kFastPath>::type> { static constexpr bool value = true; };
+template<class Op, class = void> struct OpHasPre { static constexpr bool value = false; };
+template<class B> struct OpHasPre<EvalOp<B>, typename std::enable_if<B::kHasPre>::type> { static constexpr bool value = true; };
 template<class Op, class = void> struct UsesLinTab { static constexpr bool value = false; };
 template<class Op> struct UsesLinTab<Op, typename std::enable_if<Op::kLinTab>::type> { static constexpr bool value = true; };
 
@@ -422,6 +432,12 @@ template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks)
         for(size_t g = full + first; g < groups; g += stride) op.group(g * kVec, op.bsdf);
         return;
       }
+    }
+    if constexpr (OpHasPre<Op>::value)
+    {
+      const auto q = Op::BsdfT::precompute(op.bsdf);     // parameter-only factors of the model, once per thread
+      for(size_t g = first; g < groups; g += stride) op.group_pre(g * kVec, op.bsdf, q);
+      return;
     }
     for(size_t g = first; g < groups; g += stride) op.group(g * kVec, op.bsdf);
   }

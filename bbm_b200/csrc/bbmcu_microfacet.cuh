@@ -423,10 +423,48 @@ struct NdfStudentT
     float dn = n1 + v*(2.0f*n2 + v*3.0f*n3), dd = d1 + v*(2.0f*d2 + v*3.0f*d3);
     return chain(x, ratfit(v, n0, n1, n2, n3, d0, d1, d2, d3), (dn*den - num*dd)/(den*den));
   }
+  // The factors of G1 that depend on gamma alone (two rational fits, a powf, two tgammaf, a square root): with the
+  // parameters uniform over a launch the element-wise eval kernels form them once per thread (k_foreach4, Op::group_pre)
+  // instead of twice per evaluation.  G1<float> goes through the same two functions, so both routes give the same bits.
+  static constexpr bool kHasPre = true;
+  struct Pre { float F22, F23, S1s, tgr, sq; };
+  BBMCU_D static Pre pre(const float* a)
+  {
+    const float gamma = a[NA-1];
+    Pre q;
+    q.F22 = ratfit(gamma, 14.402f, -27.145f, 20.574f, -2.745f, -30.612f, 86.567f, -84.341f, 29.938f);
+    q.F23 = ratfit(gamma, -129.404f, 324.987f, -299.305f, 93.268f, -92.609f, 256.006f, -245.663f, 86.064f);
+    q.S1s = m_pow(gamma - 1.0f, gamma) / (2.0f*gamma - 3.0f);
+    q.tgr = m_tgamma(gamma - 0.5f) / m_tgamma(gamma) * kInvSqrtPi;
+    q.sq = m_sqrt(gamma - 1.0f);
+    return q;
+  }
+  BBMCU_D static float G1_core(f3 v, const float* a, const Pre& q)     // after the two early returns of G1
+  {
+    float ax, ay; Alpha2<ANISO>::get(a, ax, ay);
+    const float gamma = a[NA-1];
+    float sx = v.x*ax, sy = v.y*ay;
+    float z = v.z * m_rsqrt(sx*sx + sy*sy);
+    float S1 = m_pow((gamma - 1.0f) + z*z, 1.5f - gamma) / z;
+    float F21 = ratfit(z, 0.0f, 1.066f, 2.655f, 4.892f, 1.038f, 2.969f, 4.305f, 4.418f);
+    float F24 = ratfit(z, 6.537f, 6.074f, -0.623f, 5.223f, 6.538f, 6.103f, -3.218f, 6.347f);
+    float S2 = F21 * (q.F22 + q.F23*F24);
+    float lambda = q.tgr * (q.S1s*S1 + q.sq*S2) - 0.5f;
+    return 1.0f / (1.0f + lambda);
+  }
+  BBMCU_D static float G1_pre(f3 v, f3 m, const float* a, const Pre& q)
+  {
+    if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return 0.0f;
+    if(!(v.z < 0.99999988079071044921875f)) return 1.0f;
+    return G1_core(v, a, q);
+  }
   template<class T> BBMCU_D static T G1(f3 v, f3 m, const T* a)
   {
     if(!((v.z > 0.0f) && (dot(v, m) > 0.0f))) return T(0.0f);
     if(!(v.z < 0.99999988079071044921875f)) return T(1.0f);
+    if constexpr (std::is_same<T, float>::value) return G1_core(v, a, pre(a));
+    else
+    {
     T ax, ay; Alpha2<ANISO>::get(a, ax, ay);
     const T& gamma = a[NA-1];
     T sx = v.x*ax, sy = v.y*ay;
@@ -440,6 +478,7 @@ struct NdfStudentT
     T S1s = m_pow(gamma - 1.0f, gamma) / (2.0f*gamma - 3.0f);
     T lambda = m_tgamma(gamma - 0.5f) / m_tgamma(gamma) * kInvSqrtPi * (S1s*S1 + m_sqrt(gamma - 1.0f)*S2) - 0.5f;
     return 1.0f / (1.0f + lambda);
+    }
   }
   BBMCU_D static float pdf(f3, f3 m, const float* a)
   {
@@ -576,6 +615,9 @@ template<class NDF, class = void> struct HasSampleUnchecked { static constexpr b
 template<class NDF> struct HasSampleUnchecked<NDF, typename std::enable_if<NDF::kHasSampleUnchecked>::type> { static constexpr bool value = true; };
 template<class NDF> BBMCU_D f3 quick_halfway(f3 a, f3 b) { if constexpr (QuickHalfway<NDF>::value) return q_normalize(a + b); else return halfway(a, b); }
 
+template<class NDF, class = void> struct NdfHasPre { static constexpr bool value = false; };
+template<class NDF> struct NdfHasPre<NDF, typename std::enable_if<NDF::kHasPre>::type> { static constexpr bool value = true; };
+
 template<class NDF, class = void> struct NdfFusedMinBlocks { static constexpr int value = 0; };
 template<class NDF> struct NdfFusedMinBlocks<NDF, typename std::enable_if<(NDF::kFusedMinBlocks > 0)>::type> { static constexpr int value = NDF::kFusedMinBlocks; };
 
@@ -670,6 +712,25 @@ struct Microfacet
     Spec<T> r = eval_unscaled<T>(in, out, a, component);
     if(SCALED) r = r * load_spec(a);
     return r;
+  }
+  // eval with the NDF's parameter-only factors formed by the caller (NDF::pre): the same operations as eval<float>
+  static constexpr bool kHasPre = NdfHasPre<NDF>::value && std::is_same<G, GUncorrelated>::value;
+  BBMCU_D static auto precompute(const float* a) { if constexpr (kHasPre) return NDF::pre(a + OFF_NDF); else return 0; }
+  template<class PRE> BBMCU_D static Spec<float> eval_pre(f3 in, f3 out, const float* a, int component, const PRE& q)
+  {
+    if constexpr (!kHasPre) return eval<float>(in, out, a, component);
+    else
+    {
+      if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return Spec<float>(0.0f);
+      f3 h = quick_halfway<NDF>(in, out);
+      float inh = dot(in, h), outh = dot(out, h);
+      auto D = NDF::template D<float>(h, a + OFF_NDF);
+      float Gv = g_mask(in, out, h) ? NDF::G1_pre(in, h, a + OFF_NDF, q) * NDF::G1_pre(out, h, a + OFF_NDF, q) : 0.0f;   // GUncorrelated
+      auto Fv = F::template evalq<float>(a + OFF_F, 0.5f*(inh + outh));
+      Spec<float> r = divide_out(to_spec(D) * to_spec(Gv) * to_spec(Fv), in.z*out.z);
+      if(SCALED) r = r * load_spec(a);
+      return r;
+    }
   }
   // pdf(h) / (4 |out.h|)  (microfacet.h:154-174)
   BBMCU_D static float pdf(f3 in, f3 out, const float* a, int component)
