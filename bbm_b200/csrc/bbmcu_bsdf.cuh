@@ -188,6 +188,8 @@ struct BsdfSingle
   BBMCU_D static auto precompute(const BsdfDesc& b) { if constexpr (kHasPre) return M::precompute(b.attrs); else return 0; }
   template<class PRE> BBMCU_D static Spec<float> eval_pre(const BsdfDesc& b, const PRE& q, f3 in, f3 out, int component)
   { if constexpr (kHasPre) return M::eval_pre(in, out, b.attrs, component, q); else return M::template eval<float>(in, out, b.attrs, component); }
+  template<class PRE> BBMCU_D static void eval_pdf_pre(const BsdfDesc& b, const PRE& q, f3 in, f3 out, int component, Spec<float>& e, float& p)
+  { if constexpr (kHasPre && SamplePdfIsPdf<M>::value) M::eval_pdf_pre(in, out, b.attrs, component, e, p, q); }
   static constexpr int kMinBlocks = LaunchMinBlocks<M>::value, kMinBlocksFused = LaunchMinBlocksFused<M>::value;
   static constexpr bool kAggregatePdfFromSample = false;
   static constexpr bool kTables = TableFloats<M>::N > 0;

@@ -199,7 +199,10 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
   static constexpr bool kFastPath = !GEN && B::kHandFused;
   BBMCU_D bool fast_ok() const { return aligned && dir && spdf && flag && rgb && pdf; }
   BBMCU_D void group(size_t i, const BsdfDesc& bsdf) const { group_t<false>(i, bsdf); }
-  template<bool FAST> BBMCU_D void group_t(size_t i, const BsdfDesc& bsdf) const
+  template<bool FAST> BBMCU_D void group_t(size_t i, const BsdfDesc& bsdf) const { group_q<FAST, int>(i, bsdf, nullptr); }
+  // q != nullptr: the model's parameter-only factors, formed once per thread by the kernel (BsdfSingle<M>::precompute)
+  template<class PRE> BBMCU_D void group_pre(size_t i, const BsdfDesc& bsdf, const PRE& q) const { group_q<false, PRE>(i, bsdf, &q); }
+  template<bool FAST, class PRE> BBMCU_D void group_q(size_t i, const BsdfDesc& bsdf, const PRE* q) const
   {
     Lanes3 b, d, c; Lanes u, v, sp, p; int f[kVec];
     if constexpr (GEN)
@@ -224,7 +227,8 @@ template<class B, bool GEN> struct SampleEvalPdfOpT
       else if constexpr (B::kFusedSample)
       {
         B::sample_dir(bsdf, o, make_f2(u.v[k], v.v[k]), component, dd, f[k]);
-        B::eval_pdf(bsdf, dd, o, component, s, p.v[k]);
+        if constexpr (!std::is_same<PRE, int>::value) B::eval_pdf_pre(bsdf, *q, dd, o, component, s, p.v[k]);
+        else B::eval_pdf(bsdf, dd, o, component, s, p.v[k]);
         sp.v[k] = (f[k] != FLAG_NONE) ? p.v[k] : 0.0f;
       }
       else
@@ -299,6 +303,21 @@ template<class B> struct EvalGridOp
       f3 x, y;
       merl_dirs_tab(s_lin, (i + k < n) ? first + (uint32_t)(i + k) : first, x, y);
       Spec<float> s = B::eval(bsdf, x, y, component);
+      a.set(k, x); b.set(k, y); r.set(k, make_f3(s.r, s.g, s.b));
+    }
+    store4x3(rgb, i, n, ld, aligned, r);
+    if(in) store4x3(in, i, n, ld, aligned, a);
+    if(out) store4x3(out, i, n, ld, aligned, b);
+  }
+  template<class PRE> BBMCU_D void group_pre(size_t i, const BsdfDesc& bsdf, const float* s_lin, const PRE& q) const
+  {
+    Lanes3 a, b, r;
+#pragma unroll
+    for(int k=0; k < kVec; ++k)
+    {
+      f3 x, y;
+      merl_dirs_tab(s_lin, (i + k < n) ? first + (uint32_t)(i + k) : first, x, y);
+      Spec<float> s = B::eval_pre(bsdf, q, x, y, component);
       a.set(k, x); b.set(k, y); r.set(k, make_f3(s.r, s.g, s.b));
     }
     store4x3(rgb, i, n, ld, aligned, r);
@@ -386,6 +405,8 @@ template<class Op, class = void> struct OpFastPath { static constexpr bool value
 template<class Op> struct OpFastPath<Op, typename std::enable_if<Op::kFastPath>::type> { static constexpr bool value = true; };
 template<class Op, class = void> struct OpHasPre { static constexpr bool value = false; };
 template<class B> struct OpHasPre<EvalOp<B>, typename std::enable_if<B::kHasPre>::type> { static constexpr bool value = true; };
+template<class B> struct OpHasPre<EvalGridOp<B>, typename std::enable_if<B::kHasPre>::type> { static constexpr bool value = true; };
+template<class B, bool GEN> struct OpHasPre<SampleEvalPdfOpT<B, GEN>, typename std::enable_if<B::kHasPre && B::kFusedSample && !B::kHandFused>::type> { static constexpr bool value = true; };
 template<class Op, class = void> struct UsesLinTab { static constexpr bool value = false; };
 template<class Op> struct UsesLinTab<Op, typename std::enable_if<Op::kLinTab>::type> { static constexpr bool value = true; };
 
@@ -403,6 +424,12 @@ template<class Op> __global__ void __launch_bounds__(Op::kBlock, Op::kMinBlocks)
     __shared__ float s_lin[kMerlLinTabFloats];
     for(int i = threadIdx.x; i < kMerlLinTabFloats; i += blockDim.x) s_lin[i] = __ldg(op.lin_tab + i);
     __syncthreads();
+    if constexpr (OpHasPre<Op>::value)
+    {
+      const auto q = Op::BsdfT::precompute(op.bsdf);
+      for(size_t g = first; g < groups; g += stride) op.group_pre(g * kVec, op.bsdf, s_lin, q);
+    }
+    else
     for(size_t g = first; g < groups; g += stride) op.group(g * kVec, op.bsdf, s_lin);
   }
   else

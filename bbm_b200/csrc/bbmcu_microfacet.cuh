@@ -800,6 +800,25 @@ struct Microfacet
     if(SCALED) e = e * load_spec(a);
     p = q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(outh));
   }
+  // eval_pdf with the NDF's parameter-only factors formed by the caller: the general branch above, G1 through G1_pre
+  template<class PRE> BBMCU_D static void eval_pdf_pre(f3 in, f3 out, const float* a, int component, Spec<float>& e, float& p, const PRE& q)
+  {
+    if constexpr (!kHasPre) eval_pdf(in, out, a, component, e, p);
+    else
+    {
+      static_assert(!kHandFusedEvalPdf && !(HasPdfVisible<NDF>::value && QuickHalfway<NDF>::value), "eval_pdf takes its general branch for this model");
+      e = Spec<float>(0.0f); p = 0.0f;
+      if(!(component & FLAG_SPECULAR) || !((in.z > 0.0f) && (out.z > 0.0f))) return;
+      f3 h = quick_halfway<NDF>(in, out);
+      float inh = dot(in, h), outh = dot(out, h);
+      auto D = NDF::template D<float>(h, a + OFF_NDF);
+      float Gv = g_mask(in, out, h) ? NDF::G1_pre(in, h, a + OFF_NDF, q) * NDF::G1_pre(out, h, a + OFF_NDF, q) : 0.0f;   // GUncorrelated
+      auto Fv = F::template evalq<float>(a + OFF_F, 0.5f*(inh + outh));
+      e = divide_out(to_spec(D) * to_spec(Gv) * to_spec(Fv), in.z*out.z);
+      if(SCALED) e = e * load_spec(a);
+      p = q_div(NDF::pdf(out, h, a + OFF_NDF), 4.0f * fabsf(outh));
+    }
+  }
   // The whole fused element - sample, eval, pdf - of the hand-merged model without a branch: every validity test of
   // sample (microfacet.h:118-127) and eval / pdf (:74-81, :154-160) becomes a predicate that selects zeros at the end; the
   // arithmetic runs on whatever the element holds (the *_raw operations neither trap nor loop on garbage).
