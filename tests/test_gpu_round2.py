@@ -402,3 +402,33 @@ def test_compact_loss_equals_generic_tile_kernel(ctx, metric):
                 del os.environ["BBMCU_LOSS_NO_COMPACT"]
             assert np.all(np.abs(lc - lg) <= 2e-5 * np.abs(lg)) and np.all(np.abs(vc - lg) <= 2e-5 * np.abs(lg)), (metric, K)
             assert np.all(np.abs(gc - gg) <= 1e-4 * np.abs(gg) + 2e-6 * np.abs(gg).max(axis=2, keepdims=True)), (metric, K)
+
+
+# ---- parameter-only factors formed once per thread (Student-t G1) --------------------------------------------------------------
+@pytest.mark.parametrize("s", ["Ribardiere()", "RibardiereAnisotropic()", "Ribardiere([0.3, 0.5, 0.7], 0.12, 2.2, 1.6)",
+                               "RibardiereAnisotropic([0.3, 0.5, 0.7], [0.1, 0.4], 3.5, 1.4)"])
+def test_studentt_factors_per_thread_equal_factors_per_evaluation(ctx, ref, s):
+    """The eval kernel, the fused sample -> eval -> pdf pass and the fused-linearizer grid eval form the gamma-only factors of
+    the Student-t G1 (ndf/studentt.h:110-140) once per thread (NdfStudentT::pre); the Aggregate(Lambertian, M) pair kernel
+    forms them per evaluation through the same functions: all routes agree bit for bit, and with the reference to 1e-5."""
+    import bbm_b200 as bb
+    rng = np.random.default_rng(5)
+    n = (1 << 18) + 3
+    z = rng.random(n, dtype=np.float32)
+    ph = rng.random(n, dtype=np.float32) * np.float32(2 * np.pi)
+    r = np.sqrt(1 - z * z)
+    out = np.ascontiguousarray(np.stack([r * np.cos(ph), r * np.sin(ph), z]).astype(np.float32))
+    xi = np.ascontiguousarray(rng.random((2, n), dtype=np.float32))
+    b = bb.Bsdf(s)
+    agg = bb.Bsdf("Aggregate(Lambertian([0, 0, 0]), " + s + ")")          # 0 + x = x: the lobe's value through the pair kernel
+    d, sp, f, rgb, p = ctx.sample_eval_pdf(b, out, xi)
+    e = ctx.eval(b, d, out)
+    assert np.count_nonzero(e[0]) > n // 2
+    assert np.array_equal(bits(rgb), bits(e))
+    assert np.array_equal(bits(ctx.eval(agg, d, out)), bits(e))
+    assert np.array_equal(bits(ctx.pdf(b, d, out))[f != 0], bits(p)[f != 0])
+    g_rgb, g_in, g_out = ctx.eval_merl_grid(b, first=1000, n=(1 << 16) + 1, dirs=True)
+    assert np.array_equal(bits(g_rgb), bits(ctx.eval(b, np.ascontiguousarray(g_in), np.ascontiguousarray(g_out))))
+    if s.endswith("()"):       # the default configurations are the ones the large-sample scan (tests/test_gpu_scan.py) holds at 0 beyond 1e-5
+        sub = slice(0, 20000)
+        assert_parity(e.T[sub], ref.eval(s, d.T[sub].copy(), out.T[sub].copy()), 1e-5, what="Student-t eval (factors per thread) vs reference: " + s)
