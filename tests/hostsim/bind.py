@@ -79,6 +79,27 @@ class HostSim:
         self._chk(self.lib.hostsim_sample(bsdf.encode(), component, self._p(o), self._p(x), C.c_size_t(n), self._p(d), self._p(p), self._p(f)))
         return d.T.copy(), p, f
 
+    def eval_pre(self, bsdf, inn, out, component=3):
+        """eval of a single Student-t lobe with its parameter-only factors formed once (EvalOp::group_pre)"""
+        i, o = soa(inn), soa(out)
+        n = i.shape[1]
+        r = np.empty((3, n), np.float32)
+        self._chk(self.lib.hostsim_eval_pre(bsdf.encode(), component, self._p(i), self._p(o), C.c_size_t(n), self._p(r)))
+        return r.T.copy()
+
+    def sample_eval_pdf_pre(self, bsdf, out, xi, component=3):
+        """the fused pass of a single Student-t lobe with its parameter-only factors formed once: (dir, sample_pdf, flag, rgb, pdf)"""
+        o, x = soa(out), soa(xi)
+        n = o.shape[1]
+        d = np.empty((3, n), np.float32)
+        sp = np.empty(n, np.float32)
+        f = np.empty(n, np.int32)
+        rgb = np.empty((3, n), np.float32)
+        p = np.empty(n, np.float32)
+        self._chk(self.lib.hostsim_sample_eval_pdf_pre(bsdf.encode(), component, self._p(o), self._p(x), C.c_size_t(n), self._p(d), self._p(sp), self._p(f),
+                                                       self._p(rgb), self._p(p)))
+        return d.T.copy(), sp, f, rgb.T.copy(), p
+
     def merl_index(self, inn, out):
         i, o = soa(inn), soa(out)
         n = i.shape[1]

@@ -34,6 +34,31 @@ template<class Op> static void run(const Op& op_in, size_t n)
 // host-compiled tests: the "device" table of a measured model is its host table
 namespace bbmcu { const float* merl_device_table(const bbmcu_host::MerlData& m, int) { return m.rgb.data(); } }
 
+// EvalOp::group_pre and the fused pass's group_pre of a single-lobe model with parameter-only factors (Student-t), the factors
+// formed once before the loop as k_foreach4 forms them once per thread
+template<class M> static void run_eval_pre(const BsdfDesc& d, int component, const float* in, const float* out, size_t n, float* rgb)
+{
+  using B = BsdfSingle<M>;
+  static_assert(B::kHasPre, "model without parameter-only factors");
+  EvalOp<B> op; op.bsdf = d; op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; op.ld = n;
+  const auto q = B::precompute(op.bsdf);
+  for(size_t i=0; i < n; i += kVec) op.group_pre(i, op.bsdf, q);
+}
+template<class M> static void run_sep_pre(const BsdfDesc& d, int component, const float* out, const float* xi, size_t n, float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf)
+{
+  using B = BsdfSingle<M>;
+  SampleEvalPdfOp<B> op; op.bsdf = d; op.component = component; op.out = out; op.xi = xi; op.dir = dir; op.spdf = spdf; op.flag = flag; op.rgb = rgb; op.pdf = pdf;
+  op.n = n; op.aligned = false; op.ld = n;
+  const auto q = B::precompute(op.bsdf);
+  for(size_t i=0; i < n; i += kVec) op.group_pre(i, op.bsdf, q);
+}
+static BsdfDesc single_lobe_desc(const char* bsdf)
+{
+  auto parsed = bbmcu_host::parse_bsdf(bsdf);
+  BsdfDesc d = make_desc(parsed);
+  if(d.n_lobes != 1 || d.aggregate || (d.model[0] != M_Ribardiere && d.model[0] != M_RibardiereAnisotropic)) throw std::invalid_argument("hostsim: a single Student-t lobe expected");
+  return d;
+}
 extern "C" {
 const char* hostsim_last_error() { return g_err.c_str(); }
 // the EPD G1 table (bbm_b200/data/epd_g1.f32), owned by the caller
@@ -43,6 +68,23 @@ float hostsim_hp_normalization_entry(int bi, int ci, int si) { return hp_normali
 
 int hostsim_eval(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
 { GUARD( EvalOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.in = in; op.out = out; op.rgb = rgb; op.n = n; op.aligned = false; run(op, n); ) }
+
+int hostsim_eval_pre(const char* bsdf, int component, const float* in, const float* out, size_t n, float* rgb)
+{
+  GUARD(
+    BsdfDesc d = single_lobe_desc(bsdf);
+    if(d.model[0] == M_Ribardiere) run_eval_pre<ModelOf<M_Ribardiere>::type>(d, component, in, out, n, rgb);
+    else run_eval_pre<ModelOf<M_RibardiereAnisotropic>::type>(d, component, in, out, n, rgb);
+  )
+}
+int hostsim_sample_eval_pdf_pre(const char* bsdf, int component, const float* out, const float* xi, size_t n, float* dir, float* spdf, int32_t* flag, float* rgb, float* pdf)
+{
+  GUARD(
+    BsdfDesc d = single_lobe_desc(bsdf);
+    if(d.model[0] == M_Ribardiere) run_sep_pre<ModelOf<M_Ribardiere>::type>(d, component, out, xi, n, dir, spdf, flag, rgb, pdf);
+    else run_sep_pre<ModelOf<M_RibardiereAnisotropic>::type>(d, component, out, xi, n, dir, spdf, flag, rgb, pdf);
+  )
+}
 
 int hostsim_pdf(const char* bsdf, int component, const float* in, const float* out, size_t n, float* pdf)
 { GUARD( PdfOp<BsdfGeneric> op; auto parsed = bbmcu_host::parse_bsdf(bsdf); op.bsdf = make_desc(parsed); op.component = component; op.in = in; op.out = out; op.pdf = pdf; op.n = n; op.aligned = false; run(op, n); ) }

@@ -56,3 +56,28 @@ def test_all_cases_sample(hostsim, golden_models):
             # the pdf of a sharp lobe amplifies last-bit differences of the direction; the strict pdf
             # parity is test_all_cases_eval_pdf_reflectance (same directions on both sides)
             assert_parity(p, want_p, 3e-2, what=f"sample pdf {s} comp {c}")
+
+
+def test_studentt_factors_formed_once_equal_factors_per_evaluation(hostsim, golden_models):
+    """NdfStudentT::pre / G1_pre (the eval kernels form the gamma-only factors of G1 once per thread, ndf/studentt.h:110-140)
+    against the per-evaluation route (eval<float>, the run-time lobe list) bit for bit, and against the golden vectors; the
+    fused pass with the factors formed once against sample + eval + pdf of the run-time lobe list"""
+    arr, meta = golden_models
+    inn, out, xi = arr["in"], arr["out"], arr["xi"]
+    checked = 0
+    for key, rec in _cases(meta):
+        s = rec["string"]
+        if not s.startswith("Ribardiere"):
+            continue
+        for c in COMPONENTS:
+            e = hostsim.eval_pre(s, inn, out, c)
+            assert np.array_equal(e.view(np.uint32), hostsim.eval(s, inn, out, c).view(np.uint32)), (s, c)
+            assert_parity(e, arr[f"{key}_eval_c{c}"], 1e-5, what=f"eval (factors once) {s} comp {c}")
+            d, sp, f, rgb, p = hostsim.sample_eval_pdf_pre(s, out, xi, c)
+            d0, p0, f0 = hostsim.sample(s, out, xi, c)
+            assert np.array_equal(f, f0) and np.array_equal(d.view(np.uint32), d0.view(np.uint32)), (s, c)
+            assert np.array_equal(rgb.view(np.uint32), hostsim.eval(s, d, out, c).view(np.uint32)), (s, c)
+            assert np.array_equal(p.view(np.uint32), hostsim.pdf(s, d, out, c).view(np.uint32)), (s, c)
+            assert np.array_equal(sp[f != 0].view(np.uint32), p0[f != 0].view(np.uint32)), (s, c)
+        checked += 1
+    assert checked >= 2
